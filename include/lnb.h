@@ -1,0 +1,175 @@
+/*
+ * lnb.h -- C-ABI of liblnb.so: the B200 (sm_100a) forward path that sits under the
+ * Go API of adalkiran/llama-nuts-and-bolts.
+ *
+ * The reference has no FFI or plugin interface (it is pure Go, CPU only); the
+ * drop-in boundary is its exported Go API, and this header is what a cgo shim in
+ * src/ml and src/model binds (INTEGRATION.md shows the stubs).  Every entry point
+ * cites the reference symbol (file:line, relative to the reference repo) whose
+ * arithmetic it replaces.  Plain C types only; no pointer is retained past a call
+ * (cgo pointer rule) -- weights are copied to HBM at upload.
+ *
+ * Error convention (reference: `(nil, error)` from every op, e.g.
+ * src/ml/operations_impl.go:428-446): every function returns 0 on success or a
+ * negative LNB_E* code; lnb_last_error() returns the thread-local message.
+ *
+ * Numeric contract: bf16 storage, f32 accumulate,
+ * f32 -> bf16 by TRUNCATION after every op (src/dtype/bfloat16.go:59-61), f64
+ * softmax without max-subtraction, table SiLU, RoPE through f64 intermediates.
+ * The accumulation ORDER of the long sums is selectable:
+ *   LNB_ACC_STRICT  k = 0,1,2,... sequentially per output, exactly the reference's
+ *                   order -> results are bit-identical to the Go CPU path.
+ *   LNB_ACC_FAST    each output's sum is split into interleaved partial sums that
+ *                   are combined in a fixed documented order -> same
+ *                   values up to fp32 summation order; faster (HBM-bound).
+ */
+#ifndef LNB_H
+#define LNB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNB_VERSION 100
+
+enum {
+  LNB_OK = 0,
+  LNB_EINVAL = -1,   /* bad argument / shape / dtype (reference: fmt.Errorf shape errors) */
+  LNB_ECUDA = -2,    /* CUDA runtime failure (sticky on the handle) */
+  LNB_ENCCL = -3,    /* NCCL failure */
+  LNB_ESTATE = -4,   /* call order (e.g. forward before finalize) */
+  LNB_ENOMEM = -5
+};
+
+enum { LNB_ACC_STRICT = 0, LNB_ACC_FAST = 1 };
+
+const char* lnb_last_error(void);
+int lnb_version(void);
+/* number of visible CUDA devices, or a negative error */
+int lnb_device_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Model-level API -- replaces model.NewLlamaTransformer / LlamaTransformer.Forward
+ * ---------------------------------------------------------------------------------- */
+
+/* mirrors model.ModelArgs (src/model/modelargs.go:10-64) plus the derived FFN width
+ * (src/model/llamatransformer.go:569-577) */
+typedef struct {
+  int32_t dim, n_layers, n_heads, n_kv_heads, head_dim, ffn_dim, vocab_size, max_seq_len;
+  float norm_eps;
+  double rope_theta;
+  int32_t use_scaled_rope;
+} lnb_model_args;
+
+typedef struct lnb_model lnb_model;     /* device-resident weights + tables of ONE rank */
+typedef struct lnb_session lnb_session; /* model.InferenceContext: KV cache + activations */
+
+/* Creates the device-side model of tensor-parallel rank `tp_rank` of `tp_size` on CUDA
+ * device `device`.  tp_size==1: nccl_unique_id may be NULL.  tp_size>1: one process per
+ * rank; nccl_unique_id is the 128-byte id from lnb_nccl_unique_id() of rank 0, sent by
+ * the host (torch.distributed / Go) to every rank.
+ * Replaces: model.NewLlamaTransformer (src/model/llamatransformer.go:64-113). */
+int lnb_model_create(const lnb_model_args* args, int device, int tp_rank, int tp_size,
+                     const void* nccl_unique_id, lnb_model** out);
+int lnb_nccl_unique_id(void* out128);
+
+/* Upload one checkpoint tensor by its reference name ("layers.7.attention.wq.weight",
+ * "tok_embeddings.weight", ...; names and shapes: llamatransformer.go:84-105,191,202,
+ * 273-282,580-586; getTensor shape check: src/model/loader.go:183-197).  `host` is the
+ * FULL bf16 row-major [out,in] tensor exactly as it sits in the checkpoint mmap
+ * (src/torch/types.go:51-56); the library copies (and, for tp_size>1, slices) it into
+ * its HBM layout and keeps no reference to `host`. */
+int lnb_model_upload_tensor(lnb_model* m, const char* name, const uint16_t* host, const int64_t* shape, int ndim);
+
+/* Random-init every tensor directly in HBM with the synthetic generator of DESIGN.md
+ * (no checkpoint exists in the build environment).  Same bits as oracle's
+ * orc_synth_fill for the same seed. */
+int lnb_model_init_synthetic(lnb_model* m, uint64_t seed);
+/* host-side twin of the generator, for callers that want the same bytes in host memory */
+int lnb_synth_fill_host(uint64_t seed, const char* name, float scale, float offset, int64_t n, uint16_t* out);
+/* scale/offset used by lnb_model_init_synthetic for a tensor name */
+int lnb_synth_spec(const lnb_model_args* args, const char* name, float* scale, float* offset);
+
+/* Optional: override the tables the library builds itself at finalize.
+ * cis: [rows][head_dim/2][2] f32 == model.precomputeFreqsCis output
+ * (llamatransformer.go:694-751); silu_bf16: ml.TABLE_SILU truncated to bf16
+ * (src/ml/activations.go:11-25,38). */
+int lnb_model_set_rope_table(lnb_model* m, const float* cis, int rows);
+int lnb_model_set_silu_table(lnb_model* m, const uint16_t* silu_bf16_65536);
+/* read back the tables in use (tests compare them with the oracle's) */
+int lnb_model_get_rope_table(lnb_model* m, float* cis_out, int rows);
+int lnb_model_get_silu_table(lnb_model* m, uint16_t* out65536);
+
+/* checks all 291 tensors are present, builds tables, makes the model immutable */
+int lnb_model_finalize(lnb_model* m);
+int lnb_model_destroy(lnb_model* m); /* hook for model.Model.Free (src/model/model.go:56) */
+
+/* model.NewInferenceContext (src/model/inferencecontext.go:17-46): KV cache of seq_len rows
+ * per layer, zero-filled.  max_rows = largest S a forward call may carry (>=1).
+ * acc_mode = LNB_ACC_STRICT / LNB_ACC_FAST. */
+int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int acc_mode, lnb_session** out);
+int lnb_session_destroy(lnb_session* s);
+
+/* LlamaTransformer.Forward (src/model/llamatransformer.go:145-180) + the last-row
+ * ml.Argmax of the generate loop (src/inference/inference.go:207-216).
+ *   tokens[S] int32, start_pos as in the reference (S>1 requires start_pos==0, F11).
+ *   logits : NULL, or host [S, vocab] f32 if all_rows, host [1, vocab] (last row) otherwise
+ *   argmax_last : NULL, or receives the greedy token of the last row.
+ * One call = one H2D of tokens, the whole forward on the device, one D2H of what was asked. */
+int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int start_pos,
+                float* logits, int all_rows, int32_t* argmax_last);
+
+/* Device-resident greedy decode: runs n_steps consecutive S=1 forwards starting with
+ * `first_token` at position start_pos, feeding each argmax back on the device (no host
+ * sync inside), optionally as CUDA-graph replays.  tokens_out[n_steps]; ms_out = device
+ * time of the n_steps steps measured with CUDA events on the session stream.
+ * This is the timed region of bench.py's `value`. */
+int lnb_decode_run(lnb_session* s, int32_t first_token, int start_pos, int n_steps, int use_graph,
+                   int32_t* tokens_out, float* ms_out);
+
+/* debugging / parity probes */
+enum { LNB_BUF_RESIDUAL = 0, LNB_BUF_CACHE_K = 1, LNB_BUF_CACHE_V = 2, LNB_BUF_LOGITS = 3 };
+/* copies a device buffer of the session to host: RESIDUAL [S,dim] bf16 (after the last
+ * forward; with lnb_session_set_layer_limit, after that many layers), CACHE_K/V of `layer`
+ * [seq_len, n_kv_local, head_dim] bf16, LOGITS [rows, vocab_local] f32. */
+int lnb_session_read(lnb_session* s, int which, int layer, void* host, int64_t nbytes);
+int lnb_session_set_layer_limit(lnb_session* s, int n_layers_to_run); /* <=0: all */
+/* number of kernels launched by this session since creation (bench.py gpu_launches) */
+int64_t lnb_session_launch_count(lnb_session* s);
+int lnb_session_sync(lnb_session* s);
+
+/* ------------------------------------------------------------------------------------
+ * Op-level API -- what the src/ml shims bind.  Host pointers in and out; each call
+ * stages through HBM and runs the same kernels the model path uses.
+ * ---------------------------------------------------------------------------------- */
+
+/* ml.LinearTransformation, BF16 (src/ml/operations_impl.go:427-447,
+ * operations_lineartransform.go:37-70,145-207): x[S,K], w[N,K] -> out[S,N] */
+int lnb_op_linear_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int S, int K, int N, int acc_mode);
+/* ml.MatMul, BF16 (operations_impl.go:449-476, operations_matmul.go:24-60,136-182):
+ * a[B,M,K] x b[B,K,N] -> out[B,M,N] */
+int lnb_op_matmul_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int B, int M, int K, int N);
+/* RMSNorm.Forward (src/model/llamatransformer.go:633-660) */
+int lnb_op_rmsnorm_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int S, int D, float eps, int acc_mode);
+/* applyRotaryEmbeddings for one tensor (llamatransformer.go:753-790): x[S,H,hd] */
+int lnb_op_rope_bf16(const uint16_t* x, const float* cis, uint16_t* out, int S, int H, int hd, int start_pos);
+/* the attention core of LlamaAttention.Forward (llamatransformer.go:402-514):
+ * q[S,n_heads,hd] rotated, cache_k/v[T,n_kv,hd] -> out[S,n_heads*hd] */
+int lnb_op_attention_bf16(const uint16_t* q, const uint16_t* cache_k, const uint16_t* cache_v, uint16_t* out,
+                          int S, int T, int n_heads, int n_kv, int hd, int causal_mask, int acc_mode);
+/* ml.Silu (activations.go:27-50), ml.Add / ml.MultiplyElementwise same-shape bf16
+ * (operations_impl.go:307-335,367-395) */
+int lnb_op_silu_bf16(const uint16_t* x, uint16_t* out, int64_t n);
+int lnb_op_add_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n);
+int lnb_op_mul_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n);
+/* ml.Softmax on f32 rows (operations_impl.go:478-511), ml.Argmax (:513-548) */
+int lnb_op_softmax_f32(const float* x, float* out, int rows, int cols);
+int lnb_op_argmax_f32(const float* x, int rows, int cols, int32_t* out);
+/* ml.Fwd_Get_Rows (operations_impl.go:142-173) */
+int lnb_op_get_rows_bf16(const uint16_t* emb, const int32_t* tokens, uint16_t* out, int S, int vocab, int dim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LNB_H */

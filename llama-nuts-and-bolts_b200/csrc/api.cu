@@ -1,0 +1,1117 @@
+// api.cu -- the C-ABI of liblnb.so (include/lnb.h): model / session lifecycle, the fused
+// forward pass, the device-resident decode loop and the op-level entry points.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lnb.h"
+#include "gemv.cuh"
+#include "kernels.cuh"
+
+namespace lnb {
+void build_rope_table(int dim, int end, double theta, bool use_scaled, std::vector<float>& out);
+void build_silu_table(std::vector<uint16_t>& out);
+}  // namespace lnb
+
+using namespace lnb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(LNB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* lnb_last_error(void) { return g_err.c_str(); }
+extern "C" int lnb_version(void) { return LNB_VERSION; }
+extern "C" int lnb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(LNB_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (single-GPU use never needs the library)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSum_ = 0, ncclMax_ = 2 };
+enum { ncclUint64_ = 5, ncclFloat32_ = 7 };
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+static int nccl_load() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.h) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return fail(LNB_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                  \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name);                       \
+  if (!g_nccl.field) return fail(LNB_ENCCL, "libnccl lacks %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return 0;
+}
+#define NC(call)                                                                                \
+  do {                                                                                          \
+    int r_ = (call);                                                                            \
+    if (r_ != 0) return fail(LNB_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_));     \
+  } while (0)
+
+extern "C" int lnb_nccl_unique_id(void* out128) {
+  if (!out128) return fail(LNB_EINVAL, "out128 is NULL");
+  int rc = nccl_load();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// model
+struct LayerW {
+  uint16_t *attn_norm = nullptr, *wqkv = nullptr, *wo = nullptr, *ffn_norm = nullptr, *w13 = nullptr, *w2 = nullptr;
+  unsigned have = 0;  // bit per checkpoint tensor (9)
+};
+enum { T_ATTN_NORM = 0, T_WQ, T_WK, T_WV, T_WO, T_FFN_NORM, T_W1, T_W2, T_W3, T_EMBD, T_NORM, T_OUTPUT };
+
+struct lnb_model {
+  lnb_model_args a;
+  int device = 0, tp_rank = 0, tp_size = 1;
+  int q_dim = 0, kv_dim = 0, q_l = 0, kv_l = 0, ffn_l = 0, vocab_l = 0;
+  uint16_t *tok_embd = nullptr, *norm = nullptr, *output = nullptr;
+  bool have_embd = false, have_norm = false, have_output = false, finalized = false;
+  std::vector<LayerW> layers;
+  float* cis = nullptr;
+  int cis_rows = 0;
+  uint16_t* silu_tab = nullptr;
+  bool cis_set = false, silu_set = false;
+  ncclComm_t comm = nullptr;
+  void* staging = nullptr;
+  size_t staging_bytes = 0;
+  int sm_count = 148;
+};
+
+static int parse_name(const lnb_model* m, const char* name, int* kind, int* layer) {
+  *layer = -1;
+  if (!strcmp(name, "tok_embeddings.weight")) { *kind = T_EMBD; return 0; }
+  if (!strcmp(name, "norm.weight")) { *kind = T_NORM; return 0; }
+  if (!strcmp(name, "output.weight")) { *kind = T_OUTPUT; return 0; }
+  int l = -1;
+  char rest[96];
+  if (sscanf(name, "layers.%d.%95s", &l, rest) != 2 || l < 0 || l >= m->a.n_layers) return -1;
+  *layer = l;
+  static const char* names[9] = {"attention_norm.weight", "attention.wq.weight", "attention.wk.weight",
+                                 "attention.wv.weight",   "attention.wo.weight", "ffn_norm.weight",
+                                 "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight"};
+  for (int i = 0; i < 9; i++)
+    if (!strcmp(rest, names[i])) { *kind = i; return 0; }
+  return -1;
+}
+
+// full checkpoint shape of a tensor kind (llamatransformer.go:84-105,191,202,273-282,580-586)
+static void full_shape(const lnb_model* m, int kind, int64_t* rows, int64_t* cols) {
+  const lnb_model_args& a = m->a;
+  switch (kind) {
+    case T_ATTN_NORM: case T_FFN_NORM: case T_NORM: *rows = a.dim; *cols = 1; break;
+    case T_WQ: *rows = m->q_dim; *cols = a.dim; break;
+    case T_WK: case T_WV: *rows = m->kv_dim; *cols = a.dim; break;
+    case T_WO: *rows = a.dim; *cols = m->q_dim; break;
+    case T_W1: case T_W3: *rows = a.ffn_dim; *cols = a.dim; break;
+    case T_W2: *rows = a.dim; *cols = a.ffn_dim; break;
+    case T_EMBD: case T_OUTPUT: *rows = a.vocab_size; *cols = a.dim; break;
+  }
+}
+
+// where a checkpoint tensor lands in the HBM layout of this rank
+struct Placement {
+  uint16_t* dst;
+  int64_t row0, col0;  // window of the full tensor owned by this rank
+  int rows, cols;      // window size
+  bool panel_major;
+  int dpanel0, dpanel_stride;
+};
+static Placement placement(lnb_model* m, int kind, int layer) {
+  Placement p{};
+  const lnb_model_args& a = m->a;
+  const int r = m->tp_rank;
+  p.dpanel0 = 0;
+  p.dpanel_stride = 1;
+  p.panel_major = true;
+  LayerW* L = layer >= 0 ? &m->layers[layer] : nullptr;
+  switch (kind) {
+    case T_ATTN_NORM: p.dst = L->attn_norm; p.rows = 1; p.cols = a.dim; p.panel_major = false; break;
+    case T_FFN_NORM: p.dst = L->ffn_norm; p.rows = 1; p.cols = a.dim; p.panel_major = false; break;
+    case T_NORM: p.dst = m->norm; p.rows = 1; p.cols = a.dim; p.panel_major = false; break;
+    case T_EMBD: p.dst = m->tok_embd; p.rows = a.vocab_size; p.cols = a.dim; p.panel_major = false; break;
+    case T_WQ: p.dst = L->wqkv; p.row0 = (int64_t)r * m->q_l; p.rows = m->q_l; p.cols = a.dim; break;
+    case T_WK: p.dst = L->wqkv; p.row0 = (int64_t)r * m->kv_l; p.rows = m->kv_l; p.cols = a.dim; p.dpanel0 = m->q_l / 16; break;
+    case T_WV: p.dst = L->wqkv; p.row0 = (int64_t)r * m->kv_l; p.rows = m->kv_l; p.cols = a.dim; p.dpanel0 = (m->q_l + m->kv_l) / 16; break;
+    case T_WO: p.dst = L->wo; p.col0 = (int64_t)r * m->q_l; p.rows = a.dim; p.cols = m->q_l; break;
+    case T_W1: p.dst = L->w13; p.row0 = (int64_t)r * m->ffn_l; p.rows = m->ffn_l; p.cols = a.dim; p.dpanel0 = 0; p.dpanel_stride = 2; break;
+    case T_W3: p.dst = L->w13; p.row0 = (int64_t)r * m->ffn_l; p.rows = m->ffn_l; p.cols = a.dim; p.dpanel0 = 1; p.dpanel_stride = 2; break;
+    case T_W2: p.dst = L->w2; p.col0 = (int64_t)r * m->ffn_l; p.rows = a.dim; p.cols = m->ffn_l; break;
+    case T_OUTPUT: p.dst = m->output; p.row0 = (int64_t)r * m->vocab_l; p.rows = m->vocab_l; p.cols = a.dim; break;
+  }
+  return p;
+}
+
+static void mark_present(lnb_model* m, int kind, int layer) {
+  if (kind == T_EMBD) m->have_embd = true;
+  else if (kind == T_NORM) m->have_norm = true;
+  else if (kind == T_OUTPUT) m->have_output = true;
+  else m->layers[layer].have |= 1u << kind;
+}
+
+extern "C" int lnb_model_create(const lnb_model_args* args, int device, int tp_rank, int tp_size,
+                                const void* nccl_unique_id, lnb_model** out) {
+  if (!args || !out) return fail(LNB_EINVAL, "args/out is NULL");
+  const lnb_model_args& a = *args;
+  if (a.dim <= 0 || a.n_layers <= 0 || a.n_heads <= 0 || a.n_kv_heads <= 0 || a.head_dim <= 0 || a.ffn_dim <= 0 ||
+      a.vocab_size <= 0 || a.max_seq_len <= 0)
+    return fail(LNB_EINVAL, "non-positive model dimension");
+  if (a.n_heads % a.n_kv_heads) return fail(LNB_EINVAL, "n_heads %d not a multiple of n_kv_heads %d", a.n_heads, a.n_kv_heads);
+  if (a.head_dim % 2) return fail(LNB_EINVAL, "head_dim must be even");
+  if (tp_size < 1 || tp_rank < 0 || tp_rank >= tp_size) return fail(LNB_EINVAL, "bad tp rank %d / size %d", tp_rank, tp_size);
+  if (a.n_kv_heads % tp_size || a.ffn_dim % tp_size || a.vocab_size % tp_size)
+    return fail(LNB_EINVAL, "tp_size %d must divide n_kv_heads, ffn_dim and vocab_size", tp_size);
+  const int q_dim = a.n_heads * a.head_dim, kv_dim = a.n_kv_heads * a.head_dim;
+  const int q_l = q_dim / tp_size, kv_l = kv_dim / tp_size, ffn_l = a.ffn_dim / tp_size, vocab_l = a.vocab_size / tp_size;
+  if (a.dim % 32 || q_l % 32 || kv_l % 32 || ffn_l % 16 || vocab_l % 16)
+    return fail(LNB_EINVAL, "dimension not tileable: dim %d q_l %d kv_l %d ffn_l %d vocab_l %d (need multiples of 32/32/32/16/16)",
+                a.dim, q_l, kv_l, ffn_l, vocab_l);
+  if (tp_size > 1 && !nccl_unique_id) return fail(LNB_EINVAL, "tp_size>1 needs an nccl unique id");
+  CU(cudaSetDevice(device));
+  lnb_model* m = new lnb_model();
+  m->a = a;
+  m->device = device;
+  m->tp_rank = tp_rank;
+  m->tp_size = tp_size;
+  m->q_dim = q_dim; m->kv_dim = kv_dim; m->q_l = q_l; m->kv_l = kv_l; m->ffn_l = ffn_l; m->vocab_l = vocab_l;
+  cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+  m->layers.resize(a.n_layers);
+  auto alloc16 = [&](uint16_t** p, size_t elems) -> cudaError_t { return cudaMalloc((void**)p, elems * 2); };
+  cudaError_t e = cudaSuccess;
+  e = alloc16(&m->tok_embd, (size_t)a.vocab_size * a.dim);
+  if (e == cudaSuccess) e = alloc16(&m->norm, a.dim);
+  if (e == cudaSuccess) e = alloc16(&m->output, (size_t)vocab_l * a.dim);
+  for (int l = 0; l < a.n_layers && e == cudaSuccess; l++) {
+    LayerW& L = m->layers[l];
+    e = alloc16(&L.attn_norm, a.dim);
+    if (e == cudaSuccess) e = alloc16(&L.ffn_norm, a.dim);
+    if (e == cudaSuccess) e = alloc16(&L.wqkv, (size_t)(q_l + 2 * kv_l) * a.dim);
+    if (e == cudaSuccess) e = alloc16(&L.wo, (size_t)a.dim * q_l);
+    if (e == cudaSuccess) e = alloc16(&L.w13, (size_t)2 * ffn_l * a.dim);
+    if (e == cudaSuccess) e = alloc16(&L.w2, (size_t)a.dim * ffn_l);
+  }
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->silu_tab, 65536 * 2);
+  if (e != cudaSuccess) {
+    lnb_model_destroy(m);
+    return fail(LNB_ENOMEM, "cudaMalloc of model weights failed: %s", cudaGetErrorString(e));
+  }
+  if (tp_size > 1) {
+    int rc = nccl_load();
+    if (rc) { lnb_model_destroy(m); return rc; }
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, 128);
+    int r = g_nccl.CommInitRank(&m->comm, tp_size, id, tp_rank);
+    if (r != 0) { lnb_model_destroy(m); return fail(LNB_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+  }
+  *out = m;
+  return 0;
+}
+
+extern "C" int lnb_model_destroy(lnb_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  if (m->comm) g_nccl.CommDestroy(m->comm);
+  cudaFree(m->tok_embd); cudaFree(m->norm); cudaFree(m->output);
+  for (auto& L : m->layers) {
+    cudaFree(L.attn_norm); cudaFree(L.ffn_norm); cudaFree(L.wqkv); cudaFree(L.wo); cudaFree(L.w13); cudaFree(L.w2);
+  }
+  cudaFree(m->cis); cudaFree(m->silu_tab); cudaFree(m->staging);
+  delete m;
+  return 0;
+}
+
+static int ensure_staging(lnb_model* m, size_t bytes) {
+  if (m->staging_bytes >= bytes) return 0;
+  if (m->staging) cudaFree(m->staging);
+  m->staging = nullptr;
+  m->staging_bytes = 0;
+  CU(cudaMalloc(&m->staging, bytes));
+  m->staging_bytes = bytes;
+  return 0;
+}
+
+extern "C" int lnb_model_upload_tensor(lnb_model* m, const char* name, const uint16_t* host, const int64_t* shape, int ndim) {
+  if (!m || !name || !host || !shape) return fail(LNB_EINVAL, "NULL argument");
+  if (m->finalized) return fail(LNB_ESTATE, "model is finalized");
+  int kind, layer;
+  if (parse_name(m, name, &kind, &layer)) return fail(LNB_EINVAL, "unknown tensor name \"%s\"", name);
+  int64_t rows, cols;
+  full_shape(m, kind, &rows, &cols);
+  // same check as getTensor (src/model/loader.go:183-197)
+  bool ok = (cols == 1) ? (ndim == 1 && shape[0] == rows) : (ndim == 2 && shape[0] == rows && shape[1] == cols);
+  if (!ok) return fail(LNB_EINVAL, "tensor \"%s\": unexpected shape (expected [%lld%s%lld])", name, (long long)rows,
+                       cols == 1 ? "] / [" : ", ", (long long)cols);
+  CU(cudaSetDevice(m->device));
+  Placement p = placement(m, kind, layer);
+  const int64_t ld = (cols == 1) ? rows : cols;
+  if (!p.panel_major) {
+    CU(cudaMemcpy(p.dst, host, (size_t)p.rows * p.cols * 2, cudaMemcpyHostToDevice));
+  } else {
+    int rc = ensure_staging(m, (size_t)p.rows * p.cols * 2);
+    if (rc) return rc;
+    CU(cudaMemcpy2D(m->staging, (size_t)p.cols * 2, host + p.row0 * ld + p.col0, (size_t)ld * 2, (size_t)p.cols * 2,
+                    p.rows, cudaMemcpyHostToDevice));
+    retile_kernel<<<m->sm_count * 8, 256>>>((const uint16_t*)m->staging, p.cols, 0, 0, p.rows, p.cols, p.dst, p.dpanel0,
+                                            p.dpanel_stride);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+  }
+  mark_present(m, kind, layer);
+  return 0;
+}
+
+// ---- synthetic checkpoint ------------------------------------------------------------------
+static uint64_t fnv1a64(const char* s) {
+  uint64_t h = 0xcbf29ce484222325ULL;
+  for (; *s; s++) { h ^= (uint8_t)*s; h *= 0x100000001b3ULL; }
+  return h;
+}
+static void synth_spec_kind(const lnb_model_args& a, int kind, float* scale, float* offset) {
+  const float s3 = 1.7320508075688772f;
+  *offset = 0.f;
+  switch (kind) {
+    case T_EMBD: *scale = 1.0f; break;
+    case T_ATTN_NORM: case T_FFN_NORM: case T_NORM: *scale = 0.1f; *offset = 1.0f; break;
+    case T_W2: *scale = s3 / sqrtf((float)a.ffn_dim); break;
+    case T_OUTPUT: *scale = 0.25f * s3 / sqrtf((float)a.dim); break;
+    case T_WO: *scale = s3 / sqrtf((float)(a.n_heads * a.head_dim)); break;
+    default: *scale = s3 / sqrtf((float)a.dim); break;
+  }
+}
+extern "C" int lnb_synth_spec(const lnb_model_args* args, const char* name, float* scale, float* offset) {
+  if (!args || !name || !scale || !offset) return fail(LNB_EINVAL, "NULL argument");
+  lnb_model tmp;
+  tmp.a = *args;
+  int kind, layer;
+  if (parse_name(&tmp, name, &kind, &layer)) return fail(LNB_EINVAL, "unknown tensor name \"%s\"", name);
+  synth_spec_kind(*args, kind, scale, offset);
+  return 0;
+}
+extern "C" int lnb_synth_fill_host(uint64_t seed, const char* name, float scale, float offset, int64_t n, uint16_t* out) {
+  if (!name || !out) return fail(LNB_EINVAL, "NULL argument");
+  const uint64_t s = seed ^ fnv1a64(name);
+  for (int64_t i = 0; i < n; i++) {
+    uint64_t z = s + ((uint64_t)i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    volatile float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+    volatile float w = 2.0f * u - 1.0f;
+    volatile float v = w * scale;
+    volatile float v2 = v + offset;
+    float vv = v2;
+    uint32_t b;
+    memcpy(&b, &vv, 4);
+    out[i] = (uint16_t)(b >> 16);
+  }
+  return 0;
+}
+
+extern "C" int lnb_model_init_synthetic(lnb_model* m, uint64_t seed) {
+  if (!m) return fail(LNB_EINVAL, "model is NULL");
+  if (m->finalized) return fail(LNB_ESTATE, "model is finalized");
+  CU(cudaSetDevice(m->device));
+  static const char* lnames[9] = {"attention_norm.weight", "attention.wq.weight", "attention.wk.weight",
+                                  "attention.wv.weight",   "attention.wo.weight", "ffn_norm.weight",
+                                  "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight"};
+  auto fill = [&](const char* name, int kind, int layer) -> int {
+    int64_t rows, cols;
+    full_shape(m, kind, &rows, &cols);
+    const int64_t ld = (cols == 1) ? rows : cols;
+    Placement p = placement(m, kind, layer);
+    float scale, offset;
+    synth_spec_kind(m->a, kind, &scale, &offset);
+    synth_fill_kernel<<<m->sm_count * 8, 256>>>(seed ^ fnv1a64(name), scale, offset, ld, p.row0, p.col0, p.rows, p.cols,
+                                                p.dst, p.panel_major ? 1 : 0, p.dpanel0, p.dpanel_stride);
+    CU(cudaGetLastError());
+    mark_present(m, kind, layer);
+    return 0;
+  };
+  int rc;
+  if ((rc = fill("tok_embeddings.weight", T_EMBD, -1))) return rc;
+  if ((rc = fill("norm.weight", T_NORM, -1))) return rc;
+  if ((rc = fill("output.weight", T_OUTPUT, -1))) return rc;
+  char name[128];
+  for (int l = 0; l < m->a.n_layers; l++)
+    for (int k = 0; k < 9; k++) {
+      snprintf(name, sizeof(name), "layers.%d.%s", l, lnames[k]);
+      if ((rc = fill(name, k, l))) return rc;
+    }
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
+// ---- tables ---------------------------------------------------------------------------------
+extern "C" int lnb_model_set_rope_table(lnb_model* m, const float* cis, int rows) {
+  if (!m || !cis || rows <= 0) return fail(LNB_EINVAL, "bad argument");
+  if (m->finalized) return fail(LNB_ESTATE, "model is finalized");
+  CU(cudaSetDevice(m->device));
+  cudaFree(m->cis);
+  m->cis = nullptr;
+  const size_t bytes = (size_t)rows * (m->a.head_dim / 2) * 2 * sizeof(float);
+  CU(cudaMalloc((void**)&m->cis, bytes));
+  CU(cudaMemcpy(m->cis, cis, bytes, cudaMemcpyHostToDevice));
+  m->cis_rows = rows;
+  m->cis_set = true;
+  return 0;
+}
+extern "C" int lnb_model_set_silu_table(lnb_model* m, const uint16_t* tab) {
+  if (!m || !tab) return fail(LNB_EINVAL, "bad argument");
+  if (m->finalized) return fail(LNB_ESTATE, "model is finalized");
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpy(m->silu_tab, tab, 65536 * 2, cudaMemcpyHostToDevice));
+  m->silu_set = true;
+  return 0;
+}
+extern "C" int lnb_model_get_rope_table(lnb_model* m, float* out, int rows) {
+  if (!m || !out || !m->cis || rows > m->cis_rows) return fail(LNB_EINVAL, "bad argument / table not built");
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpy(out, m->cis, (size_t)rows * (m->a.head_dim / 2) * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int lnb_model_get_silu_table(lnb_model* m, uint16_t* out) {
+  if (!m || !out) return fail(LNB_EINVAL, "bad argument");
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpy(out, m->silu_tab, 65536 * 2, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int lnb_model_finalize(lnb_model* m) {
+  if (!m) return fail(LNB_EINVAL, "model is NULL");
+  if (m->finalized) return 0;
+  if (!m->have_embd) return fail(LNB_ESTATE, "missing tensor tok_embeddings.weight");
+  if (!m->have_norm) return fail(LNB_ESTATE, "missing tensor norm.weight");
+  if (!m->have_output) return fail(LNB_ESTATE, "missing tensor output.weight");
+  for (int l = 0; l < m->a.n_layers; l++)
+    if (m->layers[l].have != 0x1ffu) return fail(LNB_ESTATE, "layer %d: missing tensors (mask 0x%x)", l, m->layers[l].have);
+  CU(cudaSetDevice(m->device));
+  if (!m->cis_set) {
+    std::vector<float> cis;
+    const int rows = m->a.max_seq_len * 2;  // llamatransformer.go:109
+    build_rope_table(m->a.head_dim, rows, m->a.rope_theta, m->a.use_scaled_rope != 0, cis);
+    int rc = lnb_model_set_rope_table(m, cis.data(), rows);
+    if (rc) return rc;
+  }
+  if (!m->silu_set) {
+    std::vector<uint16_t> tab;
+    build_silu_table(tab);
+    int rc = lnb_model_set_silu_table(m, tab.data());
+    if (rc) return rc;
+  }
+  if (m->staging) { cudaFree(m->staging); m->staging = nullptr; m->staging_bytes = 0; }
+  CU(cudaDeviceSynchronize());
+  m->finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMV dispatch
+using CfgS1 = GemvCfg<32, 1, 1, 256, 4>;
+using CfgS2 = GemvCfg<32, 1, 2, 256, 4>;
+using CfgS8 = GemvCfg<32, 1, 8, 256, 4>;
+using CfgF1 = GemvCfg<32, 8, 1, 256, 4>;
+using CfgF2 = GemvCfg<32, 8, 2, 256, 4>;
+using CfgF8 = GemvCfg<32, 8, 8, 256, 4>;
+
+static const size_t kMaxSmem = 227 * 1024;
+
+struct Launcher {
+  cudaStream_t stream;
+  bool pdl;
+  int64_t* counter;
+};
+
+template <class Cfg, int PRO, int EPI>
+static int launch_gemv_cfg(const Launcher& L, const GemvParams& p) {
+  auto kern = gemv_kernel<Cfg, PRO, EPI>;
+  const size_t smem = Cfg::smem_bytes(p.K);
+  static bool attr_set = false;  // per instantiation
+  static size_t attr_smem = 0;
+  if (!attr_set || smem > attr_smem) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    attr_set = true;
+    attr_smem = kMaxSmem;
+  }
+  cudaLaunchConfig_t cfg{};
+  const int n_panels = p.N / 16;
+  cfg.gridDim = dim3((n_panels + Cfg::kP - 1) / Cfg::kP);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = L.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = L.pdl ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, kern, p));
+  if (L.counter) (*L.counter)++;
+  return 0;
+}
+
+// picks the row-block size: largest MB in {8,2,1} that is useful for M and whose smem fits
+template <int PRO, int EPI>
+static int launch_gemv(const Launcher& L, int mode, GemvParams p, int M_total) {
+  if (p.N % 16 || p.K % 8) return fail(LNB_EINVAL, "gemv: N %d must be a multiple of 16 and K %d of 8", p.N, p.K);
+  if ((EPI == EPI_QKV_ROPE || EPI == EPI_SWIGLU) && p.N % 32) return fail(LNB_EINVAL, "gemv: N %d must be a multiple of 32", p.N);
+  const bool strict = (mode == LNB_ACC_STRICT);
+  p.strict_norm = strict ? 1 : 0;
+  int mb = 1;
+  if (M_total >= 3 && (strict ? CfgS8::smem_bytes(p.K) : CfgF8::smem_bytes(p.K)) <= kMaxSmem) mb = 8;
+  else if (M_total >= 2 && (strict ? CfgS2::smem_bytes(p.K) : CfgF2::smem_bytes(p.K)) <= kMaxSmem) mb = 2;
+  if ((strict ? CfgS1::smem_bytes(p.K) : CfgF1::smem_bytes(p.K)) > kMaxSmem)
+    return fail(LNB_EINVAL, "gemv: K %d too large for shared memory", p.K);
+  const uint16_t* x0 = p.x;
+  uint16_t* ob0 = p.out_bf16;
+  float* of0 = p.out_f32;
+  const uint16_t* res0 = p.res;
+  const int moff0 = p.m_off;
+  LnbDevState* st0 = p.st;
+  const int arg_row = p.argmax_row;
+  for (int m0 = 0; m0 < M_total; m0 += mb) {
+    p.M = (M_total - m0 < mb) ? (M_total - m0) : mb;
+    p.x = x0 + (size_t)m0 * p.ldx;
+    p.out_bf16 = ob0 ? ob0 + (size_t)m0 * p.ldo : nullptr;
+    p.out_f32 = of0 ? of0 + (size_t)m0 * p.ldo : nullptr;
+    p.res = res0 ? res0 + (size_t)m0 * p.ldo : nullptr;
+    p.m_off = moff0 + m0;
+    if (EPI == EPI_LOGITS) {
+      const bool covers = st0 && arg_row >= m0 && arg_row < m0 + p.M;
+      p.st = covers ? st0 : nullptr;
+      p.argmax_row = covers ? arg_row - m0 : -1;
+    }
+    int rc;
+    if (strict) {
+      if (mb == 8) rc = launch_gemv_cfg<CfgS8, PRO, EPI>(L, p);
+      else if (mb == 2) rc = launch_gemv_cfg<CfgS2, PRO, EPI>(L, p);
+      else rc = launch_gemv_cfg<CfgS1, PRO, EPI>(L, p);
+    } else {
+      if (mb == 8) rc = launch_gemv_cfg<CfgF8, PRO, EPI>(L, p);
+      else if (mb == 2) rc = launch_gemv_cfg<CfgF2, PRO, EPI>(L, p);
+      else rc = launch_gemv_cfg<CfgF1, PRO, EPI>(L, p);
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+template <typename... Args>
+static int launch_simple(const Launcher& L, void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = L.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = L.pdl ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, kern, args...));
+  if (L.counter) (*L.counter)++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// session
+__global__ void set_state_kernel(LnbDevState* st, int pos, int n_rows, int next_token, int reset_step) {
+  st->pos = pos;
+  st->n_rows = n_rows;
+  st->amax_key = LNB_ARGMAX_EMPTY;
+  st->done_ctr = 0;
+  if (next_token >= 0) st->next_token = next_token;
+  if (reset_step) st->step = 0;
+}
+// tensor-parallel tail of the LM head: decode the reduced key, advance the decode state
+__global__ void publish_kernel(LnbDevState* st, int advance, int32_t* tok_out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const unsigned long long key = st->amax_key;
+  const int32_t tok = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+  st->next_token = tok;
+  st->amax_key = LNB_ARGMAX_EMPTY;
+  st->done_ctr = 0;
+  if (advance) {
+    if (tok_out) tok_out[st->step] = tok;
+    st->step += 1;
+    st->pos += 1;
+  }
+}
+
+struct lnb_session {
+  lnb_model* m = nullptr;
+  int seq_len = 0, max_rows = 1, mode = LNB_ACC_FAST;
+  cudaStream_t stream = nullptr;
+  uint16_t *x = nullptr, *h1 = nullptr, *q = nullptr, *o = nullptr, *mbuf = nullptr;
+  float* part = nullptr;
+  float* logits = nullptr;
+  size_t logits_rows = 0;
+  float* logits_full = nullptr;  // tp>1: gathered [rows, vocab]
+  std::vector<uint16_t*> ck, cv;
+  int32_t* d_tokens = nullptr;
+  LnbDevState* st = nullptr;
+  int32_t* d_tok_out = nullptr;
+  int32_t* h_pin = nullptr;
+  int layer_limit = 0;
+  int64_t launches = 0;
+  cudaGraphExec_t graph = nullptr;
+  bool graph_tried = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;
+  int last_rows = 0;
+};
+
+extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int acc_mode, lnb_session** out) {
+  if (!m || !out) return fail(LNB_EINVAL, "NULL argument");
+  if (!m->finalized) return fail(LNB_ESTATE, "model is not finalized");
+  if (seq_len <= 0 || max_rows <= 0) return fail(LNB_EINVAL, "seq_len and max_rows must be positive");
+  if (seq_len > m->cis_rows) return fail(LNB_EINVAL, "seq_len %d exceeds the RoPE table (%d rows)", seq_len, m->cis_rows);
+  if (acc_mode != LNB_ACC_STRICT && acc_mode != LNB_ACC_FAST) return fail(LNB_EINVAL, "bad acc_mode %d", acc_mode);
+  if ((size_t)seq_len * 12 + (size_t)m->a.head_dim * 4 > 200 * 1024)
+    return fail(LNB_EINVAL, "seq_len %d too long for the decode attention kernel", seq_len);
+  CU(cudaSetDevice(m->device));
+  lnb_session* s = new lnb_session();
+  s->m = m;
+  s->seq_len = seq_len;
+  s->max_rows = max_rows;
+  s->mode = acc_mode;
+  const lnb_model_args& a = m->a;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  auto al = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  al((void**)&s->x, (size_t)max_rows * a.dim * 2);
+  al((void**)&s->h1, (size_t)max_rows * a.dim * 2);
+  al((void**)&s->q, (size_t)max_rows * m->q_l * 2);
+  al((void**)&s->o, (size_t)max_rows * m->q_l * 2);
+  al((void**)&s->mbuf, (size_t)max_rows * m->ffn_l * 2);
+  al((void**)&s->part, (size_t)max_rows * a.dim * 4);
+  al((void**)&s->d_tokens, (size_t)max_rows * 4);
+  al((void**)&s->st, sizeof(LnbDevState));
+  al((void**)&s->d_tok_out, (size_t)seq_len * 4);
+  s->ck.assign(a.n_layers, nullptr);
+  s->cv.assign(a.n_layers, nullptr);
+  const size_t cbytes = (size_t)seq_len * m->kv_l * 2;
+  for (int l = 0; l < a.n_layers; l++) {
+    al((void**)&s->ck[l], cbytes);
+    al((void**)&s->cv[l], cbytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->ck[l], 0, cbytes, s->stream);  // ml.Zeros, inferencecontext.go:31-43
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->cv[l], 0, cbytes, s->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->st, 0, sizeof(LnbDevState), s->stream);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_pin, (size_t)(max_rows + seq_len + 16) * 4);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) {
+    lnb_session_destroy(s);
+    return fail(LNB_ENOMEM, "session allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return 0;
+}
+
+extern "C" int lnb_session_destroy(lnb_session* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->m->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->graph) cudaGraphExecDestroy(s->graph);
+  cudaFree(s->x); cudaFree(s->h1); cudaFree(s->q); cudaFree(s->o); cudaFree(s->mbuf); cudaFree(s->part);
+  cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out);
+  for (auto p : s->ck) cudaFree(p);
+  for (auto p : s->cv) cudaFree(p);
+  if (s->h_pin) cudaFreeHost(s->h_pin);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return 0;
+}
+
+extern "C" int lnb_session_set_layer_limit(lnb_session* s, int n) {
+  if (!s) return fail(LNB_EINVAL, "session is NULL");
+  s->layer_limit = n;
+  return 0;
+}
+extern "C" int64_t lnb_session_launch_count(lnb_session* s) { return s ? s->launches : 0; }
+extern "C" int lnb_session_sync(lnb_session* s) {
+  if (!s) return fail(LNB_EINVAL, "session is NULL");
+  CU(cudaSetDevice(s->m->device));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+static int ensure_logits(lnb_session* s, size_t rows) {
+  if (s->logits_rows >= rows) return 0;
+  cudaFree(s->logits);
+  cudaFree(s->logits_full);
+  s->logits = s->logits_full = nullptr;
+  s->logits_rows = 0;
+  CU(cudaMalloc((void**)&s->logits, rows * (size_t)s->m->vocab_l * 4));
+  if (s->m->tp_size > 1) CU(cudaMalloc((void**)&s->logits_full, rows * (size_t)s->m->a.vocab_size * 4));
+  s->logits_rows = rows;
+  return 0;
+}
+
+// Enqueue one LlamaTransformer.Forward (llamatransformer.go:145-180) for S rows on the
+// session stream.  from_state_token: row 0's token is st->next_token (device-driven decode).
+// logits_rows: 0 = none stored, 1 = last row, S = all rows.  advance: decode-loop bookkeeping.
+static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int logits_rows, bool advance, bool pdl) {
+  lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  Launcher L{s->stream, pdl, &s->launches};
+  const int mode = s->mode;
+  const int32_t* pos_ptr = &s->st->pos;
+  int rc;
+  rc = launch_simple(L, gather_rows_kernel, dim3(S), dim3(256), 0, (const uint16_t*)m->tok_embd,
+                     (const int32_t*)(from_state_token ? nullptr : s->d_tokens), (const LnbDevState*)s->st, s->x, a.dim);
+  if (rc) return rc;
+  const int n_layers = (s->layer_limit > 0 && s->layer_limit < a.n_layers) ? s->layer_limit : a.n_layers;
+  const float scale = [&] {  // dtype.BFloat16fromFloat32(float32(math.Sqrt(float64(HeadDim)))) :464
+    float f = (float)sqrt((double)a.head_dim);
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u &= 0xffff0000u;
+    memcpy(&f, &u, 4);
+    return f;
+  }();
+  const size_t sdpa_smem = (size_t)s->seq_len * 12 + (size_t)a.head_dim * 4;
+  for (int l = 0; l < n_layers; l++) {
+    LayerW& W = m->layers[l];
+    {  // attn_norm -> wq|wk|wv -> RoPE -> KV append            (:222, :297-403)
+      GemvParams p{};
+      p.W = W.wqkv; p.N = m->q_l + 2 * m->kv_l; p.K = a.dim;
+      p.x = s->x; p.ldx = a.dim; p.norm_w = W.attn_norm; p.eps = a.norm_eps;
+      p.out_bf16 = s->q; p.ldo = m->q_l;
+      p.q_dim = m->q_l; p.kv_dim = m->kv_l; p.head_dim = a.head_dim;
+      p.cache_k = s->ck[l]; p.cache_v = s->cv[l]; p.cis = m->cis; p.pos_ptr = pos_ptr;
+      if ((rc = launch_gemv<PRO_RMSNORM, EPI_QKV_ROPE>(L, mode, p, S))) return rc;
+    }
+    rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
+                       (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
+                       s->o, m->q_l, pos_ptr, 0, S, S > 1 ? 1 : 0, mode == LNB_ACC_STRICT ? 1 : 0, scale);
+    if (rc) return rc;
+    {  // wo + residual                                             (:522, :232)
+      GemvParams p{};
+      p.W = W.wo; p.N = a.dim; p.K = m->q_l; p.x = s->o; p.ldx = m->q_l; p.ldo = a.dim;
+      if (m->tp_size == 1) {
+        p.out_bf16 = s->h1; p.res = s->x;
+        if ((rc = launch_gemv<PRO_PLAIN, EPI_RESID>(L, mode, p, S))) return rc;
+      } else {
+        p.out_f32 = s->part;
+        if ((rc = launch_gemv<PRO_PLAIN, EPI_F32RAW>(L, mode, p, S))) return rc;
+        NC(g_nccl.AllReduce(s->part, s->part, (size_t)S * a.dim, ncclFloat32_, ncclSum_, m->comm, s->stream));
+        if ((rc = launch_simple(L, resid_from_f32_kernel, dim3(std::min(148, (S * a.dim + 255) / 256)), dim3(256), 0,
+                                (const float*)s->part, (const uint16_t*)s->x, s->h1, (int64_t)S * a.dim)))
+          return rc;
+      }
+    }
+    {  // ffn_norm -> w1|w3 -> SiLU * up                             (:237, :601-614)
+      GemvParams p{};
+      p.W = W.w13; p.N = 2 * m->ffn_l; p.K = a.dim; p.x = s->h1; p.ldx = a.dim; p.norm_w = W.ffn_norm; p.eps = a.norm_eps;
+      p.out_bf16 = s->mbuf; p.ldo = m->ffn_l; p.silu_tab = m->silu_tab;
+      if ((rc = launch_gemv<PRO_RMSNORM, EPI_SWIGLU>(L, mode, p, S))) return rc;
+    }
+    {  // w2 + residual                                             (:619, :248)
+      GemvParams p{};
+      p.W = W.w2; p.N = a.dim; p.K = m->ffn_l; p.x = s->mbuf; p.ldx = m->ffn_l; p.ldo = a.dim;
+      if (m->tp_size == 1) {
+        p.out_bf16 = s->x; p.res = s->h1;
+        if ((rc = launch_gemv<PRO_PLAIN, EPI_RESID>(L, mode, p, S))) return rc;
+      } else {
+        p.out_f32 = s->part;
+        if ((rc = launch_gemv<PRO_PLAIN, EPI_F32RAW>(L, mode, p, S))) return rc;
+        NC(g_nccl.AllReduce(s->part, s->part, (size_t)S * a.dim, ncclFloat32_, ncclSum_, m->comm, s->stream));
+        if ((rc = launch_simple(L, resid_from_f32_kernel, dim3(std::min(148, (S * a.dim + 255) / 256)), dim3(256), 0,
+                                (const float*)s->part, (const uint16_t*)s->h1, s->x, (int64_t)S * a.dim)))
+          return rc;
+      }
+    }
+  }
+  {  // output_norm -> output -> f32 logits (+ greedy argmax of the last row)   (:166-175; inference.go:207-216)
+    const int rows = (logits_rows > 1) ? S : 1;  // rows of the head actually computed
+    const int row0 = S - rows;
+    GemvParams p{};
+    p.W = m->output; p.N = m->vocab_l; p.K = a.dim;
+    p.x = s->x + (size_t)row0 * a.dim; p.ldx = a.dim; p.norm_w = m->norm; p.eps = a.norm_eps;
+    p.out_f32 = logits_rows > 0 ? s->logits : nullptr; p.ldo = m->vocab_l;
+    p.n_offset = m->tp_rank * m->vocab_l;
+    p.st = s->st; p.argmax_row = rows - 1; p.m_off = 0;
+    p.publish = (m->tp_size == 1) ? 1 : 0;
+    p.advance = advance ? 1 : 0; p.tok_out = s->d_tok_out;
+    if ((rc = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(L, mode, p, rows))) return rc;
+    if (m->tp_size > 1) {
+      NC(g_nccl.AllReduce(&s->st->amax_key, &s->st->amax_key, 1, ncclUint64_, ncclMax_, m->comm, s->stream));
+      if ((rc = launch_simple(L, publish_kernel, dim3(1), dim3(1), 0, s->st, advance ? 1 : 0, s->d_tok_out))) return rc;
+      if (logits_rows > 0)
+        for (int r = 0; r < rows; r++)
+          NC(g_nccl.AllGather(s->logits + (size_t)r * m->vocab_l, s->logits_full + (size_t)r * a.vocab_size, m->vocab_l,
+                              ncclFloat32_, m->comm, s->stream));
+    }
+  }
+  s->last_rows = S;
+  return 0;
+}
+
+extern "C" int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int start_pos, float* logits, int all_rows,
+                           int32_t* argmax_last) {
+  if (!s || !tokens) return fail(LNB_EINVAL, "NULL argument");
+  if (S <= 0) return fail(LNB_EINVAL, "empty token array");  // llamatransformer.go:146-148
+  if (S > s->max_rows) return fail(LNB_EINVAL, "S %d exceeds the session's max_rows %d", S, s->max_rows);
+  if (start_pos < 0 || start_pos + S > s->seq_len)
+    return fail(LNB_EINVAL, "positions [%d, %d) exceed SequenceLength %d", start_pos, start_pos + S, s->seq_len);
+  if (S > 1 && start_pos != 0)
+    return fail(LNB_EINVAL, "S>1 requires startPos 0 (the reference's [S,S] mask does not broadcast to [S,T])");
+  for (int i = 0; i < S; i++)
+    if (tokens[i] < 0 || tokens[i] >= s->m->a.vocab_size) return fail(LNB_EINVAL, "token id %d out of range", tokens[i]);
+  std::lock_guard<std::mutex> lk(s->mu);
+  lnb_model* m = s->m;
+  CU(cudaSetDevice(m->device));
+  const int lrows = logits ? (all_rows ? S : 1) : 0;
+  if (lrows) {
+    int rc = ensure_logits(s, (size_t)(all_rows ? s->max_rows : 1));
+    if (rc) return rc;
+  }
+  memcpy(s->h_pin, tokens, (size_t)S * 4);
+  CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)S * 4, cudaMemcpyHostToDevice, s->stream));
+  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, S, -1, 0);
+  s->launches++;
+  int rc = enqueue_forward(s, S, false, lrows, false, true);
+  if (rc) return rc;
+  if (lrows) {
+    const float* src = (m->tp_size > 1) ? s->logits_full : s->logits;
+    CU(cudaMemcpyAsync(logits, src, (size_t)lrows * m->a.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
+  }
+  int32_t* tokpin = s->h_pin + s->max_rows;
+  if (argmax_last) CU(cudaMemcpyAsync(tokpin, &s->st->next_token, 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  if (argmax_last) *argmax_last = *tokpin;
+  return 0;
+}
+
+extern "C" int lnb_decode_run(lnb_session* s, int32_t first_token, int start_pos, int n_steps, int use_graph,
+                              int32_t* tokens_out, float* ms_out) {
+  if (!s) return fail(LNB_EINVAL, "session is NULL");
+  if (n_steps <= 0 || start_pos < 0 || start_pos + n_steps > s->seq_len)
+    return fail(LNB_EINVAL, "positions [%d, %d) exceed SequenceLength %d", start_pos, start_pos + n_steps, s->seq_len);
+  if (first_token < 0 || first_token >= s->m->a.vocab_size) return fail(LNB_EINVAL, "token id %d out of range", first_token);
+  std::lock_guard<std::mutex> lk(s->mu);
+  CU(cudaSetDevice(s->m->device));
+  if (use_graph && !s->graph && !s->graph_tried) {
+    s->graph_tried = true;
+    cudaGraph_t g = nullptr;
+    const int64_t saved = s->launches;
+    cudaError_t e = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    if (e == cudaSuccess) {
+      rc = enqueue_forward(s, 1, true, 0, true, true);
+      e = cudaStreamEndCapture(s->stream, &g);
+    }
+    if (e == cudaSuccess && rc == 0 && g) {
+      e = cudaGraphInstantiate(&s->graph, g, 0);
+      if (e != cudaSuccess) s->graph = nullptr;
+    }
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    s->launches = saved;
+  }
+  const bool graph = use_graph && s->graph;
+  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, 1, first_token, 1);
+  CU(cudaEventRecord(s->ev0, s->stream));
+  const int64_t per_step_before = s->launches;
+  for (int i = 0; i < n_steps; i++) {
+    if (graph) {
+      CU(cudaGraphLaunch(s->graph, s->stream));
+    } else {
+      int rc = enqueue_forward(s, 1, true, 0, true, true);
+      if (rc) return rc;
+    }
+  }
+  if (graph) {
+    // count what the graph replays launch: one forward's worth per step
+    static thread_local int64_t per_step = 0;
+    if (!per_step) {
+      const lnb_model_args& a = s->m->a;
+      per_step = 2 + (int64_t)a.n_layers * (s->m->tp_size == 1 ? 5 : 7) + (s->m->tp_size == 1 ? 0 : 1);
+    }
+    s->launches = per_step_before + per_step * n_steps;
+  }
+  CU(cudaEventRecord(s->ev1, s->stream));
+  CU(cudaMemcpyAsync(s->h_pin + s->max_rows + 8, s->d_tok_out, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  if (ms_out) *ms_out = ms;
+  if (tokens_out) memcpy(tokens_out, s->h_pin + s->max_rows + 8, (size_t)n_steps * 4);
+  return graph ? 1 : 0;
+}
+
+extern "C" int lnb_session_read(lnb_session* s, int which, int layer, void* host, int64_t nbytes) {
+  if (!s || !host) return fail(LNB_EINVAL, "NULL argument");
+  lnb_model* m = s->m;
+  CU(cudaSetDevice(m->device));
+  const void* src = nullptr;
+  int64_t avail = 0;
+  switch (which) {
+    case LNB_BUF_RESIDUAL: src = s->x; avail = (int64_t)s->max_rows * m->a.dim * 2; break;
+    case LNB_BUF_CACHE_K:
+    case LNB_BUF_CACHE_V:
+      if (layer < 0 || layer >= m->a.n_layers) return fail(LNB_EINVAL, "bad layer %d", layer);
+      src = which == LNB_BUF_CACHE_K ? s->ck[layer] : s->cv[layer];
+      avail = (int64_t)s->seq_len * m->kv_l * 2;
+      break;
+    case LNB_BUF_LOGITS: src = s->logits; avail = (int64_t)s->logits_rows * m->vocab_l * 4; break;
+    default: return fail(LNB_EINVAL, "bad buffer id %d", which);
+  }
+  if (!src || nbytes > avail) return fail(LNB_EINVAL, "buffer %d holds %lld bytes, %lld requested", which, (long long)avail, (long long)nbytes);
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaMemcpy(host, src, (size_t)nbytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// op-level API: host pointers in / out, staged through HBM, same kernels as the model path
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+#define OPBUF(buf, bytes)                                                                     \
+  DevBuf buf;                                                                                 \
+  { cudaError_t e_ = buf.alloc(bytes); if (e_ != cudaSuccess) return fail(LNB_ENOMEM, "cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e_)); }
+#define H2D(buf, host, bytes) CU(cudaMemcpy(buf.p, host, bytes, cudaMemcpyHostToDevice))
+#define D2H(host, buf, bytes) CU(cudaMemcpy(host, buf.p, bytes, cudaMemcpyDeviceToHost))
+static int op_finish() {
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+static int grid_for(int64_t n) { return (int)std::min<int64_t>(148 * 8, (n + 255) / 256); }
+
+extern "C" int lnb_op_linear_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int S, int K, int N, int acc_mode) {
+  if (!x || !w || !out) return fail(LNB_EINVAL, "NULL argument");
+  if (S <= 0 || K <= 0 || N <= 0) return fail(LNB_EINVAL, "non-positive shape");
+  if (acc_mode != LNB_ACC_STRICT && acc_mode != LNB_ACC_FAST) return fail(LNB_EINVAL, "bad acc_mode %d", acc_mode);
+  const size_t xb = (size_t)S * K * 2, wb = (size_t)N * K * 2, ob = (size_t)S * N * 2;
+  OPBUF(dx, xb); OPBUF(dw, wb); OPBUF(dout, ob);
+  H2D(dx, x, xb); H2D(dw, w, wb);
+  const bool tileable = (N % 16 == 0) && (K % 8 == 0) && (CfgF1::smem_bytes(K) <= kMaxSmem);
+  if (!tileable) {
+    // shapes outside the panel layout (e.g. the reference's 2x3 . 4x3^T test): reference order, one thread per output
+    linear_naive_kernel<<<(int)(((int64_t)S * N + 255) / 256), 256>>>(dx.as<uint16_t>(), dw.as<uint16_t>(), dout.as<uint16_t>(), S, K, N);
+  } else {
+    OPBUF(dwp, wb);
+    retile_kernel<<<grid_for((int64_t)N * K / 8), 256>>>(dw.as<uint16_t>(), K, 0, 0, N, K, dwp.as<uint16_t>(), 0, 1);
+    GemvParams p{};
+    p.W = dwp.as<uint16_t>(); p.N = N; p.K = K; p.x = dx.as<uint16_t>(); p.ldx = K; p.out_bf16 = dout.as<uint16_t>(); p.ldo = N;
+    Launcher L{nullptr, false, nullptr};
+    int rc = launch_gemv<PRO_PLAIN, EPI_BF16>(L, acc_mode, p, S);
+    if (rc) return rc;
+    rc = op_finish();
+    if (rc) return rc;
+    D2H(out, dout, ob);
+    return 0;
+  }
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, ob);
+  return 0;
+}
+
+extern "C" int lnb_op_matmul_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int B, int M, int K, int N) {
+  if (!a || !b || !out) return fail(LNB_EINVAL, "NULL argument");
+  if (B <= 0 || M <= 0 || K <= 0 || N <= 0) return fail(LNB_EINVAL, "non-positive shape");
+  const size_t ab = (size_t)B * M * K * 2, bb = (size_t)B * K * N * 2, ob = (size_t)B * M * N * 2;
+  OPBUF(da, ab); OPBUF(db, bb); OPBUF(dout, ob);
+  H2D(da, a, ab); H2D(db, b, bb);
+  matmul_naive_kernel<<<(int)(((int64_t)B * M * N + 255) / 256), 256>>>(da.as<uint16_t>(), db.as<uint16_t>(), dout.as<uint16_t>(), B, M, K, N);
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, ob);
+  return 0;
+}
+
+extern "C" int lnb_op_rmsnorm_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int S, int D, float eps, int acc_mode) {
+  if (!x || !w || !out) return fail(LNB_EINVAL, "NULL argument");
+  if (S <= 0 || D <= 0) return fail(LNB_EINVAL, "non-positive shape");
+  const size_t xb = (size_t)S * D * 2;
+  OPBUF(dx, xb); OPBUF(dw, (size_t)D * 2); OPBUF(dout, xb);
+  H2D(dx, x, xb); H2D(dw, w, (size_t)D * 2);
+  rmsnorm_kernel<<<S, 256>>>(dx.as<uint16_t>(), dw.as<uint16_t>(), dout.as<uint16_t>(), D, eps, acc_mode == LNB_ACC_STRICT ? 1 : 0);
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, xb);
+  return 0;
+}
+
+extern "C" int lnb_op_rope_bf16(const uint16_t* x, const float* cis, uint16_t* out, int S, int H, int hd, int start_pos) {
+  if (!x || !cis || !out) return fail(LNB_EINVAL, "NULL argument");
+  if (S <= 0 || H <= 0 || hd <= 0 || (hd & 1) || start_pos < 0) return fail(LNB_EINVAL, "bad shape");
+  const size_t xb = (size_t)S * H * hd * 2, cb = (size_t)(start_pos + S) * (hd / 2) * 2 * 4;
+  OPBUF(dx, xb); OPBUF(dc, cb); OPBUF(dout, xb);
+  H2D(dx, x, xb); H2D(dc, cis, cb);
+  rope_kernel<<<grid_for((int64_t)S * H * hd / 2), 256>>>(dx.as<uint16_t>(), dc.as<float>(), dout.as<uint16_t>(), S, H, hd, start_pos);
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, xb);
+  return 0;
+}
+
+extern "C" int lnb_op_attention_bf16(const uint16_t* q, const uint16_t* cache_k, const uint16_t* cache_v, uint16_t* out,
+                                     int S, int T, int n_heads, int n_kv, int hd, int causal_mask, int acc_mode) {
+  if (!q || !cache_k || !cache_v || !out) return fail(LNB_EINVAL, "NULL argument");
+  if (S <= 0 || T < S || n_heads <= 0 || n_kv <= 0 || n_heads % n_kv || hd <= 0 || hd % 8) return fail(LNB_EINVAL, "bad shape");
+  if (causal_mask && T != S) return fail(LNB_EINVAL, "causal mask needs T == S (reference mask is [S,S])");
+  const size_t smem = (size_t)T * 12 + (size_t)hd * 4;
+  if (smem > 200 * 1024) return fail(LNB_EINVAL, "T %d too long", T);
+  const size_t qb = (size_t)S * n_heads * hd * 2, cb = (size_t)T * n_kv * hd * 2;
+  OPBUF(dq, qb); OPBUF(dk, cb); OPBUF(dv, cb); OPBUF(dout, qb);
+  H2D(dq, q, qb); H2D(dk, cache_k, cb); H2D(dv, cache_v, cb);
+  CU(cudaFuncSetAttribute(sdpa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  float f = (float)sqrt((double)hd);
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u &= 0xffff0000u;
+  memcpy(&f, &u, 4);
+  sdpa_kernel<<<dim3(n_heads, S), 128, smem>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(), dv.as<uint16_t>(), n_kv * hd,
+                                                n_heads / n_kv, hd, dout.as<uint16_t>(), n_heads * hd, nullptr, T - S, S,
+                                                causal_mask ? 1 : 0, acc_mode == LNB_ACC_STRICT ? 1 : 0, f);
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, qb);
+  return 0;
+}
+
+static int silu_table_device(uint16_t** out) {
+  static uint16_t* tab = nullptr;  // per process, device 0 of the calling thread's current device
+  static int tab_dev = -1;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (!tab || tab_dev != dev) {
+    std::vector<uint16_t> h;
+    build_silu_table(h);
+    CU(cudaMalloc((void**)&tab, 65536 * 2));
+    CU(cudaMemcpy(tab, h.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    tab_dev = dev;
+  }
+  *out = tab;
+  return 0;
+}
+
+extern "C" int lnb_op_silu_bf16(const uint16_t* x, uint16_t* out, int64_t n) {
+  if (!x || !out || n < 0) return fail(LNB_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  uint16_t* tab;
+  int rc = silu_table_device(&tab);
+  if (rc) return rc;
+  OPBUF(dx, (size_t)n * 2); OPBUF(dout, (size_t)n * 2);
+  H2D(dx, x, (size_t)n * 2);
+  silu_kernel<<<grid_for(n), 256>>>(dx.as<uint16_t>(), tab, dout.as<uint16_t>(), n);
+  rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, (size_t)n * 2);
+  return 0;
+}
+
+static int binary_op(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n, bool is_add) {
+  if (!a || !b || !out || n < 0) return fail(LNB_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  OPBUF(da, (size_t)n * 2); OPBUF(db, (size_t)n * 2); OPBUF(dout, (size_t)n * 2);
+  H2D(da, a, (size_t)n * 2); H2D(db, b, (size_t)n * 2);
+  if (is_add) add_kernel<<<grid_for(n), 256>>>(da.as<uint16_t>(), db.as<uint16_t>(), dout.as<uint16_t>(), n);
+  else mul_kernel<<<grid_for(n), 256>>>(da.as<uint16_t>(), db.as<uint16_t>(), dout.as<uint16_t>(), n);
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, (size_t)n * 2);
+  return 0;
+}
+extern "C" int lnb_op_add_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n) { return binary_op(a, b, out, n, true); }
+extern "C" int lnb_op_mul_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n) { return binary_op(a, b, out, n, false); }
+
+extern "C" int lnb_op_softmax_f32(const float* x, float* out, int rows, int cols) {
+  if (!x || !out || rows <= 0 || cols <= 0) return fail(LNB_EINVAL, "bad argument");
+  const size_t b = (size_t)rows * cols * 4;
+  OPBUF(dx, b); OPBUF(dout, b);
+  H2D(dx, x, b);
+  softmax_f32_kernel<<<rows, 256>>>(dx.as<float>(), dout.as<float>(), cols);
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, b);
+  return 0;
+}
+
+extern "C" int lnb_op_argmax_f32(const float* x, int rows, int cols, int32_t* out) {
+  if (!x || !out || rows <= 0 || cols <= 0) return fail(LNB_EINVAL, "bad argument");
+  const size_t b = (size_t)rows * cols * 4;
+  OPBUF(dx, b); OPBUF(dout, (size_t)rows * 4);
+  H2D(dx, x, b);
+  argmax_f32_kernel<<<rows, 256>>>(dx.as<float>(), cols, dout.as<int32_t>());
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, (size_t)rows * 4);
+  return 0;
+}
+
+extern "C" int lnb_op_get_rows_bf16(const uint16_t* emb, const int32_t* tokens, uint16_t* out, int S, int vocab, int dim) {
+  if (!emb || !tokens || !out || S <= 0 || vocab <= 0 || dim <= 0 || dim % 8) return fail(LNB_EINVAL, "bad argument");
+  for (int i = 0; i < S; i++)
+    if (tokens[i] < 0 || tokens[i] >= vocab) return fail(LNB_EINVAL, "token id %d out of range", tokens[i]);
+  OPBUF(de, (size_t)vocab * dim * 2); OPBUF(dt, (size_t)S * 4); OPBUF(dout, (size_t)S * dim * 2);
+  H2D(de, emb, (size_t)vocab * dim * 2); H2D(dt, tokens, (size_t)S * 4);
+  gather_rows_kernel<<<S, 256>>>(de.as<uint16_t>(), dt.as<int32_t>(), nullptr, dout.as<uint16_t>(), dim);
+  int rc = op_finish();
+  if (rc) return rc;
+  D2H(out, dout, (size_t)S * dim * 2);
+  return 0;
+}

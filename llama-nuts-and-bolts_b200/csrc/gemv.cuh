@@ -1,0 +1,371 @@
+// gemv.cuh -- the projection kernel of the decode path (M = 1..8 rows of activations
+// against a bf16 weight matrix that is streamed from HBM exactly once).
+//
+// Replaces ml.LinearTransformation (src/ml/operations_impl.go:427-447 ->
+// operations_lineartransform.go:37-70,145-207) for Wq/Wk/Wv, Wo, w1/w3, w2 and the LM
+// head, with the neighbouring elementwise ops of LlamaAttention / LlamaFeedForward /
+// RMSNorm fused into its prologue and epilogue (each fused op keeps the reference's
+// truncation point; see the EPI_* / PRO_* notes).
+//
+// HBM layout of a weight matrix W[N,K] ("panel-major", built once at upload):
+//   panel p = rows 16p..16p+15;  chunk c = k 8c..8c+7;
+//   address(p, c, r, e) = ((p * K/8 + c) * 16 + r) * 8 + e        (bf16 elements)
+// so a (panel, k-range) block is ONE contiguous byte range -> a single bulk-async copy
+// (TMA engine, cp.async.bulk + mbarrier complete_tx) per panel per stage, and inside shared
+// memory the 16 rows of a chunk are 256 contiguous bytes -> conflict-free 128-bit LDS
+// for "one thread = one output row".
+//
+// Thread roles: warp 0 = producer (one lane issues bulk copies into an NST-stage ring);
+// the other TN*KS threads are consumers.  Consumer (r, j): output row r of the CTA's TN
+// rows, k-stream j of KS.  Stream j owns the 8-element chunks g with g % KS == j and
+// accumulates them sequentially (fp32 FMA; bf16*bf16 products are exact in fp32, so FMA ==
+// mul-then-add).  KS == 1 (LNB_ACC_STRICT) is exactly the reference's k = 0,1,2,... order.
+// KS > 1 (LNB_ACC_FAST): out = ((p0 + p1) + p2) + ... + p_{KS-1}, combined in stream order.
+#pragma once
+#include "common.cuh"
+
+namespace lnb {
+
+enum { PRO_PLAIN = 0, PRO_RMSNORM = 1 };
+enum {
+  EPI_BF16 = 0,      // out_bf16[m,n] = t(acc)                                  (ToBFloat16, :205)
+  EPI_F32RAW = 1,    // out_f32[m,n] = acc     (tensor-parallel partial, reduced over ranks before truncation)
+  EPI_RESID = 2,     // out_bf16[m,n] = t(res[m,n] + t(acc))                    (ml.Add, llamatransformer.go:232,248)
+  EPI_LOGITS = 3,    // out_f32[m,n] = f32(t(acc)); greedy argmax of row n_rows-1 (llamatransformer.go:170-175; inference.go:207-216)
+  EPI_QKV_ROPE = 4,  // q -> rope -> q_out ; k -> rope -> cacheK[pos+m] ; v -> cacheV[pos+m]   (llamatransformer.go:374-403)
+  EPI_SWIGLU = 5     // panels alternate w1/w3: out[m,i] = t( silu_tab[t(g)] * t(u) )          (llamatransformer.go:601-614)
+};
+
+struct GemvParams {
+  const uint16_t* W;       // panel-major weights
+  int N, K;                // N = rows of W (multiple of 16), K multiple of 8
+  int M;                   // activation rows in this launch (<= MB)
+  // prologue
+  const uint16_t* x;       // [M, ldx] bf16 activations (PRO_PLAIN) / residual stream (PRO_RMSNORM)
+  int ldx;
+  const uint16_t* norm_w;  // [K] bf16 (PRO_RMSNORM)
+  float eps;
+  int strict_norm;         // 1: sequential sum of squares (reference order)
+  // epilogue
+  uint16_t* out_bf16;      // EPI_BF16 / EPI_RESID / EPI_SWIGLU(out [M, N/2]) / EPI_QKV_ROPE(q_out [M, q_dim])
+  float* out_f32;          // EPI_F32RAW / EPI_LOGITS (may be NULL for LOGITS)
+  int ldo;                 // row pitch of the output in elements
+  const uint16_t* res;     // EPI_RESID residual [M, ldo]
+  // EPI_QKV_ROPE
+  int q_dim, kv_dim, head_dim;
+  uint16_t* cache_k;       // [seq_len, kv_dim]
+  uint16_t* cache_v;
+  const float* cis;        // [rows][head_dim/2][2]
+  // EPI_SWIGLU
+  const uint16_t* silu_tab;
+  // EPI_LOGITS
+  int n_offset;            // global index of row 0 (vocab shard offset)
+  LnbDevState* st;         // device state: pos, argmax key, next token (NULL: no argmax in this launch)
+  int argmax_row;          // activation row of this launch whose greedy argmax is wanted (-1: none)
+  int publish;             // 1: the last CTA decodes the key into st->next_token (tp_size == 1)
+  int advance;             // 1: last CTA also advances st->pos and appends the token to tok_out (device-driven decode)
+  int32_t* tok_out;        // device [n_steps] (advance mode)
+  const int32_t* pos_ptr;  // == &st->pos (kept separate so op-level calls can pass a plain int buffer)
+  int m_off;               // index of activation row 0 of this launch inside the forward call (row blocking)
+};
+
+template <int TN, int KS, int MB, int KT, int NST>
+struct GemvCfg {
+  static constexpr int kTN = TN, kKS = KS, kMB = MB, kKT = KT, kNST = NST;
+  static constexpr int kP = TN / 16;                   // panels per CTA
+  static constexpr int kNCons = TN * KS;               // consumer threads
+  static constexpr int kThreads = kNCons + 32;         // + producer warp
+  static constexpr int kStageBytes = TN * KT * 2;
+  static constexpr int kChunksPerTile = KT / 8;
+  static_assert(TN % 16 == 0 && (TN == 16 || TN == 32), "TN");
+  static_assert(kNCons % 32 == 0, "consumer warps");
+  static_assert(kChunksPerTile % KS == 0, "k-tile must hold a whole number of chunk rounds");
+  static size_t smem_bytes(int K) {
+    size_t b = 1024;                                   // barriers + scalars (first 1 KB)
+    b += (size_t)NST * kStageBytes;
+    b += (size_t)MB * K * 4;                           // activations as f32
+    b += (size_t)KS * MB * TN * 4;                     // partial sums for the stream combine
+    return b;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+template <class Cfg, int PRO, int EPI>
+__global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p) {
+  constexpr int TN = Cfg::kTN, KS = Cfg::kKS, MB = Cfg::kMB, KT = Cfg::kKT, NST = Cfg::kNST;
+  constexpr int P = Cfg::kP, NCONS = Cfg::kNCons, STAGE = Cfg::kStageBytes;
+  constexpr int CPT = Cfg::kChunksPerTile;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);            // [NST]
+  uint64_t* empty_bar = full_bar + NST;                              // [NST]
+  float* s_scalar = reinterpret_cast<float*>(smem + 512);            // [MB] rms scale, + scratch
+  uint8_t* s_stage = smem + 1024;
+  float* s_x = reinterpret_cast<float*>(s_stage + (size_t)NST * STAGE);  // [MB][K]
+  float* s_part = s_x + (size_t)MB * p.K;                                // [KS][MB][TN]
+
+  const int tid = threadIdx.x;
+  const int K = p.K;
+  const int n_tiles = (K + KT - 1) / KT;
+  const int panel0 = blockIdx.x * P;
+  const int n_panels_total = p.N / 16;
+  const int my_panels = min(P, n_panels_total - panel0);
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NCONS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  // let the next kernel in the stream start its own weight prefetch as early as possible
+  pdl_launch_dependents();
+
+  if (tid < 32) {
+    // ===================== producer: weights never depend on the previous kernel ==========
+    if (tid == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.W);
+      for (int t = 0; t < n_tiles; t++) {
+        const int s = t % NST;
+        const uint32_t ph = (uint32_t)(t / NST) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int k0 = t * KT;
+        const int kt = min(KT, K - k0);
+        const uint32_t bytes_per_panel = (uint32_t)kt * 32u;  // kt/8 chunks * 256 B
+        mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)my_panels);
+        for (int pp = 0; pp < my_panels; pp++) {
+          const uint8_t* src = wbase + ((size_t)(panel0 + pp) * (size_t)K + (size_t)k0) * 32u;
+          bulk_g2s(s_stage + (size_t)s * STAGE + (size_t)pp * (KT * 32), src, bytes_per_panel, &full_bar[s], pol);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers ========================================================
+  const int c = tid - 32;
+  const int r = c % TN;        // row within the CTA tile
+  const int j = c / TN;        // k-stream
+  const int pp = r / 16, rr = r % 16;
+  const int cw = c / 32;       // consumer warp index
+  const int lane = tid & 31;
+
+  pdl_wait();  // activations come from the previous kernel
+
+  // ---- prologue: activations -> f32 in shared memory -----------------------------------
+  if (PRO == PRO_PLAIN) {
+    for (int m = 0; m < MB; m++)
+      for (int k = c * 2; k < K; k += NCONS * 2) {
+        float2 v = make_float2(0.f, 0.f);
+        if (m < p.M) {
+          uint32_t w = *reinterpret_cast<const uint32_t*>(p.x + (size_t)m * p.ldx + k);
+          v.x = bf_lo(w);
+          v.y = bf_hi(w);
+        }
+        *reinterpret_cast<float2*>(s_x + (size_t)m * K + k) = v;
+      }
+  } else {
+    // RMSNorm.Forward (llamatransformer.go:633-660): Pow(x,2) -> f32, sequential f32 Mean,
+    // +eps, f32(1/sqrt(f64)), t(x*r), t(.*w)
+    for (int m = 0; m < MB; m++)
+      for (int k = c * 2; k < K; k += NCONS * 2) {
+        float2 v = make_float2(0.f, 0.f);
+        if (m < p.M) {
+          uint32_t w = *reinterpret_cast<const uint32_t*>(p.x + (size_t)m * p.ldx + k);
+          v.x = bf_lo(w);
+          v.y = bf_hi(w);
+        }
+        *reinterpret_cast<float2*>(s_x + (size_t)m * K + k) = v;
+      }
+    named_bar_sync(1, NCONS);
+    if (p.strict_norm) {
+      // reference order: one sequential chain per row; rows are spread over threads
+      if (c < MB) {
+        float sum = 0.f;
+        const float* xr = s_x + (size_t)c * K;
+        for (int k = 0; k < K; k++) sum = __fmaf_rn(xr[k], xr[k], sum);  // x*x exact (16-bit mantissa)
+        float me = __fadd_rn(__fdiv_rn(sum, (float)K), p.eps);
+        s_scalar[c] = (float)(1.0 / sqrt((double)me));
+      }
+    } else {
+      // FAST: NCONS interleaved partial sums (element i -> partial i % NCONS), butterfly within
+      // each warp, then sequentially over warps.
+      for (int m = 0; m < MB; m++) {
+        float sum = 0.f;
+        const float* xr = s_x + (size_t)m * K;
+        for (int k = c; k < K; k += NCONS) sum = __fmaf_rn(xr[k], xr[k], sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+        if (lane == 0) s_part[m * (NCONS / 32) + cw] = sum;
+      }
+      named_bar_sync(1, NCONS);
+      if (c < MB) {
+        float sum = 0.f;
+        for (int w = 0; w < NCONS / 32; w++) sum = __fadd_rn(sum, s_part[c * (NCONS / 32) + w]);
+        float me = __fadd_rn(__fdiv_rn(sum, (float)K), p.eps);
+        s_scalar[c] = (float)(1.0 / sqrt((double)me));
+      }
+    }
+    named_bar_sync(1, NCONS);
+    for (int m = 0; m < MB; m++) {
+      const float rs = s_scalar[m];
+      for (int k = c; k < K; k += NCONS) {
+        float n1 = trunc_bf(__fmul_rn(s_x[(size_t)m * K + k], rs));
+        s_x[(size_t)m * K + k] = trunc_bf(__fmul_rn(n1, bf2f(p.norm_w[k])));
+      }
+    }
+  }
+  named_bar_sync(1, NCONS);
+
+  // ---- main loop ------------------------------------------------------------------------
+  float acc[MB];
+#pragma unroll
+  for (int m = 0; m < MB; m++) acc[m] = 0.f;
+
+  for (int t = 0; t < n_tiles; t++) {
+    const int s = t % NST;
+    const uint32_t ph = (uint32_t)(t / NST) & 1u;
+    mbar_wait(&full_bar[s], ph);
+    const int k0 = t * KT;
+    const int nchunks = min(KT, K - k0) / 8;
+    const uint8_t* tile = s_stage + (size_t)s * STAGE + (size_t)pp * (KT * 32) + rr * 16;
+#pragma unroll 4
+    for (int ch = j; ch < nchunks; ch += KS) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(tile + ch * 256);
+      const float w0 = bf_lo(wv.x), w1 = bf_hi(wv.x), w2 = bf_lo(wv.y), w3 = bf_hi(wv.y);
+      const float w4 = bf_lo(wv.z), w5 = bf_hi(wv.z), w6 = bf_lo(wv.w), w7 = bf_hi(wv.w);
+      const float* xk = s_x + k0 + ch * 8;
+#pragma unroll
+      for (int m = 0; m < MB; m++) {
+        const float4 xa = *reinterpret_cast<const float4*>(xk + (size_t)m * K);
+        const float4 xb = *reinterpret_cast<const float4*>(xk + (size_t)m * K + 4);
+        float a = acc[m];
+        a = __fmaf_rn(xa.x, w0, a);
+        a = __fmaf_rn(xa.y, w1, a);
+        a = __fmaf_rn(xa.z, w2, a);
+        a = __fmaf_rn(xa.w, w3, a);
+        a = __fmaf_rn(xb.x, w4, a);
+        a = __fmaf_rn(xb.y, w5, a);
+        a = __fmaf_rn(xb.z, w6, a);
+        a = __fmaf_rn(xb.w, w7, a);
+        acc[m] = a;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // ---- combine the KS streams in stream order --------------------------------------------
+  if (KS > 1) {
+#pragma unroll
+    for (int m = 0; m < MB; m++) s_part[((size_t)j * MB + m) * TN + r] = acc[m];
+    named_bar_sync(1, NCONS);
+  }
+  // after the combine, thread e < TN*MB owns output (row e % TN, activation row e / TN)
+  constexpr int NOUT = TN * MB;
+  static_assert(NOUT % 32 == 0, "epilogue shuffles need whole warps");
+  for (int e = c; e < NOUT; e += NCONS) {
+    const int er = e % TN, em = e / TN;
+    float v;
+    if (KS > 1) {
+      v = s_part[(size_t)em * TN + er];
+      for (int jj = 1; jj < KS; jj++) v = __fadd_rn(v, s_part[((size_t)jj * MB + em) * TN + er]);
+    } else {
+      v = 0.f;
+#pragma unroll
+      for (int m = 0; m < MB; m++)
+        if (m == em) v = acc[m];
+    }
+    const int n = (panel0 + er / 16) * 16 + (er % 16);  // global row of W
+    const bool valid = (em < p.M) && (er / 16 < my_panels);
+
+    if (EPI == EPI_BF16) {
+      if (valid) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(v);
+    } else if (EPI == EPI_F32RAW) {
+      if (valid) p.out_f32[(size_t)em * p.ldo + n] = v;
+    } else if (EPI == EPI_RESID) {
+      if (valid) {
+        float a = trunc_bf(v);
+        float rsd = bf2f(p.res[(size_t)em * p.ldo + n]);
+        p.out_bf16[(size_t)em * p.ldo + n] = f2bf(__fadd_rn(rsd, a));
+      }
+    } else if (EPI == EPI_LOGITS) {
+      float lv = trunc_bf(v);
+      if (valid && p.out_f32) p.out_f32[(size_t)em * p.ldo + n] = lv;
+      unsigned long long key = LNB_ARGMAX_EMPTY;
+      if (valid && em == p.argmax_row && lv > -3.402823466e+38f) key = argmax_key(lv, (uint32_t)(n + p.n_offset));
+      if (p.st) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other > key ? other : key;
+        }
+        if (lane == 0 && key != LNB_ARGMAX_EMPTY) atomicMax(&p.st->amax_key, key);
+      }
+    } else if (EPI == EPI_QKV_ROPE) {
+      // rows [0,q_dim) = q, [q_dim, q_dim+kv_dim) = k, rest = v.  RoPE pairs (2i,2i+1) are
+      // adjacent rows == adjacent lanes.  Go evaluates complex64*complex64 through float64
+      // (operations_impl.go:414-417), products are exact in f64.
+      const float mine = trunc_bf(v);                                     // t(linear)  (:306-344)
+      const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+      if (valid) {
+        const int pos = *p.pos_ptr + p.m_off + em;
+        if (n < p.q_dim + p.kv_dim) {
+          const int nn = (n < p.q_dim) ? n : n - p.q_dim;
+          const int i = (nn % p.head_dim) >> 1;
+          const float2 fc = *reinterpret_cast<const float2*>(p.cis + ((size_t)pos * (p.head_dim / 2) + i) * 2);
+          const double cc = (double)fc.x, dd = (double)fc.y;
+          float o;
+          if ((n & 1) == 0) {
+            const double a = (double)mine, b = (double)other;
+            o = (float)(a * cc - b * dd);
+          } else {
+            const double a = (double)other, b = (double)mine;
+            o = (float)(a * dd + b * cc);
+          }
+          if (n < p.q_dim) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(o);
+          else p.cache_k[(size_t)pos * p.kv_dim + nn] = f2bf(o);           // SetSlice :402
+        } else {
+          p.cache_v[(size_t)pos * p.kv_dim + (n - p.q_dim - p.kv_dim)] = f2bf(mine);  // :403
+        }
+      }
+    } else if (EPI == EPI_SWIGLU) {
+      // TN == 32: rows 0..15 of the tile are w1 (gate) rows, 16..31 the same rows of w3 (up)
+      const float mine = trunc_bf(v);
+      const float up = __shfl_down_sync(0xffffffffu, mine, 16);
+      if (valid && er < 16) {
+        const uint16_t sg = p.silu_tab[f2bf(mine)];                       // t(TABLE_SILU[bits]) activations.go:38
+        const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
+        p.out_bf16[(size_t)em * p.ldo + (size_t)blockIdx.x * 16 + er] = f2bf(mm);
+      }
+    }
+  }
+
+  if (EPI == EPI_LOGITS) {
+    // last CTA done: publish the greedy token and advance the device-side decode state
+    if (p.st && p.publish) {
+      __threadfence();
+      named_bar_sync(1, NCONS);
+      if (c == 0) {
+        const unsigned int done = atomicAdd(&p.st->done_ctr, 1u);
+        if (done == gridDim.x - 1) {
+          __threadfence();
+          const unsigned long long key = atomicExch(&p.st->amax_key, LNB_ARGMAX_EMPTY);
+          const int32_t tok = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+          p.st->next_token = tok;
+          p.st->done_ctr = 0;
+          if (p.advance) {
+            if (p.tok_out) p.tok_out[p.st->step] = tok;
+            p.st->step += 1;
+            p.st->pos += 1;
+          }
+          __threadfence();
+        }
+      }
+    }
+  }
+}
+
+}  // namespace lnb

@@ -1,0 +1,334 @@
+// kernels.cuh -- the non-GEMV kernels of the forward path plus generic-shape kernels that
+// back the op-level C-ABI.  All of them call pdl_wait() first so that they can sit in a
+// programmatic-dependent-launch chain.
+#pragma once
+#include "common.cuh"
+
+namespace lnb {
+
+// ------------------------------------------------------------------------------------------
+// Upload-time layout change: row-major W[rows x ld] (a [row0.., col0..] window of it) ->
+// panel-major (see gemv.cuh).  dst panel index of source panel q is
+// dpanel0 + q * dpanel_stride (w1/w3 are interleaved panel-wise for the fused SwiGLU).
+// One thread moves one 16-byte chunk (8 bf16).
+__global__ void retile_kernel(const uint16_t* __restrict__ src, int64_t ld, int64_t row0, int64_t col0, int rows,
+                              int K, uint16_t* __restrict__ dst, int dpanel0, int dpanel_stride) {
+  const int64_t chunks_per_row = K / 8;
+  const int64_t total = (int64_t)rows * chunks_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / chunks_per_row, ch = i % chunks_per_row;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (row0 + row) * ld + col0 + ch * 8);
+    const int64_t q = row / 16, rr = row % 16;
+    const int64_t dp = dpanel0 + q * dpanel_stride;
+    *reinterpret_cast<uint4*>(dst + ((dp * chunks_per_row + ch) * 16 + rr) * 8) = v;
+  }
+}
+
+// inverse (debug / tests): panel-major -> row-major
+__global__ void untile_kernel(const uint16_t* __restrict__ src, int rows, int K, uint16_t* __restrict__ dst,
+                              int spanel0, int spanel_stride) {
+  const int64_t chunks_per_row = K / 8;
+  const int64_t total = (int64_t)rows * chunks_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / chunks_per_row, ch = i % chunks_per_row;
+    const int64_t q = row / 16, rr = row % 16;
+    const int64_t sp = spanel0 + q * spanel_stride;
+    *reinterpret_cast<uint4*>(dst + row * K + ch * 8) =
+        *reinterpret_cast<const uint4*>(src + ((sp * chunks_per_row + ch) * 16 + rr) * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic checkpoint generator (DESIGN.md "Synthetic weights"): element i of the FULL
+// row-major tensor `name` is t((2u-1)*scale + offset), u = top 24 bits of
+// splitmix64(seed ^ fnv1a(name), i).  Writes either row-major (panel_major=0) or panel-major.
+LNB_DEVINL uint64_t splitmix64_at(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+LNB_DEVINL uint16_t synth_value(uint64_t seed, uint64_t i, float scale, float offset) {
+  const uint64_t z = splitmix64_at(seed, i);
+  const float u = __fmul_rn((float)(z >> 40), 1.0f / 16777216.0f);
+  const float w = __fadd_rn(__fmul_rn(2.0f, u), -1.0f);
+  const float v = __fadd_rn(__fmul_rn(w, scale), offset);
+  return f2bf(v);
+}
+__global__ void synth_fill_kernel(uint64_t seed, float scale, float offset, int64_t ld, int64_t row0, int64_t col0,
+                                  int rows, int K, uint16_t* __restrict__ dst, int panel_major, int dpanel0,
+                                  int dpanel_stride) {
+  const int64_t total = (int64_t)rows * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / K, col = i % K;
+    const uint16_t v = synth_value(seed, (uint64_t)((row0 + row) * ld + col0 + col), scale, offset);
+    if (panel_major) {
+      const int64_t q = row / 16, rr = row % 16, ch = col / 8, e = col % 8;
+      const int64_t dp = dpanel0 + q * dpanel_stride;
+      dst[((dp * (K / 8) + ch) * 16 + rr) * 8 + e] = v;
+    } else {
+      dst[i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ml.Fwd_Get_Rows (src/ml/operations_impl.go:142-173): x[s,:] = emb[tok[s],:].
+// tok_src: tokens of this call, or NULL -> use st->next_token (device-driven decode, S == 1).
+__global__ void gather_rows_kernel(const uint16_t* __restrict__ emb, const int32_t* __restrict__ tok_src,
+                                   const LnbDevState* st, uint16_t* __restrict__ x, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int s = blockIdx.x;
+  const int32_t tok = tok_src ? tok_src[s] : st->next_token;
+  const uint4* src = reinterpret_cast<const uint4*>(emb + (size_t)tok * dim);
+  uint4* dst = reinterpret_cast<uint4*>(x + (size_t)s * dim);
+  for (int i = threadIdx.x; i < dim / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention core of LlamaAttention.Forward (src/model/llamatransformer.go:402-514) for one
+// (query row, head) per CTA, reading K/V in place from the cache (attentionRepeatKV :529-559
+// becomes kv_head = head / n_rep; the four Transposes :435-449 become index arithmetic).
+//   sc_t = t( t(sum_seq_d q_d * k_td) / t(sqrt(hd)) )            MatMul :459, DivToScalar :464
+//   (+ mask: entries t > s are -inf -> e = 0, p = 0: skipped; kept entries add 0)   :471
+//   e_t = exp_f64(sc_t);  Z = sum_seq_t e_t (f64);  p_t = t(f32(e_t / Z))          Softmax :484-495
+//   o_d = t( sum_seq_t p_t * v_td )                                                 MatMul :504
+// All sums are in the reference's sequential order in both accumulation modes except Z,
+// which LNB_ACC_FAST reduces as a tree in f64.
+// grid = (n_heads, S); block = 128; dyn smem = T*(8+4) + hd*4 bytes.
+__global__ void __launch_bounds__(128) sdpa_kernel(const uint16_t* __restrict__ q, int ldq,
+                                                   const uint16_t* __restrict__ cache_k,
+                                                   const uint16_t* __restrict__ cache_v, int kv_dim, int n_rep,
+                                                   int hd, uint16_t* __restrict__ out, int ldo,
+                                                   const int32_t* __restrict__ pos_ptr, int pos_fixed, int S,
+                                                   int causal, int strict, float scale_bf16_as_f32) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int H = blockIdx.x, s = blockIdx.y;
+  const int pos0 = pos_ptr ? *pos_ptr : pos_fixed;
+  const int T = pos0 + S;
+  const int Teff = causal ? min(T, pos0 + s + 1) : T;
+  double* e = reinterpret_cast<double*>(sm);                  // [T]
+  float* pf = reinterpret_cast<float*>(sm + (size_t)T * 8);   // [T]
+  float* qs = pf + T;                                         // [hd]
+  __shared__ double zsh[4];
+  __shared__ double zfinal;
+  const int h = H / n_rep;
+  const int tid = threadIdx.x;
+
+  for (int d = tid; d < hd; d += blockDim.x) qs[d] = bf2f(q[(size_t)s * ldq + (size_t)H * hd + d]);
+  __syncthreads();
+
+  for (int t = tid; t < Teff; t += blockDim.x) {
+    const uint16_t* kr = cache_k + (size_t)t * kv_dim + (size_t)h * hd;
+    float acc = 0.f;
+    for (int d = 0; d < hd; d += 8) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
+      acc = __fmaf_rn(qs[d + 0], bf_lo(kv.x), acc);
+      acc = __fmaf_rn(qs[d + 1], bf_hi(kv.x), acc);
+      acc = __fmaf_rn(qs[d + 2], bf_lo(kv.y), acc);
+      acc = __fmaf_rn(qs[d + 3], bf_hi(kv.y), acc);
+      acc = __fmaf_rn(qs[d + 4], bf_lo(kv.z), acc);
+      acc = __fmaf_rn(qs[d + 5], bf_hi(kv.z), acc);
+      acc = __fmaf_rn(qs[d + 6], bf_lo(kv.w), acc);
+      acc = __fmaf_rn(qs[d + 7], bf_hi(kv.w), acc);
+    }
+    float sc = trunc_bf(acc);
+    sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
+    e[t] = exp((double)sc);
+  }
+  __syncthreads();
+
+  if (strict) {
+    if (tid == 0) {
+      double z = 0.0;
+      for (int t = 0; t < Teff; t++) z = __dadd_rn(z, e[t]);
+      zfinal = z;
+    }
+  } else {
+    double z = 0.0;
+    for (int t = tid; t < Teff; t += blockDim.x) z = __dadd_rn(z, e[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, o));
+    if ((tid & 31) == 0) zsh[tid >> 5] = z;
+    __syncthreads();
+    if (tid == 0) zfinal = __dadd_rn(__dadd_rn(__dadd_rn(zsh[0], zsh[1]), zsh[2]), zsh[3]);
+  }
+  __syncthreads();
+  const double Z = zfinal;
+  for (int t = tid; t < Teff; t += blockDim.x) pf[t] = trunc_bf((float)__ddiv_rn(e[t], Z));
+  __syncthreads();
+
+  for (int d = tid; d < hd; d += blockDim.x) {
+    const uint16_t* vc = cache_v + (size_t)h * hd + d;
+    float acc = 0.f;
+    for (int t = 0; t < Teff; t++) acc = __fmaf_rn(pf[t], bf2f(vc[(size_t)t * kv_dim]), acc);
+    out[(size_t)s * ldo + (size_t)H * hd + d] = f2bf(acc);  // Transpose(0,1)+Reshape :508-514
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor-parallel tail of Wo / w2: h[m,n] = t( res[m,n] + t(sum[m,n]) ) after the fp32
+// allreduce (ml.Add, llamatransformer.go:232,248, on the reduced partials).
+__global__ void resid_from_f32_kernel(const float* __restrict__ sum, const uint16_t* __restrict__ res,
+                                      uint16_t* __restrict__ out, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = f2bf(__fadd_rn(bf2f(res[i]), trunc_bf(sum[i])));
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic-shape kernels behind the op-level C-ABI (any S, K, N): one thread per output,
+// reference order.  Used when a shape does not meet the panel GEMV's constraints
+// (e.g. the reference's own 2x3 . 4x3^T golden case).
+__global__ void linear_naive_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
+                                    uint16_t* __restrict__ out, int S, int K, int N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)S * N) return;
+  const int s = (int)(i / N), n = (int)(i % N);
+  float acc = 0.f;
+  for (int k = 0; k < K; k++) acc = __fmaf_rn(bf2f(x[(size_t)s * K + k]), bf2f(w[(size_t)n * K + k]), acc);
+  out[i] = f2bf(acc);
+}
+
+// ml.MatMul BF16 (operations_matmul.go:24-60): out[g,m,n] = t(sum_seq_k a[g,m,k]*b[g,k,n])
+__global__ void matmul_naive_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b,
+                                    uint16_t* __restrict__ out, int B, int M, int K, int N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * M * N) return;
+  const int n = (int)(i % N);
+  const int64_t gm = i / N;
+  const int g = (int)(gm / M);
+  const uint16_t* ar = a + gm * K;
+  const uint16_t* bg = b + (size_t)g * K * N;
+  float acc = 0.f;
+  for (int k = 0; k < K; k++) acc = __fmaf_rn(bf2f(ar[k]), bf2f(bg[(size_t)k * N + n]), acc);
+  out[i] = f2bf(acc);
+}
+
+// RMSNorm.Forward (llamatransformer.go:633-660), one CTA (256 threads) per row.
+// strict: sequential sum; fast: the same 256-way interleave + butterfly as gemv.cuh's prologue.
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
+                                                      uint16_t* __restrict__ out, int D, float eps, int strict) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float wsum[8];
+  __shared__ float rs;
+  const uint16_t* xr = x + (size_t)blockIdx.x * D;
+  const int tid = threadIdx.x;
+  if (strict) {
+    if (tid == 0) {
+      float sum = 0.f;
+      for (int k = 0; k < D; k++) {
+        const float v = bf2f(xr[k]);
+        sum = __fmaf_rn(v, v, sum);
+      }
+      const float me = __fadd_rn(__fdiv_rn(sum, (float)D), eps);
+      rs = (float)(1.0 / sqrt((double)me));
+    }
+  } else {
+    float sum = 0.f;
+    for (int k = tid; k < D; k += 256) {
+      const float v = bf2f(xr[k]);
+      sum = __fmaf_rn(v, v, sum);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    if ((tid & 31) == 0) wsum[tid >> 5] = sum;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < 8; i++) tot = __fadd_rn(tot, wsum[i]);
+      const float me = __fadd_rn(__fdiv_rn(tot, (float)D), eps);
+      rs = (float)(1.0 / sqrt((double)me));
+    }
+  }
+  __syncthreads();
+  const float r = rs;
+  for (int k = tid; k < D; k += 256) {
+    const float n1 = trunc_bf(__fmul_rn(bf2f(xr[k]), r));
+    out[(size_t)blockIdx.x * D + k] = f2bf(__fmul_rn(n1, bf2f(w[k])));
+  }
+}
+
+// applyRotaryEmbeddings (llamatransformer.go:753-790) standalone: x[S,H,hd]
+__global__ void rope_kernel(const uint16_t* __restrict__ x, const float* __restrict__ cis, uint16_t* __restrict__ out,
+                            int S, int H, int hd, int start_pos) {
+  const int half = hd / 2;
+  const int64_t total = (int64_t)S * H * half;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ii = (int)(i % half);
+    const int64_t sh = i / half;
+    const int s = (int)(sh / H);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(x + sh * hd + 2 * ii);
+    const double a = (double)bf_lo(w), b = (double)bf_hi(w);
+    const float2 fc = *reinterpret_cast<const float2*>(cis + ((size_t)(start_pos + s) * half + ii) * 2);
+    const double c = (double)fc.x, d = (double)fc.y;
+    const float re = (float)(a * c - b * d);
+    const float im = (float)(a * d + b * c);
+    *reinterpret_cast<uint32_t*>(out + sh * hd + 2 * ii) = (uint32_t)f2bf(re) | ((uint32_t)f2bf(im) << 16);
+  }
+}
+
+__global__ void silu_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ tab,
+                            uint16_t* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = tab[x[i]];
+}
+__global__ void add_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, uint16_t* __restrict__ out,
+                           int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = f2bf(__fadd_rn(bf2f(a[i]), bf2f(b[i])));
+}
+__global__ void mul_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, uint16_t* __restrict__ out,
+                           int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = f2bf(__fmul_rn(bf2f(a[i]), bf2f(b[i])));
+}
+
+// ml.Softmax (operations_impl.go:478-511): one CTA per row; the f64 sum is sequential
+// (reference order) -- this op-level kernel is only used by the ml.Softmax shim.
+__global__ void softmax_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int cols) {
+  __shared__ double zs;
+  const float* xr = x + (size_t)blockIdx.x * cols;
+  if (threadIdx.x == 0) {
+    double z = 0.0;
+    for (int c = 0; c < cols; c++) z = __dadd_rn(z, exp((double)xr[c]));
+    zs = z;
+  }
+  __syncthreads();
+  const double z = zs;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    out[(size_t)blockIdx.x * cols + c] = (float)__ddiv_rn(exp((double)xr[c]), z);
+}
+
+// ml.Argmax (operations_impl.go:513-548): first maximum wins, NaN and values <= -MaxFloat32
+// are never selected (-1 if nothing is).
+__global__ void __launch_bounds__(256) argmax_f32_kernel(const float* __restrict__ x, int cols, int32_t* __restrict__ out) {
+  __shared__ unsigned long long best[8];
+  const float* xr = x + (size_t)blockIdx.x * cols;
+  unsigned long long key = LNB_ARGMAX_EMPTY;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float v = xr[c];
+    if (v > -3.402823466e+38f) {
+      const unsigned long long k2 = argmax_key(v, (uint32_t)c);
+      key = k2 > key ? k2 : key;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) key = best[i] > key ? best[i] : key;
+    out[blockIdx.x] = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+  }
+}
+
+}  // namespace lnb

@@ -40,24 +40,54 @@ void orc_set_num_threads(int n) {
 
 /* One output feature, S==1: strictly sequential k, f32 accumulate
  * (operations_lineartransform.go:45-69).  Eight independent outputs are
- * interleaved only to give the CPU independent dependency chains. */
+ * processed side by side (one per SIMD lane / scalar chain) only to give the
+ * CPU independent dependency chains; each output still sees k = 0,1,2,... */
+#if defined(__AVX2__)
+#include <immintrin.h>
+static inline __m256 bf8_to_f32(const uint16_t* p) {
+  __m128i h = _mm_loadu_si128((const __m128i*)p);
+  return _mm256_castsi256_ps(_mm256_slli_epi32(_mm256_cvtepu16_epi32(h), 16));
+}
+static inline void transpose8(__m256* r) {
+  __m256 t0 = _mm256_unpacklo_ps(r[0], r[1]), t1 = _mm256_unpackhi_ps(r[0], r[1]);
+  __m256 t2 = _mm256_unpacklo_ps(r[2], r[3]), t3 = _mm256_unpackhi_ps(r[2], r[3]);
+  __m256 t4 = _mm256_unpacklo_ps(r[4], r[5]), t5 = _mm256_unpackhi_ps(r[4], r[5]);
+  __m256 t6 = _mm256_unpacklo_ps(r[6], r[7]), t7 = _mm256_unpackhi_ps(r[6], r[7]);
+  __m256 u0 = _mm256_shuffle_ps(t0, t2, 0x44), u1 = _mm256_shuffle_ps(t0, t2, 0xEE);
+  __m256 u2 = _mm256_shuffle_ps(t1, t3, 0x44), u3 = _mm256_shuffle_ps(t1, t3, 0xEE);
+  __m256 u4 = _mm256_shuffle_ps(t4, t6, 0x44), u5 = _mm256_shuffle_ps(t4, t6, 0xEE);
+  __m256 u6 = _mm256_shuffle_ps(t5, t7, 0x44), u7 = _mm256_shuffle_ps(t5, t7, 0xEE);
+  r[0] = _mm256_permute2f128_ps(u0, u4, 0x20); r[1] = _mm256_permute2f128_ps(u1, u5, 0x20);
+  r[2] = _mm256_permute2f128_ps(u2, u6, 0x20); r[3] = _mm256_permute2f128_ps(u3, u7, 0x20);
+  r[4] = _mm256_permute2f128_ps(u0, u4, 0x31); r[5] = _mm256_permute2f128_ps(u1, u5, 0x31);
+  r[6] = _mm256_permute2f128_ps(u2, u6, 0x31); r[7] = _mm256_permute2f128_ps(u3, u7, 0x31);
+}
+#endif
+
 static void linear_s1(const float* xf, const uint16_t* w, float* accout, int K, int N, int kbeg, int kend) {
 #pragma omp parallel for schedule(static)
   for (int nb = 0; nb < (N + 7) / 8; nb++) {
     int n0 = nb * 8, cnt = N - n0 < 8 ? N - n0 : 8;
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint16_t* wr[8];
     for (int j = 0; j < 8; j++) wr[j] = w + (size_t)(n0 + (j < cnt ? j : 0)) * K;
-    for (int k = kbeg; k < kend; k++) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int k = kbeg;
+#if defined(__AVX2__)
+    __m256 acc = _mm256_setzero_ps(); /* lane j = output n0+j */
+    for (; k + 8 <= kend; k += 8) {
+      __m256 r[8];
+      for (int j = 0; j < 8; j++) r[j] = bf8_to_f32(wr[j] + k);
+      transpose8(r); /* r[kk] lane j = w[n0+j][k+kk] */
+      for (int kk = 0; kk < 8; kk++) {
+        __m256 p = _mm256_mul_ps(_mm256_set1_ps(xf[k + kk]), r[kk]); /* exact product */
+        acc = _mm256_add_ps(acc, p);                                  /* one rounding per add */
+      }
+    }
+    _mm256_storeu_ps(a, acc);
+#endif
+    for (; k < kend; k++) {
       float xv = xf[k];
-      a[0] += xv * bf(wr[0][k]);
-      a[1] += xv * bf(wr[1][k]);
-      a[2] += xv * bf(wr[2][k]);
-      a[3] += xv * bf(wr[3][k]);
-      a[4] += xv * bf(wr[4][k]);
-      a[5] += xv * bf(wr[5][k]);
-      a[6] += xv * bf(wr[6][k]);
-      a[7] += xv * bf(wr[7][k]);
+      for (int j = 0; j < 8; j++) a[j] += xv * bf(wr[j][k]);
     }
     for (int j = 0; j < cnt; j++) accout[n0 + j] = a[j];
   }

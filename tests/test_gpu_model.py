@@ -1,0 +1,184 @@
+"""GPU parity of the model-level C-ABI (LlamaTransformer.Forward / generate loop) against the CPU
+oracle on a structurally identical miniature of Llama-3.1 (all fusion paths, GQA, RoPE, KV cache).
+STRICT mode must reproduce the oracle bit for bit; FAST within north_star's tolerance."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import bf16_ulp_diff, host_tensors, oracle_model
+
+pytestmark = pytest.mark.gpu
+
+SEED = 1234
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lnb_b200
+    return lnb_b200
+
+
+@pytest.fixture(scope="module")
+def tiny(L):
+    args = dict(L.synth.TINY)
+    tensors = host_tensors(args, SEED)
+    om = oracle_model(args, tensors)
+    gm = L.model.LoadModelFromTensors(args, tensors)       # the reference's flow: host tensors -> upload
+    yield args, tensors, om, gm
+    gm.Free()
+    om.close()
+
+
+def test_tables_match_oracle(L, tiny):
+    args, _, _, gm = tiny
+    _, cis = O.rope_table(args["head_dim"], args["max_seq_len"] * 2, args["rope_theta"], bool(args["use_scaled_rope"]))
+    assert np.array_equal(gm.Transformer.rope_table(), cis)
+    assert np.array_equal(gm.Transformer.silu_table(), O.silu_table_bf16())
+
+
+def test_device_generator_equals_host_generator(L, tiny):
+    args, tensors, om, gm = tiny
+    g2 = L.model.LoadSyntheticModel(args, seed=SEED)        # generated directly in HBM
+    try:
+        toks = np.array([3, 77, 1000, 5, 9], np.int32)
+        c1 = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(16), acc_mode=L._capi.LNB_ACC_STRICT)
+        c2 = L.model.InferenceContext(g2.Transformer, L.model.InferenceArgs(16), acc_mode=L._capi.LNB_ACC_STRICT)
+        l1 = gm.Transformer.Forward(c1, L.ml.Tensor(toks, L.ml.DT_INT32), 0).RawData
+        l2 = g2.Transformer.Forward(c2, L.ml.Tensor(toks, L.ml.DT_INT32), 0).RawData
+        assert np.array_equal(l1, l2)
+        c1.close(); c2.close()
+    finally:
+        g2.Free()
+    # and the host twin inside the product library
+    name = "layers.1.feed_forward.w2.weight"
+    assert np.array_equal(L.synth.fill_host(args, name, SEED), tensors[name])
+
+
+@pytest.mark.parametrize("prompt_len", [1, 5, 8])
+def test_forward_strict_bit_exact(L, tiny, prompt_len):
+    args, _, om, gm = tiny
+    rng = np.random.default_rng(prompt_len)
+    seq = 24
+    toks = rng.integers(0, args["vocab_size"], size=seq).astype(np.int32)
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(seq), acc_mode=L._capi.LNB_ACC_STRICT)
+    osess = om.new_session(seq)
+    try:
+        # prefill
+        exp, tr = osess.forward(toks[:prompt_len], 0, all_rows=True, trace=True)
+        got = gm.Transformer.Forward(ctx, L.ml.Tensor(toks[:prompt_len], L.ml.DT_INT32), 0).RawData
+        assert np.array_equal(ctx.residual(prompt_len), tr[-1]), "residual stream after the last layer differs"
+        assert np.array_equal(got, exp)
+        # decode steps
+        for pos in range(prompt_len, prompt_len + 6):
+            exp = osess.forward(toks[pos:pos + 1], pos)
+            got = gm.Transformer.Forward(ctx, L.ml.Tensor(toks[pos:pos + 1], L.ml.DT_INT32), pos).RawData
+            assert np.array_equal(got, exp), f"logits differ at position {pos}"
+        for layer in range(args["n_layers"]):
+            ok, ov = osess.cache(layer)
+            assert np.array_equal(ctx.CacheK(layer).RawData, ok)
+            assert np.array_equal(ctx.CacheV(layer).RawData, ov)
+    finally:
+        ctx.close(); osess.close()
+
+
+def test_forward_per_layer_trace_strict(L, tiny):
+    args, _, om, gm = tiny
+    toks = np.array([1, 2, 3], np.int32)
+    osess = om.new_session(8)
+    _, tr = osess.forward(toks, 0, trace=True)
+    osess.close()
+    for n in range(1, args["n_layers"] + 1):
+        ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(8), acc_mode=L._capi.LNB_ACC_STRICT)
+        ctx.set_layer_limit(n)
+        gm.Transformer.forward_argmax(ctx, toks, 0)
+        assert np.array_equal(ctx.residual(3), tr[n]), f"layer {n}"
+        ctx.close()
+
+
+def test_forward_fast_within_tolerance(L, tiny):
+    args, _, om, gm = tiny
+    rng = np.random.default_rng(11)
+    seq = 24
+    toks = rng.integers(0, args["vocab_size"], size=seq).astype(np.int32)
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(seq), acc_mode=L._capi.LNB_ACC_FAST)
+    osess = om.new_session(seq)
+    try:
+        exp = osess.forward(toks[:8], 0)
+        got = gm.Transformer.Forward(ctx, L.ml.Tensor(toks[:8], L.ml.DT_INT32), 0).RawData
+        assert np.abs(got - exp).max() <= 1e-2                      # north_star tolerance
+        for pos in range(8, 16):
+            exp = osess.forward(toks[pos:pos + 1], pos)
+            got = gm.Transformer.Forward(ctx, L.ml.Tensor(toks[pos:pos + 1], L.ml.DT_INT32), pos).RawData
+            assert np.abs(got - exp).max() <= 1e-2
+    finally:
+        ctx.close(); osess.close()
+
+
+def test_forward_errors_like_reference(L, tiny):
+    args, _, _, gm = tiny
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(8))
+    T = L.ml.Tensor
+    with pytest.raises(L.ml.MlError, match="empty token array"):
+        gm.Transformer.Forward(ctx, T(np.zeros(0, np.int32), L.ml.DT_INT32), 0)
+    with pytest.raises(L._capi.LnbError, match="SequenceLength"):
+        gm.Transformer.Forward(ctx, T(np.zeros(1, np.int32), L.ml.DT_INT32), 8)
+    with pytest.raises(L._capi.LnbError, match="out of range"):
+        gm.Transformer.Forward(ctx, T(np.array([args["vocab_size"]], np.int32), L.ml.DT_INT32), 0)
+    with pytest.raises(L._capi.LnbError, match="startPos 0"):
+        gm.Transformer.Forward(ctx, T(np.zeros(2, np.int32), L.ml.DT_INT32), 3)
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_generate_loop_matches_oracle(L, tiny, mode):
+    args, _, om, gm = tiny
+    acc = L._capi.LNB_ACC_STRICT if mode == "strict" else L._capi.LNB_ACC_FAST
+    prompt = [1, 50, 999, 7, 300, 12, 64, 2]
+    seq = 40
+    exp = om.generate(prompt, seq, stop_ids=(10**9,))
+    eng = L.inference.InferenceEngine(gm, L.model.InferenceArgs(seq), acc_mode=acc)
+    got_ref_api = [t for _, t in eng.GenerateTokens(prompt, use_reference_api=True)]
+    got_fused = [t for _, t in eng.GenerateTokens(prompt, use_reference_api=False)]
+    assert got_ref_api == got_fused
+    assert len(got_fused) == seq - len(prompt)
+    if mode == "strict":
+        assert got_fused == list(exp)
+    else:
+        n = next((i for i, (a, b) in enumerate(zip(got_fused, exp)) if a != b), len(exp))
+        assert n >= 1  # first token must agree; the full-size statistics live in test_gpu_8b.py
+
+
+def test_generate_stops_on_eos(L, tiny):
+    args, _, om, gm = tiny
+    prompt = [1, 50, 999]
+    free = list(om.generate(prompt, 20, stop_ids=(10**9,)))
+    stop = free[4]
+    gm.Vocabulary.StopTokenIds = (stop,)
+    try:
+        eng = L.inference.InferenceEngine(gm, L.model.InferenceArgs(20), acc_mode=L._capi.LNB_ACC_STRICT)
+        out = list(eng.GenerateTokens(prompt))
+        k = free.index(stop)
+        assert [t for _, t in out] == free[:k + 1]
+        assert out[-1][0] == L.inference.GSFinishedByReachingEOS
+        assert list(om.generate(prompt, 20, stop_ids=(stop,))) == free[:k + 1]
+    finally:
+        gm.Vocabulary.StopTokenIds = L.synth.STOP_IDS
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_device_resident_decode_equals_host_loop(L, tiny, use_graph):
+    args, _, om, gm = tiny
+    prompt = [1, 50, 999, 7, 300, 12, 64, 2]
+    seq = 40
+    exp = list(om.generate(prompt, seq, stop_ids=(10**9,)))
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(seq), acc_mode=L._capi.LNB_ACC_STRICT)
+    try:
+        first, _ = gm.Transformer.forward_argmax(ctx, np.array(prompt, np.int32), 0)
+        assert first == exp[0]
+        toks, ms, graphed = ctx.decode_run(first, len(prompt), seq - len(prompt) - 1, use_graph=use_graph)
+        assert list(toks) == exp[1:]
+        assert ms > 0
+        assert graphed == use_graph
+        assert ctx.launch_count() > 0
+    finally:
+        ctx.close()

@@ -1,0 +1,187 @@
+"""GPU parity tests of the op-level C-ABI (what the src/ml shims bind) against the CPU oracle.
+STRICT accumulation must be bit-identical to the oracle; FAST must be bit-identical to the NumPy
+emulation of its documented order and within 1 bf16 ulp of the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import bf, bf16_ulp_diff, emulate_fast_linear, emulate_fast_rms_scale, f32, rand_bf16
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import lnb_b200
+    return lnb_b200
+
+
+def test_device_present(L):
+    assert L._capi.lib.lnb_device_count() >= 1
+
+
+# ---- the reference's own golden cases, through the C-ABI (src/ml/operations_test.go:831-946) ----
+
+def test_linear_bf16_reference_golden(L):
+    ml = L.ml
+    w = ml.Tensor.from_f32([[0.01, 0.02, 0.03], [0.04, 0.05, 0.06], [0.07, 0.08, 0.09], [0.10, 0.11, 0.12]])
+    x = ml.Tensor.from_f32([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]])
+    exp = np.array([[0.0138, 0.0317, 0.0495, 0.0673], [0.0317, 0.0761, 0.1210, 0.1660]], np.float32)
+    got = ml.LinearTransformation(x, w)
+    assert got.Size == [2, 4]
+    assert np.abs(got.to_f32_array() - exp).max() <= 1e-3      # common.THRESHOLD_F32
+    assert np.array_equal(got.RawData, O.linear_bf16(x.RawData, w.RawData))
+
+
+def test_matmul_bf16_reference_golden(L):
+    ml = L.ml
+    a = ml.Tensor.from_f32([[[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]]] * 2)
+    b = ml.Tensor.from_f32([[[0.01, 0.02, 0.03, 0.04], [0.05, 0.06, 0.07, 0.08], [0.09, 0.10, 0.11, 0.12]]] * 2)
+    exp = np.array([[[3.7598e-02, 4.3457e-02, 4.9561e-02, 5.5420e-02], [8.2520e-02, 9.7168e-02, 1.1230e-01, 1.2695e-01]]] * 2,
+                   np.float32)
+    got = ml.MatMul(a, b)
+    assert got.Size == [2, 2, 4]
+    assert np.abs(got.to_f32_array() - exp).max() <= 1e-3
+    assert np.array_equal(got.RawData, O.matmul_bf16(a.RawData, b.RawData))
+
+
+def test_linear_shape_errors_like_reference(L):
+    ml = L.ml
+    with pytest.raises(ml.MlError, match="columns size"):
+        ml.LinearTransformation(ml.Tensor.from_f32(np.zeros((2, 3))), ml.Tensor.from_f32(np.zeros((4, 5))))
+    with pytest.raises(ml.MlError, match="same data type"):
+        ml.LinearTransformation(ml.Tensor.from_f32(np.zeros((2, 3))), ml.Tensor.from_f32(np.zeros((4, 3)), ml.DT_F32))
+
+
+# ---- panel GEMV vs oracle -------------------------------------------------------------------
+
+@pytest.mark.parametrize("S,K,N", [(1, 64, 16), (1, 256, 48), (1, 4096, 4096), (2, 512, 32), (5, 1024, 96),
+                                   (8, 4096, 1024), (11, 256, 64), (1, 14336, 512), (3, 14336, 64), (1, 264, 32),
+                                   (1, 8, 16), (1, 1000, 20)])
+def test_linear_strict_bit_exact(L, S, K, N):
+    rng = np.random.default_rng(S * 1000003 + K * 101 + N)
+    x = rand_bf16(rng, (S, K))
+    w = rand_bf16(rng, (N, K), 1.0 / math.sqrt(K))
+    ml = L.ml
+    ml.ACC_MODE = L._capi.LNB_ACC_STRICT
+    got = ml.LinearTransformation(ml.Tensor(x, ml.DT_BF16), ml.Tensor(w, ml.DT_BF16)).RawData
+    exp = O.linear_bf16(x, w)
+    assert np.array_equal(got, exp), f"{(got != exp).sum()} of {got.size} outputs differ"
+
+
+@pytest.mark.parametrize("S,K,N", [(1, 64, 16), (1, 4096, 4096), (2, 512, 32), (8, 4096, 256), (1, 14336, 512),
+                                   (1, 264, 32), (3, 72, 48)])
+def test_linear_fast_matches_documented_order(L, S, K, N):
+    rng = np.random.default_rng(S * 7 + K * 13 + N)
+    x = rand_bf16(rng, (S, K))
+    w = rand_bf16(rng, (N, K), 1.0 / math.sqrt(K))
+    ml = L.ml
+    ml.ACC_MODE = L._capi.LNB_ACC_FAST
+    try:
+        got = ml.LinearTransformation(ml.Tensor(x, ml.DT_BF16), ml.Tensor(w, ml.DT_BF16)).RawData
+    finally:
+        ml.ACC_MODE = L._capi.LNB_ACC_STRICT
+    emu = emulate_fast_linear(x, w)
+    assert np.array_equal(got, emu), f"{(got != emu).sum()} of {got.size} differ from the emulated FAST order"
+    exp = O.linear_bf16(x, w)
+    d = bf16_ulp_diff(got, exp)
+    # reorder noise only: never more than 1 bf16 ulp unless the result is a cancellation near zero
+    big = np.abs(f32(exp)) > 1e-2
+    assert d[big].max(initial=0) <= 1
+    assert (d > 0).mean() < 0.02
+
+
+# ---- RMSNorm / RoPE / attention / elementwise ----------------------------------------------
+
+@pytest.mark.parametrize("S,D", [(1, 4096), (3, 4096), (2, 256), (1, 1000)])
+def test_rmsnorm_strict_bit_exact(L, S, D):
+    rng = np.random.default_rng(D + S)
+    x, w = rand_bf16(rng, (S, D), 2.0), bf(1 + 0.1 * rng.standard_normal(D))
+    out = np.empty((S, D), np.uint16)
+    c = L._capi
+    c.check(c.lib.lnb_op_rmsnorm_bf16(c.ptr(x, c.u16p), c.ptr(w, c.u16p), c.ptr(out, c.u16p), S, D, 1e-5, c.LNB_ACC_STRICT))
+    assert np.array_equal(out, O.rmsnorm(x, w, 1e-5))
+
+
+def test_rmsnorm_fast_matches_documented_order(L):
+    rng = np.random.default_rng(5)
+    S, D = 2, 4096
+    x, w = rand_bf16(rng, (S, D), 2.0), bf(1 + 0.1 * rng.standard_normal(D))
+    out = np.empty((S, D), np.uint16)
+    c = L._capi
+    c.check(c.lib.lnb_op_rmsnorm_bf16(c.ptr(x, c.u16p), c.ptr(w, c.u16p), c.ptr(out, c.u16p), S, D, 1e-5, c.LNB_ACC_FAST))
+    for s in range(S):
+        r = emulate_fast_rms_scale(x[s], 1e-5)
+        n1 = bf(f32(x[s]) * r)
+        assert np.array_equal(out[s], bf(f32(n1) * f32(w)))
+    assert bf16_ulp_diff(out, O.rmsnorm(x, w, 1e-5)).max() <= 1
+
+
+def test_rope_bit_exact(L):
+    rng = np.random.default_rng(6)
+    _, cis = O.rope_table(128, 300, 500000.0, True)
+    for S, H, pos in [(1, 32, 0), (1, 8, 137), (5, 32, 0), (3, 8, 255)]:
+        x = rand_bf16(rng, (S, H, 128))
+        out = np.empty_like(x)
+        c = L._capi
+        c.check(c.lib.lnb_op_rope_bf16(c.ptr(x, c.u16p), c.ptr(cis, c.f32p), c.ptr(out, c.u16p), S, H, 128, pos))
+        assert np.array_equal(out, O.rope_apply(x, cis, pos))
+
+
+@pytest.mark.parametrize("S,T,causal", [(1, 1, 0), (1, 37, 0), (1, 135, 0), (5, 5, 1), (8, 8, 1), (1, 300, 0)])
+def test_attention_strict_bit_exact(L, S, T, causal):
+    rng = np.random.default_rng(S * 31 + T)
+    nh, nkv, hd = 32, 8, 128
+    q = rand_bf16(rng, (S, nh, hd))
+    ck, cv = rand_bf16(rng, (T, nkv, hd)), rand_bf16(rng, (T, nkv, hd))
+    out = np.empty((S, nh * hd), np.uint16)
+    c = L._capi
+    c.check(c.lib.lnb_op_attention_bf16(c.ptr(q, c.u16p), c.ptr(ck, c.u16p), c.ptr(cv, c.u16p), c.ptr(out, c.u16p),
+                                        S, T, nh, nkv, hd, causal, c.LNB_ACC_STRICT))
+    exp = O.attention(q, ck, cv, T, causal)
+    assert np.array_equal(out, exp), f"{(out != exp).sum()} of {out.size} differ"
+    # FAST only reorders the f64 softmax denominator
+    c.check(c.lib.lnb_op_attention_bf16(c.ptr(q, c.u16p), c.ptr(ck, c.u16p), c.ptr(cv, c.u16p), c.ptr(out, c.u16p),
+                                        S, T, nh, nkv, hd, causal, c.LNB_ACC_FAST))
+    assert bf16_ulp_diff(out, exp).max() <= 1 and (out != exp).mean() < 1e-3
+
+
+def test_attention_mask_shape_error(L):
+    c = L._capi
+    z = np.zeros((2, 8, 32), np.uint16)
+    k = np.zeros((5, 2, 32), np.uint16)
+    out = np.zeros((2, 256), np.uint16)
+    rc = c.lib.lnb_op_attention_bf16(c.ptr(z, c.u16p), c.ptr(k, c.u16p), c.ptr(k, c.u16p), c.ptr(out, c.u16p), 2, 5, 8, 2, 32, 1, 0)
+    assert rc == -1 and b"T == S" in c.lib.lnb_last_error()
+
+
+def test_elementwise_ops_bit_exact(L):
+    ml = L.ml
+    rng = np.random.default_rng(7)
+    a, b = rand_bf16(rng, (3, 1000), 3.0), rand_bf16(rng, (3, 1000), 3.0)
+    ta, tb = ml.Tensor(a, ml.DT_BF16), ml.Tensor(b, ml.DT_BF16)
+    assert np.array_equal(ml.Add(ta, tb).RawData, O.add_bf16(a, b))
+    assert np.array_equal(ml.MultiplyElementwise(ta, tb).RawData, O.mul_bf16(a, b))
+    allbits = np.arange(65536, dtype=np.uint16)
+    got, exp = ml.Silu(ml.Tensor(allbits, ml.DT_BF16)).RawData, O.silu_bf16(allbits)
+    assert np.array_equal(got, exp)                       # every entry of TABLE_SILU
+
+
+def test_softmax_argmax_getrows(L):
+    ml = L.ml
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal((4, 135)) * 2).astype(np.float32)
+    assert np.array_equal(ml.Softmax(ml.Tensor(x, ml.DT_F32), 1).RawData, O.softmax_f32(x))
+    lg = f32(rand_bf16(rng, (3, 128256), 0.25)).reshape(3, 128256)
+    lg[1, 500] = lg[1].max(); lg[1, 90000] = lg[1].max()              # tie -> lowest index
+    lg[2, :] = np.nan
+    got = ml.Argmax(ml.Tensor(lg, ml.DT_F32), 1).RawData
+    assert list(got) == [O.argmax_f32(lg[0]), 500, -1]
+    emb = rand_bf16(rng, (64, 256))
+    tok = np.array([5, 0, 63, 5], np.int32)
+    got = ml.Fwd_Get_Rows(ml.Tensor(emb, ml.DT_BF16), ml.Tensor(tok, ml.DT_INT32)).RawData
+    assert np.array_equal(got, emb[tok])
+    with pytest.raises(L._capi.LnbError):
+        ml.Fwd_Get_Rows(ml.Tensor(emb, ml.DT_BF16), ml.Tensor(np.array([64], np.int32), ml.DT_INT32))
