@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/sec of Llama-3.1-8B bf16 on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): random-init weights of the 8B
+architecture, the fixed 8-token synthetic prompt, SequenceLength 136 -> one prefill call
+(S=8) that yields token #1 plus 127 S=1 decode calls = exactly 128 generated tokens
+(src/inference/inference.go:194-253).  ONE STEP = one such generation.
+
+  value  = 127*K / (device time of the K*127 decode steps), CUDA events on the launching
+           stream inside lnb_decode_run; inputs (weights, KV cache, token) resident in HBM.
+  e2e    = the same metric through the reference-facing API with HOST buffers:
+           inference.GenerateTokens(use_reference_api=True), i.e. per iteration
+           Transformer.Forward (tokens H2D, f32 logits [S,V] D2H) -> Slice -> ml.Argmax.
+  roofline = the dominant kernel (w1|w3 GEMV, 54 % of the step's bytes) timed alone.
+  cpu_baseline = the CPU oracle ("port" of the Go path) on this box's host cores, bounded sample.
+
+`--impl reference` times only that CPU restatement (the Go toolchain does not exist in this
+image, so the reference binary itself cannot run).
+Multi-GPU (torchrun, one rank per GPU): tensor parallel, "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PROMPT, SEQ_LEN = 8, 136
+N_DECODE = SEQ_LEN - N_PROMPT - 1  # 127 S=1 steps
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = int(float(self.rows[0][1])) if self.rows else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_setup():
+    """host copy of the synthetic checkpoint (oracle generator) + oracle model"""
+    import numpy as np
+    import lnb_b200 as L
+    from tests.helpers import host_tensors, oracle_model
+    args = dict(L.synth.LLAMA31_8B)
+    t0 = time.time()
+    tensors = host_tensors(args, L.synth.SEED)
+    om = oracle_model(args, tensors)
+    return om, tensors, time.time() - t0, np
+
+
+def cpu_sample(om, np, n_decode: int):
+    """one bounded sample of the workload on the CPU: prefill the 8-token prompt, then n_decode
+    S=1 steps; returns (prefill_s, decode_s, tokens, last-row logits per call)"""
+    import lnb_b200 as L
+    prompt = np.array(L.synth.PROMPT_8, np.int32)
+    sess = om.new_session(SEQ_LEN)
+    toks, logits = [], []
+    t0 = time.perf_counter()
+    lg = sess.forward(prompt, 0, all_rows=False)
+    t_prefill = time.perf_counter() - t0
+    from oracle import oracle as O
+    nxt = O.argmax_f32(lg[0])
+    toks.append(nxt); logits.append(lg[0].copy())
+    t0 = time.perf_counter()
+    for i in range(n_decode):
+        lg = sess.forward(np.array([nxt], np.int32), N_PROMPT + i, all_rows=False)
+        nxt = O.argmax_f32(lg[0])
+        toks.append(nxt); logits.append(lg[0].copy())
+    t_decode = time.perf_counter() - t0
+    sess.close()
+    return t_prefill, t_decode, toks, logits
+
+
+def run_reference(a):
+    """--impl reference: the CPU restatement of the Go path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    om, _, t_setup, np = cpu_oracle_setup()
+    n_dec = 4
+    for _ in range(max(0, a.warmup - 2)):  # CPU steps cost seconds; one warm-up sample is plenty
+        break
+    cpu_sample(om, np, 1)
+    t_dec_total, t_pre_total = 0.0, 0.0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        tp, td, _, _ = cpu_sample(om, np, n_dec)
+        t_dec_total += td
+        t_pre_total += tp
+    wall = time.perf_counter() - t0
+    val = a.steps * n_dec / t_dec_total
+    cores = O.lib().orc_num_threads()
+    line = {
+        "impl": "reference", "metric": "decode tokens/sec Llama-3.1-8B bf16", "value": round(val, 4), "unit": "tokens/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1000 * wall / a.steps, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Llama-3.1-8B bf16 random-init, 8-token prompt, seq_len=1 decode over KV cache "
+                               "(configs[1]); each step = prefill + %d decode tokens (bounded sample)" % n_dec,
+                   "seq_len": SEQ_LEN, "prompt_tokens": N_PROMPT},
+        "cpu_baseline": {"value": round(val, 4), "unit": "tokens/s", "cores": cores, "kind": "port",
+                         "sample": f"{a.steps} x (prefill 8 + {n_dec} decode steps) of the same workload; C restatement of "
+                                   "the Go goroutine path (Go toolchain absent)",
+                         "prefill_s": round(t_pre_total / a.steps, 3)},
+        "e2e": {"value": round(val, 4), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lnb", choices=["lnb", "reference"])
+    ap.add_argument("--acc", default=os.environ.get("LNB_BENCH_ACC", "fast"), choices=["fast", "strict"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-decode", type=int, default=6, help="decode steps in the cpu_baseline sample")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    a.warmup = max(a.warmup, 3)
+
+    import numpy as np
+    import torch
+    import lnb_b200 as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {a.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            import ctypes
+            raw = ctypes.create_string_buffer(128)
+            L._capi.check(L._capi.lib.lnb_nccl_unique_id(raw))
+            buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().numpy().tobytes())
+
+    acc = L._capi.LNB_ACC_FAST if a.acc == "fast" else L._capi.LNB_ACC_STRICT
+    args = dict(L.synth.LLAMA31_8B)
+    t0 = time.time()
+    model = L.model.LoadSyntheticModel(args, seed=L.synth.SEED, device=local, tp_rank=rank, tp_size=world, nccl_id=nccl_id)
+    t_load = time.time() - t0
+    prompt = np.array(L.synth.PROMPT_8, np.int32)
+    tf = model.Transformer
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm (`value`) -----------------------------------------------------
+    ctx = L.model.InferenceContext(tf, L.model.InferenceArgs(SEQ_LEN), max_rows=8, acc_mode=acc)
+
+    def one_generation():
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        first, _ = tf.forward_argmax(ctx, prompt, 0)                       # prefill, token #1
+        t_pre = time.perf_counter() - t0
+        toks, ms, graphed = ctx.decode_run(first, N_PROMPT, N_DECODE, use_graph=True)
+        return first, toks, ms, t_pre, graphed
+
+    for _ in range(a.warmup):
+        first, toks, _, _, graphed = one_generation()
+    gen_tokens = [int(first)] + [int(t) for t in toks]
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    dec_ms, pre_s = 0.0, 0.0
+    for _ in range(a.steps):
+        _, toks_k, ms, t_pre, _ = one_generation()
+        dec_ms += ms
+        pre_s += t_pre
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.summary()
+    launches = ctx.launch_count() - launches0
+    assert [int(first)] + [int(t) for t in toks_k] == gen_tokens, "generation is not reproducible run to run"
+    if dist is not None:
+        t = torch.tensor([dec_ms, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dec_ms, wall = float(t[0]), float(t[1])
+    value = a.steps * N_DECODE / (dec_ms / 1e3)
+    stop_hit = any(t in L.synth.STOP_IDS for t in gen_tokens)
+
+    # ---- roofline of the dominant kernel (w1|w3 GEMV), timed alone ----------------------------
+    peak, peak_kind = load_peaks()
+    kinds = {0: "wqkv", 1: "wo", 2: "w13", 3: "w2", 4: "lm_head"}
+    kern = {}
+    for k, nm in kinds.items():
+        ms, nb, nl = ctx.bench_kernel(k, reps=3)
+        kern[nm] = {"us": round(ms * 1e3, 2), "bytes": nb, "gbs": round(nb / (ms * 1e-3) / 1e9, 1), "launches": nl}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("w13_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    dom = kern["w13"]
+    roofline = {"bound": "hbm", "kernel": "gemv_kernel<w1|w3, rmsnorm prologue, SwiGLU epilogue>",
+                "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": round(dom["gbs"] / peak, 4),
+                "traffic": traffic, "peak_kind": peak_kind + " (burst copy bandwidth)",
+                "bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]}
+    # whole decode step against the weight-read roofline (SURVEY.md 8d bytes)
+    per_gpu_bytes = (13_958_643_712 + 1_050_673_152) / world + 524_288 + 16_384 + 131_072 / world * 72
+    step_s = dec_ms / 1e3 / (a.steps * N_DECODE)
+    roofline_step = {"bytes_per_token_per_gpu": int(per_gpu_bytes), "achieved": round(per_gpu_bytes / step_s / 1e9, 1),
+                     "peak": peak, "unit": "GB/s", "frac": round(per_gpu_bytes / step_s / 1e9 / peak, 4),
+                     "roofline_tokens_per_s": round(peak * 1e9 / per_gpu_bytes, 1)}
+
+    # ---- e2e arm: the reference-facing API with host buffers ----------------------------------
+    e2e = None
+    if world == 1:
+        eng = L.inference.InferenceEngine(model, L.model.InferenceArgs(SEQ_LEN), acc_mode=acc)
+        saved_stop = model.Vocabulary.StopTokenIds
+        model.Vocabulary.StopTokenIds = () if stop_hit else saved_stop
+        for _ in range(2):
+            list(eng.GenerateTokens(list(prompt), use_reference_api=True))
+        times, e2e_tokens = [], None
+        barrier()
+        for _ in range(a.steps):
+            st = []
+            e2e_tokens = [t for _, t in eng.GenerateTokens(list(prompt), use_reference_api=True, step_times=st)]
+            times.append(st)
+        barrier()
+        dec = sum(sum(st[1:]) for st in times)
+        ndec = sum(len(st) - 1 for st in times)
+        V = args["vocab_size"]
+        h2d = N_PROMPT * 4 + N_DECODE * 4 + (N_DECODE + 1) * V * 4        # tokens + ml.Argmax shim re-upload
+        d2h = (N_PROMPT + N_DECODE) * V * 4 + (N_DECODE + 1) * 4          # all-row logits + argmax ids
+        e2e = {"value": round(ndec / dec, 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "inference.GenerateTokens -> Transformer.Forward (host tokens in, host f32 logits [S,V] out) -> "
+                      "Slice -> ml.Argmax", "tokens_equal_device_loop": e2e_tokens == gen_tokens[:len(e2e_tokens)],
+               "prefill_ms": round(1e3 * sum(st[0] for st in times) / len(times), 2)}
+        # the fused forward+argmax entry (4-byte read-back) for comparison
+        st = []
+        list(eng.GenerateTokens(list(prompt), use_reference_api=False, step_times=st))
+        e2e["fused_call_tokens_per_s"] = round((len(st) - 1) / sum(st[1:]), 2)
+        model.Vocabulary.StopTokenIds = saved_stop
+
+    # ---- strict-mode number (bit-exact arm) for the record ------------------------------------
+    other = None
+    if world == 1:
+        oacc = L._capi.LNB_ACC_STRICT if a.acc == "fast" else L._capi.LNB_ACC_FAST
+        c2 = L.model.InferenceContext(tf, L.model.InferenceArgs(SEQ_LEN), max_rows=8, acc_mode=oacc)
+        f2, _ = tf.forward_argmax(c2, prompt, 0)
+        c2.decode_run(f2, N_PROMPT, N_DECODE, use_graph=True)
+        f2, _ = tf.forward_argmax(c2, prompt, 0)
+        t2, ms2, _ = c2.decode_run(f2, N_PROMPT, N_DECODE, use_graph=True)
+        o_tokens = [int(f2)] + [int(t) for t in t2]
+        n_same = next((i for i, (x, y) in enumerate(zip(o_tokens, gen_tokens)) if x != y), len(gen_tokens))
+        other = {"acc": "strict" if a.acc == "fast" else "fast", "value": round(N_DECODE / (ms2 / 1e3), 2),
+                 "unit": "tokens/s", "tokens_equal_to_headline_arm": n_same}
+        c2.close()
+
+    # ---- cpu_baseline + parity against the oracle on the same workload ---------------------------
+    cpu, parity = None, None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        from oracle import oracle as O
+        om, _, t_setup, _ = cpu_oracle_setup()
+        cpu_sample(om, np, 1)
+        t_pre, t_dec, o_toks, o_logits = cpu_sample(om, np, a.cpu_decode)
+        cpu = {"value": round(a.cpu_decode / t_dec, 4), "unit": "tokens/s", "cores": O.lib().orc_num_threads(),
+               "kind": "port", "sample": f"prefill 8 tokens ({t_pre:.2f} s) + {a.cpu_decode} S=1 decode steps of the same "
+               "workload; C restatement of the Go goroutine path (Go toolchain absent)", "host_weight_gen_s": round(t_setup, 1)}
+        # teacher-forced comparison of the GPU arm with the oracle on those positions
+        c3 = L.model.InferenceContext(tf, L.model.InferenceArgs(SEQ_LEN), max_rows=8, acc_mode=acc)
+        maxabs, agree, nd = 0.0, 0, 0
+        nxt, lg = tf.forward_argmax(c3, prompt, 0, want_logits="last")
+        seq_in = [None] + o_toks[:-1]
+        for i in range(len(o_toks)):
+            if i > 0:
+                nxt, lg = tf.forward_argmax(c3, np.array([seq_in[i]], np.int32), N_PROMPT + i - 1, want_logits="last")
+            d = np.abs(lg[0] - o_logits[i])
+            maxabs = max(maxabs, float(d.max()))
+            nd += int((d > 0).sum())
+            agree += int(nxt == o_toks[i])
+        c3.close()
+        parity = {"vs": "cpu oracle, teacher-forced, first %d tokens" % len(o_toks), "acc": a.acc,
+                  "logits_max_abs": round(maxabs, 6), "logits_differing": nd, "argmax_agree": f"{agree}/{len(o_toks)}",
+                  "free_running_tokens_equal": next((i for i, (x, y) in enumerate(zip(gen_tokens, o_toks)) if x != y),
+                                                    len(o_toks)), "tolerance": 1e-2}
+        om.close()
+
+    if rank == 0:
+        line = {
+            "metric": "decode tokens/sec Llama-3.1-8B bf16", "value": round(value, 2), "unit": "tokens/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1e3 * wall / a.steps, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Llama-3.1-8B bf16 random-init, 8-token prompt, 128-token generation, seq_len=1 decode "
+                                   "over KV cache (BASELINE.json configs[1]%s)" % ("" if world == 1 else f", tensor-parallel x{world}"),
+                       "seq_len": SEQ_LEN, "prompt_tokens": N_PROMPT, "decode_steps_per_generation": N_DECODE,
+                       "parallelism": "tp%d" % world, "acc": a.acc, "cuda_graph": bool(graphed),
+                       "l2": "working set 15 GB per token >> 126 MB L2 (no flush needed)",
+                       "stop_id_generated": stop_hit},
+            "decode_ms_per_token": round(dec_ms / (a.steps * N_DECODE), 4),
+            "prefill_ms": round(1e3 * pre_s / a.steps, 3),
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline, "roofline_step": roofline_step, "kernels_alone": kern,
+            "e2e": e2e, "other_acc_mode": other, "cpu_baseline": cpu, "parity": parity,
+            "model_load_s": round(t_load, 2),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    model.Free()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -138,6 +138,11 @@ int lnb_session_set_layer_limit(lnb_session* s, int n_layers_to_run); /* <=0: al
 /* number of kernels launched by this session since creation (bench.py gpu_launches) */
 int64_t lnb_session_launch_count(lnb_session* s);
 int lnb_session_sync(lnb_session* s);
+/* Measurement hook for bench.py's roofline: times ONE projection kernel of the decode step in
+ * isolation (all layers' weights back to back so every launch streams from HBM; `reps` sweeps;
+ * CUDA events on the session stream).  kind: 0 wq|wk|wv, 1 wo, 2 w1|w3, 3 w2, 4 LM head. */
+int lnb_session_bench_kernel(lnb_session* s, int kind, int reps, float* ms_per_launch, int64_t* bytes_per_launch,
+                             int* launches);
 
 /* ------------------------------------------------------------------------------------
  * Op-level API -- what the src/ml shims bind.  Host pointers in and out; each call

@@ -56,6 +56,7 @@ SIGNATURES = {
     "lnb_session_set_layer_limit": (C.c_int, [vp, C.c_int]),
     "lnb_session_launch_count": (C.c_int64, [vp]),
     "lnb_session_sync": (C.c_int, [vp]),
+    "lnb_session_bench_kernel": (C.c_int, [vp, C.c_int, C.c_int, f32p, i64p, i32p]),
     "lnb_op_linear_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_matmul_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_rmsnorm_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_float, C.c_int]),

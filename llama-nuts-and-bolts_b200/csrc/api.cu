@@ -896,6 +896,76 @@ extern "C" int lnb_decode_run(lnb_session* s, int32_t first_token, int start_pos
   return graph ? 1 : 0;
 }
 
+// Times one projection kernel of the decode step in isolation: launches it for every layer's
+// weights back to back (n_layers * 100+ MB >> L2, so every launch streams from HBM), `reps`
+// sweeps, CUDA events on the session stream.  kind: 0 = wq|wk|wv, 1 = wo, 2 = w1|w3, 3 = w2,
+// 4 = LM head.  Outputs go to the session's scratch activations (results are discarded).
+extern "C" int lnb_session_bench_kernel(lnb_session* s, int kind, int reps, float* ms_per_launch, int64_t* bytes_per_launch,
+                                        int* launches) {
+  if (!s || reps <= 0 || kind < 0 || kind > 4) return fail(LNB_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> lk(s->mu);
+  lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  CU(cudaSetDevice(m->device));
+  Launcher L{s->stream, true, &s->launches};
+  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, 0, 1, 0, 0);
+  int n_launch = 0;
+  int64_t bytes = 0;
+  auto sweep = [&]() -> int {
+    int rc = 0;
+    const int nl = (kind == 4) ? 4 : a.n_layers;  // the LM head is one 1 GB matrix: repeat it
+    for (int l = 0; l < nl && !rc; l++) {
+      LayerW& W = m->layers[kind == 4 ? 0 : l];
+      GemvParams p{};
+      p.eps = a.norm_eps;
+      switch (kind) {
+        case 0:
+          p.W = W.wqkv; p.N = m->q_l + 2 * m->kv_l; p.K = a.dim; p.x = s->x; p.ldx = a.dim; p.norm_w = W.attn_norm;
+          p.out_bf16 = s->q; p.ldo = m->q_l; p.q_dim = m->q_l; p.kv_dim = m->kv_l; p.head_dim = a.head_dim;
+          p.cache_k = s->ck[l]; p.cache_v = s->cv[l]; p.cis = m->cis; p.pos_ptr = &s->st->pos;
+          rc = launch_gemv<PRO_RMSNORM, EPI_QKV_ROPE>(L, s->mode, p, 1);
+          break;
+        case 1:
+          p.W = W.wo; p.N = a.dim; p.K = m->q_l; p.x = s->o; p.ldx = m->q_l; p.ldo = a.dim; p.out_bf16 = s->h1; p.res = s->x;
+          rc = launch_gemv<PRO_PLAIN, EPI_RESID>(L, s->mode, p, 1);
+          break;
+        case 2:
+          p.W = W.w13; p.N = 2 * m->ffn_l; p.K = a.dim; p.x = s->h1; p.ldx = a.dim; p.norm_w = W.ffn_norm;
+          p.out_bf16 = s->mbuf; p.ldo = m->ffn_l; p.silu_tab = m->silu_tab;
+          rc = launch_gemv<PRO_RMSNORM, EPI_SWIGLU>(L, s->mode, p, 1);
+          break;
+        case 3:
+          p.W = W.w2; p.N = a.dim; p.K = m->ffn_l; p.x = s->mbuf; p.ldx = m->ffn_l; p.ldo = a.dim; p.out_bf16 = s->h1; p.res = s->x;
+          rc = launch_gemv<PRO_PLAIN, EPI_RESID>(L, s->mode, p, 1);
+          break;
+        case 4:
+          p.W = m->output; p.N = m->vocab_l; p.K = a.dim; p.x = s->x; p.ldx = a.dim; p.norm_w = m->norm; p.ldo = m->vocab_l;
+          p.st = nullptr; p.argmax_row = -1;
+          rc = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(L, s->mode, p, 1);
+          break;
+      }
+      bytes = (int64_t)p.N * p.K * 2;
+      n_launch++;
+    }
+    return rc;
+  };
+  int rc = sweep();  // warm-up sweep
+  if (rc) return rc;
+  n_launch = 0;
+  CU(cudaEventRecord(s->ev0, s->stream));
+  for (int r = 0; r < reps; r++)
+    if ((rc = sweep())) return rc;
+  CU(cudaEventRecord(s->ev1, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  if (ms_per_launch) *ms_per_launch = ms / (float)n_launch;
+  if (bytes_per_launch) *bytes_per_launch = bytes;
+  if (launches) *launches = n_launch;
+  return 0;
+}
+
 extern "C" int lnb_session_read(lnb_session* s, int which, int layer, void* host, int64_t nbytes) {
   if (!s || !host) return fail(LNB_EINVAL, "NULL argument");
   lnb_model* m = s->m;

@@ -186,6 +186,12 @@ class InferenceContext:
                                       ptr(toks, _capi.i32p), C.byref(ms)))
         return toks, ms.value, bool(rc)
 
+    def bench_kernel(self, kind: int, reps: int = 3):
+        """(ms per launch, algorithmic weight bytes per launch, launches timed) -- bench.py roofline"""
+        ms, nb, nl = C.c_float(0), C.c_int64(0), C.c_int32(0)
+        check(lib.lnb_session_bench_kernel(self.h, kind, reps, C.byref(ms), C.byref(nb), C.byref(nl)))
+        return ms.value, nb.value, nl.value
+
     def close(self):
         if self.h:
             lib.lnb_session_destroy(self.h)
