@@ -155,7 +155,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lnb", choices=["lnb", "reference"])
-    ap.add_argument("--acc", default=os.environ.get("LNB_BENCH_ACC", "fast"), choices=["fast", "strict"])
+    ap.add_argument("--acc", default=os.environ.get("LNB_BENCH_ACC", "auto"), choices=["auto", "fast", "strict"],
+                    help="accumulation order: strict = the reference's k order (bit-identical logits; headline at 1 GPU), "
+                         "fast = interleaved partial sums (tensor-parallel runs reorder the sums anyway)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-decode", type=int, default=6, help="decode steps in the cpu_baseline sample")
     a = ap.parse_args()
@@ -189,6 +191,8 @@ def main():
         dist.broadcast(buf, 0)
         nccl_id = bytes(buf.cpu().numpy().tobytes())
 
+    if a.acc == "auto":
+        a.acc = "strict" if world == 1 else "fast"
     acc = L._capi.LNB_ACC_FAST if a.acc == "fast" else L._capi.LNB_ACC_STRICT
     args = dict(L.synth.LLAMA31_8B)
     t0 = time.time()

@@ -457,7 +457,14 @@ extern "C" int lnb_model_finalize(lnb_model* m) {
 
 // ------------------------------------------------------------------------------------------
 // GEMV dispatch
-using CfgS1 = GemvCfg<32, 1, 1, 256, 4>;
+// LNB_ACC_STRICT, one activation row.  The accumulation chain is issue-bound on its scheduler
+// (~2.4 instructions per k at one instruction per 2 cycles), so every chain warp needs an SMSP to
+// itself: ONE CTA per SM (>113 KB of shared memory each) holding 1, 2 or 4 chain warps (warps 1..4
+// sit on SMSPs 1,2,3,0; the producer warp 0 sleeps on its mbarrier), picked from N so that the grid
+// stays close to one wave.  Two chain warps on one scheduler run at half speed each.
+using CfgS1 = GemvCfg<32, 1, 1, 512, 3>;    // N <= 32*148 rows
+using CfgS1M = GemvCfg<64, 1, 1, 512, 3>;   // N <= 64*148
+using CfgS1W = GemvCfg<128, 1, 1, 256, 3>;  // larger N (w1|w3, LM head): several waves, HBM-bound
 using CfgS2 = GemvCfg<32, 1, 2, 256, 4>;
 using CfgS8 = GemvCfg<32, 1, 8, 256, 4>;
 using CfgF1 = GemvCfg<32, 8, 1, 256, 4>;
@@ -515,6 +522,7 @@ static int launch_gemv(const Launcher& L, int mode, GemvParams p, int M_total) {
   uint16_t* ob0 = p.out_bf16;
   float* of0 = p.out_f32;
   const uint16_t* res0 = p.res;
+  const float* rs0 = p.rscale;
   const int moff0 = p.m_off;
   LnbDevState* st0 = p.st;
   const int arg_row = p.argmax_row;
@@ -524,6 +532,7 @@ static int launch_gemv(const Launcher& L, int mode, GemvParams p, int M_total) {
     p.out_bf16 = ob0 ? ob0 + (size_t)m0 * p.ldo : nullptr;
     p.out_f32 = of0 ? of0 + (size_t)m0 * p.ldo : nullptr;
     p.res = res0 ? res0 + (size_t)m0 * p.ldo : nullptr;
+    p.rscale = rs0 ? rs0 + m0 : nullptr;
     p.m_off = moff0 + m0;
     if (EPI == EPI_LOGITS) {
       const bool covers = st0 && arg_row >= m0 && arg_row < m0 + p.M;
@@ -532,9 +541,11 @@ static int launch_gemv(const Launcher& L, int mode, GemvParams p, int M_total) {
     }
     int rc;
     if (strict) {
-      if (mb == 8) rc = launch_gemv_cfg<CfgS8, PRO, EPI>(L, p);
-      else if (mb == 2) rc = launch_gemv_cfg<CfgS2, PRO, EPI>(L, p);
-      else rc = launch_gemv_cfg<CfgS1, PRO, EPI>(L, p);
+      if (mb == 1 && p.N > 64 * 148 && p.N % 128 == 0 && CfgS1W::smem_bytes(p.K) <= kMaxSmem) rc = launch_gemv_cfg<CfgS1W, PRO, EPI>(L, p);
+      else if (mb == 1 && p.N > 32 * 148 && p.N % 64 == 0 && CfgS1M::smem_bytes(p.K) <= kMaxSmem) rc = launch_gemv_cfg<CfgS1M, PRO, EPI>(L, p);
+      else if (mb == 1) rc = launch_gemv_cfg<CfgS1, PRO, EPI>(L, p);
+      else if (mb == 8) rc = launch_gemv_cfg<CfgS8, PRO, EPI>(L, p);
+      else rc = launch_gemv_cfg<CfgS2, PRO, EPI>(L, p);
     } else {
       if (mb == 8) rc = launch_gemv_cfg<CfgF8, PRO, EPI>(L, p);
       else if (mb == 2) rc = launch_gemv_cfg<CfgF2, PRO, EPI>(L, p);
@@ -594,6 +605,7 @@ struct lnb_session {
   cudaStream_t stream = nullptr;
   uint16_t *x = nullptr, *h1 = nullptr, *q = nullptr, *o = nullptr, *mbuf = nullptr;
   float* part = nullptr;
+  float* rs = nullptr;  // [max_rows] strict-mode RMSNorm scales
   float* logits = nullptr;
   size_t logits_rows = 0;
   float* logits_full = nullptr;  // tp>1: gathered [rows, vocab]
@@ -634,6 +646,7 @@ extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int a
   al((void**)&s->o, (size_t)max_rows * m->q_l * 2);
   al((void**)&s->mbuf, (size_t)max_rows * m->ffn_l * 2);
   al((void**)&s->part, (size_t)max_rows * a.dim * 4);
+  al((void**)&s->rs, (size_t)max_rows * 4);
   al((void**)&s->d_tokens, (size_t)max_rows * 4);
   al((void**)&s->st, sizeof(LnbDevState));
   al((void**)&s->d_tok_out, (size_t)seq_len * 4);
@@ -664,7 +677,7 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   cudaSetDevice(s->m->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->graph) cudaGraphExecDestroy(s->graph);
-  cudaFree(s->x); cudaFree(s->h1); cudaFree(s->q); cudaFree(s->o); cudaFree(s->mbuf); cudaFree(s->part);
+  cudaFree(s->x); cudaFree(s->h1); cudaFree(s->q); cudaFree(s->o); cudaFree(s->mbuf); cudaFree(s->part); cudaFree(s->rs);
   cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
@@ -724,10 +737,17 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
     return f;
   }();
   const size_t sdpa_smem = (size_t)s->seq_len * 12 + (size_t)a.head_dim * 4;
+  const bool strict = (mode == LNB_ACC_STRICT);
+  auto strict_scale = [&](const uint16_t* xin, int rows) -> int {
+    if (!strict) return 0;
+    return launch_simple(L, rms_scale_kernel, dim3(rows), dim3(128), (size_t)a.dim * 4, xin, a.dim, s->rs, a.dim, a.norm_eps);
+  };
   for (int l = 0; l < n_layers; l++) {
     LayerW& W = m->layers[l];
+    if ((rc = strict_scale(s->x, S))) return rc;
     {  // attn_norm -> wq|wk|wv -> RoPE -> KV append            (:222, :297-403)
       GemvParams p{};
+      p.rscale = strict ? s->rs : nullptr;
       p.W = W.wqkv; p.N = m->q_l + 2 * m->kv_l; p.K = a.dim;
       p.x = s->x; p.ldx = a.dim; p.norm_w = W.attn_norm; p.eps = a.norm_eps;
       p.out_bf16 = s->q; p.ldo = m->q_l;
@@ -754,8 +774,10 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
           return rc;
       }
     }
+    if ((rc = strict_scale(s->h1, S))) return rc;
     {  // ffn_norm -> w1|w3 -> SiLU * up                             (:237, :601-614)
       GemvParams p{};
+      p.rscale = strict ? s->rs : nullptr;
       p.W = W.w13; p.N = 2 * m->ffn_l; p.K = a.dim; p.x = s->h1; p.ldx = a.dim; p.norm_w = W.ffn_norm; p.eps = a.norm_eps;
       p.out_bf16 = s->mbuf; p.ldo = m->ffn_l; p.silu_tab = m->silu_tab;
       if ((rc = launch_gemv<PRO_RMSNORM, EPI_SWIGLU>(L, mode, p, S))) return rc;
@@ -779,7 +801,9 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
   {  // output_norm -> output -> f32 logits (+ greedy argmax of the last row)   (:166-175; inference.go:207-216)
     const int rows = (logits_rows > 1) ? S : 1;  // rows of the head actually computed
     const int row0 = S - rows;
+    if ((rc = strict_scale(s->x + (size_t)row0 * a.dim, rows))) return rc;
     GemvParams p{};
+    p.rscale = strict ? s->rs : nullptr;
     p.W = m->output; p.N = m->vocab_l; p.K = a.dim;
     p.x = s->x + (size_t)row0 * a.dim; p.ldx = a.dim; p.norm_w = m->norm; p.eps = a.norm_eps;
     p.out_f32 = logits_rows > 0 ? s->logits : nullptr; p.ldo = m->vocab_l;
@@ -878,10 +902,11 @@ extern "C" int lnb_decode_run(lnb_session* s, int32_t first_token, int start_pos
   }
   if (graph) {
     // count what the graph replays launch: one forward's worth per step
-    static thread_local int64_t per_step = 0;
-    if (!per_step) {
+    int64_t per_step = 0;
+    {
       const lnb_model_args& a = s->m->a;
-      per_step = 2 + (int64_t)a.n_layers * (s->m->tp_size == 1 ? 5 : 7) + (s->m->tp_size == 1 ? 0 : 1);
+      per_step = 2 + (int64_t)a.n_layers * (s->m->tp_size == 1 ? 5 : 7) + (s->m->tp_size == 1 ? 0 : 1) +
+                 (s->mode == LNB_ACC_STRICT ? 2 * (int64_t)a.n_layers + 1 : 0);
     }
     s->launches = per_step_before + per_step * n_steps;
   }
@@ -918,6 +943,7 @@ extern "C" int lnb_session_bench_kernel(lnb_session* s, int kind, int reps, floa
       LayerW& W = m->layers[kind == 4 ? 0 : l];
       GemvParams p{};
       p.eps = a.norm_eps;
+      p.rscale = (s->mode == LNB_ACC_STRICT) ? s->rs : nullptr;
       switch (kind) {
         case 0:
           p.W = W.wqkv; p.N = m->q_l + 2 * m->kv_l; p.K = a.dim; p.x = s->x; p.ldx = a.dim; p.norm_w = W.attn_norm;
@@ -949,6 +975,11 @@ extern "C" int lnb_session_bench_kernel(lnb_session* s, int kind, int reps, floa
     }
     return rc;
   };
+  if (s->mode == LNB_ACC_STRICT) {
+    int rc0 = launch_simple(L, rms_scale_kernel, dim3(1), dim3(128), (size_t)a.dim * 4, (const uint16_t*)s->x, a.dim, s->rs,
+                            a.dim, a.norm_eps);
+    if (rc0) return rc0;
+  }
   int rc = sweep();  // warm-up sweep
   if (rc) return rc;
   n_launch = 0;

@@ -11,7 +11,9 @@
 LNB_DEVINL float bf2f(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
 LNB_DEVINL uint16_t f2bf(float f) { return (uint16_t)(__float_as_uint(f) >> 16); }  // truncation
 // a 32-bit word holding two consecutive bf16 (little endian: element 0 in the low half)
-LNB_DEVINL float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+// PRMT (ALU pipe) instead of a shift: ptxas would turn `w << 16` into IMAD.U32 on the FMA pipe,
+// where it competes with the dependent-FFMA accumulation chains of the GEMV.
+LNB_DEVINL float bf_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0u, 0x1044)); }
 LNB_DEVINL float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 LNB_DEVINL float trunc_bf(float f) { return __uint_as_float(__float_as_uint(f) & 0xffff0000u); }  // bf2f(f2bf(f))
 
@@ -42,6 +44,14 @@ LNB_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 LNB_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// polite variant for warps that are NOT on the critical path: back off between polls so that the
+// spinning warp does not steal issue slots from the accumulation-chain warp on the same scheduler
+#ifndef LNB_BACKOFF_NS
+#define LNB_BACKOFF_NS 64
+#endif
+LNB_DEVINL void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(LNB_BACKOFF_NS);
 }
 
 // ---- bulk async copy global -> shared (TMA engine, 1-D; SASS: UBLKCP) -------------------

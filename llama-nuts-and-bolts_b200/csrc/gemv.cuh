@@ -46,6 +46,7 @@ struct GemvParams {
   const uint16_t* norm_w;  // [K] bf16 (PRO_RMSNORM)
   float eps;
   int strict_norm;         // 1: sequential sum of squares (reference order)
+  const float* rscale;     // [M] precomputed f32(1/sqrt(mean+eps)) per row (rms_scale_kernel); NULL: computed in-CTA
   // epilogue
   uint16_t* out_bf16;      // EPI_BF16 / EPI_RESID / EPI_SWIGLU(out [M, N/2]) / EPI_QKV_ROPE(q_out [M, q_dim])
   float* out_f32;          // EPI_F32RAW / EPI_LOGITS (may be NULL for LOGITS)
@@ -77,7 +78,7 @@ struct GemvCfg {
   static constexpr int kThreads = kNCons + 32;         // + producer warp
   static constexpr int kStageBytes = TN * KT * 2;
   static constexpr int kChunksPerTile = KT / 8;
-  static_assert(TN % 16 == 0 && (TN == 16 || TN == 32), "TN");
+  static_assert(TN % 32 == 0 && TN <= 128, "TN");
   static_assert(kNCons % 32 == 0, "consumer warps");
   static_assert(kChunksPerTile % KS == 0, "k-tile must hold a whole number of chunk rounds");
   static size_t smem_bytes(int K) {
@@ -90,11 +91,100 @@ struct GemvCfg {
 };
 
 // ------------------------------------------------------------------------------------------
+// Epilogue of one output element: v = the untruncated fp32 dot product of activation row em with
+// weight row n.  Must be called by all 32 lanes of a warp (it shuffles); lane == tile row % 32.
+template <int EPI>
+LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool valid, int panel, int er, int lane) {
+  if (EPI == EPI_BF16) {
+    if (valid) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(v);
+  } else if (EPI == EPI_F32RAW) {
+    if (valid) p.out_f32[(size_t)em * p.ldo + n] = v;
+  } else if (EPI == EPI_RESID) {
+    if (valid) {
+      float a = trunc_bf(v);
+      float rsd = bf2f(p.res[(size_t)em * p.ldo + n]);
+      p.out_bf16[(size_t)em * p.ldo + n] = f2bf(__fadd_rn(rsd, a));
+    }
+  } else if (EPI == EPI_LOGITS) {
+    float lv = trunc_bf(v);
+    if (valid && p.out_f32) p.out_f32[(size_t)em * p.ldo + n] = lv;
+    unsigned long long key = LNB_ARGMAX_EMPTY;
+    if (valid && em == p.argmax_row && lv > -3.402823466e+38f) key = argmax_key(lv, (uint32_t)(n + p.n_offset));
+    if (p.st) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+      }
+      if (lane == 0 && key != LNB_ARGMAX_EMPTY) atomicMax(&p.st->amax_key, key);
+    }
+  } else if (EPI == EPI_QKV_ROPE) {
+    // rows [0,q_dim) = q, [q_dim, q_dim+kv_dim) = k, rest = v.  RoPE pairs (2i,2i+1) are
+    // adjacent rows == adjacent lanes.  Go evaluates complex64*complex64 through float64
+    // (operations_impl.go:414-417), products are exact in f64.
+    const float mine = trunc_bf(v);                                     // t(linear)  (:306-344)
+    const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    if (valid) {
+      const int pos = *p.pos_ptr + p.m_off + em;
+      if (n < p.q_dim + p.kv_dim) {
+        const int nn = (n < p.q_dim) ? n : n - p.q_dim;
+        const int i = (nn % p.head_dim) >> 1;
+        const float2 fc = *reinterpret_cast<const float2*>(p.cis + ((size_t)pos * (p.head_dim / 2) + i) * 2);
+        const double cc = (double)fc.x, dd = (double)fc.y;
+        float o;
+        if ((n & 1) == 0) {
+          const double a = (double)mine, b = (double)other;
+          o = (float)(a * cc - b * dd);
+        } else {
+          const double a = (double)other, b = (double)mine;
+          o = (float)(a * dd + b * cc);
+        }
+        if (n < p.q_dim) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(o);
+        else p.cache_k[(size_t)pos * p.kv_dim + nn] = f2bf(o);           // SetSlice :402
+      } else {
+        p.cache_v[(size_t)pos * p.kv_dim + (n - p.q_dim - p.kv_dim)] = f2bf(mine);  // :403
+      }
+    }
+  } else if (EPI == EPI_SWIGLU) {
+    // panels alternate: even panel = 16 w1 (gate) rows, odd panel = the same 16 rows of w3 (up);
+    // the partner of tile row er (er % 32 < 16) is er + 16 == lane + 16 of the same warp
+    const float mine = trunc_bf(v);
+    const float up = __shfl_down_sync(0xffffffffu, mine, 16);
+    if (valid && (er & 16) == 0) {
+      const uint16_t sg = p.silu_tab[f2bf(mine)];                       // t(TABLE_SILU[bits]) activations.go:38
+      const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
+      p.out_bf16[(size_t)em * p.ldo + (size_t)(panel >> 1) * 16 + (er & 15)] = f2bf(mm);
+    }
+  }
+}
+
+// LM head, tp_size == 1: the last CTA to finish decodes the argmax key into the greedy token and
+// (device-driven decode) advances the per-session state.  Called by ONE thread per CTA after that
+// CTA's atomicMax contributions are fenced.
+LNB_DEVINL void logits_publish(const GemvParams& p) {
+  const unsigned int done = atomicAdd(&p.st->done_ctr, 1u);
+  if (done == gridDim.x - 1) {
+    __threadfence();
+    const unsigned long long key = atomicExch(&p.st->amax_key, LNB_ARGMAX_EMPTY);
+    const int32_t tok = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+    p.st->next_token = tok;
+    p.st->done_ctr = 0;
+    if (p.advance) {
+      if (p.tok_out) p.tok_out[p.st->step] = tok;
+      p.st->step += 1;
+      p.st->pos += 1;
+    }
+    __threadfence();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 template <class Cfg, int PRO, int EPI>
 __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p) {
   constexpr int TN = Cfg::kTN, KS = Cfg::kKS, MB = Cfg::kMB, KT = Cfg::kKT, NST = Cfg::kNST;
   constexpr int P = Cfg::kP, NCONS = Cfg::kNCons, STAGE = Cfg::kStageBytes;
   constexpr int CPT = Cfg::kChunksPerTile;
+  static_assert(CPT % KS == 0, "chunks per tile");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);            // [NST]
@@ -180,7 +270,9 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
         *reinterpret_cast<float2*>(s_x + (size_t)m * K + k) = v;
       }
     named_bar_sync(1, NCONS);
-    if (p.strict_norm) {
+    if (p.rscale) {
+      if (c < MB) s_scalar[c] = (c < p.M) ? p.rscale[c] : 0.f;
+    } else if (p.strict_norm) {
       // reference order: one sequential chain per row; rows are spread over threads
       if (c < MB) {
         float sum = 0.f;
@@ -224,6 +316,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
 #pragma unroll
   for (int m = 0; m < MB; m++) acc[m] = 0.f;
 
+  constexpr int NI = CPT / KS;  // chunks of one thread per full k-tile
   for (int t = 0; t < n_tiles; t++) {
     const int s = t % NST;
     const uint32_t ph = (uint32_t)(t / NST) & 1u;
@@ -231,26 +324,66 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
     const int k0 = t * KT;
     const int nchunks = min(KT, K - k0) / 8;
     const uint8_t* tile = s_stage + (size_t)s * STAGE + (size_t)pp * (KT * 32) + rr * 16;
-#pragma unroll 4
-    for (int ch = j; ch < nchunks; ch += KS) {
-      const uint4 wv = *reinterpret_cast<const uint4*>(tile + ch * 256);
-      const float w0 = bf_lo(wv.x), w1 = bf_hi(wv.x), w2 = bf_lo(wv.y), w3 = bf_hi(wv.y);
-      const float w4 = bf_lo(wv.z), w5 = bf_hi(wv.z), w6 = bf_lo(wv.w), w7 = bf_hi(wv.w);
-      const float* xk = s_x + k0 + ch * 8;
+    if (MB == 1 && NI % 4 == 0 && nchunks == CPT) {
+      // Full tile, one activation row: groups of 4 chunks with register double buffering, so the
+      // shared-memory loads of group g+1 are in flight while the 32 dependent FMAs of group g
+      // issue (the chain is the critical path in LNB_ACC_STRICT: 4 cycles per k).
+      constexpr int G = 4, NG = NI / G;
+      uint4 wa[G], wb[G];
+      float4 xa0[G], xa1[G], xb0[G], xb1[G];
+      const float* xt = s_x + k0;
+#define LNB_LOAD_GROUP(gi, W_, X0_, X1_)                                      \
+  _Pragma("unroll") for (int q_ = 0; q_ < G; q_++) {                          \
+    const int ch_ = j + KS * ((gi) * G + q_);                                 \
+    W_[q_] = *reinterpret_cast<const uint4*>(tile + ch_ * 256);               \
+    X0_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8);                 \
+    X1_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8 + 4);             \
+  }
+#define LNB_FMA_GROUP(W_, X0_, X1_)                                           \
+  _Pragma("unroll") for (int q_ = 0; q_ < G; q_++) {                          \
+    float a_ = acc[0];                                                        \
+    a_ = __fmaf_rn(X0_[q_].x, bf_lo(W_[q_].x), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].y, bf_hi(W_[q_].x), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].z, bf_lo(W_[q_].y), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].w, bf_hi(W_[q_].y), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].x, bf_lo(W_[q_].z), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].y, bf_hi(W_[q_].z), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].z, bf_lo(W_[q_].w), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].w, bf_hi(W_[q_].w), a_);                           \
+    acc[0] = a_;                                                              \
+  }
+      LNB_LOAD_GROUP(0, wa, xa0, xa1)
 #pragma unroll
-      for (int m = 0; m < MB; m++) {
-        const float4 xa = *reinterpret_cast<const float4*>(xk + (size_t)m * K);
-        const float4 xb = *reinterpret_cast<const float4*>(xk + (size_t)m * K + 4);
-        float a = acc[m];
-        a = __fmaf_rn(xa.x, w0, a);
-        a = __fmaf_rn(xa.y, w1, a);
-        a = __fmaf_rn(xa.z, w2, a);
-        a = __fmaf_rn(xa.w, w3, a);
-        a = __fmaf_rn(xb.x, w4, a);
-        a = __fmaf_rn(xb.y, w5, a);
-        a = __fmaf_rn(xb.z, w6, a);
-        a = __fmaf_rn(xb.w, w7, a);
-        acc[m] = a;
+      for (int gi = 0; gi < NG; gi += 2) {
+        if (gi + 1 < NG) { LNB_LOAD_GROUP(gi + 1, wb, xb0, xb1) }
+        LNB_FMA_GROUP(wa, xa0, xa1)
+        if (gi + 2 < NG) { LNB_LOAD_GROUP(gi + 2, wa, xa0, xa1) }
+        if (gi + 1 < NG) { LNB_FMA_GROUP(wb, xb0, xb1) }
+      }
+#undef LNB_LOAD_GROUP
+#undef LNB_FMA_GROUP
+    } else {
+#pragma unroll 4
+      for (int ch = j; ch < nchunks; ch += KS) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(tile + ch * 256);
+        const float w0 = bf_lo(wv.x), w1 = bf_hi(wv.x), w2 = bf_lo(wv.y), w3 = bf_hi(wv.y);
+        const float w4 = bf_lo(wv.z), w5 = bf_hi(wv.z), w6 = bf_lo(wv.w), w7 = bf_hi(wv.w);
+        const float* xk = s_x + k0 + ch * 8;
+#pragma unroll
+        for (int m = 0; m < MB; m++) {
+          const float4 xa = *reinterpret_cast<const float4*>(xk + (size_t)m * K);
+          const float4 xb = *reinterpret_cast<const float4*>(xk + (size_t)m * K + 4);
+          float a = acc[m];
+          a = __fmaf_rn(xa.x, w0, a);
+          a = __fmaf_rn(xa.y, w1, a);
+          a = __fmaf_rn(xa.z, w2, a);
+          a = __fmaf_rn(xa.w, w3, a);
+          a = __fmaf_rn(xb.x, w4, a);
+          a = __fmaf_rn(xb.y, w5, a);
+          a = __fmaf_rn(xb.z, w6, a);
+          a = __fmaf_rn(xb.w, w7, a);
+          acc[m] = a;
+        }
       }
     }
     __syncwarp();
@@ -280,92 +413,17 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
     }
     const int n = (panel0 + er / 16) * 16 + (er % 16);  // global row of W
     const bool valid = (em < p.M) && (er / 16 < my_panels);
-
-    if (EPI == EPI_BF16) {
-      if (valid) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(v);
-    } else if (EPI == EPI_F32RAW) {
-      if (valid) p.out_f32[(size_t)em * p.ldo + n] = v;
-    } else if (EPI == EPI_RESID) {
-      if (valid) {
-        float a = trunc_bf(v);
-        float rsd = bf2f(p.res[(size_t)em * p.ldo + n]);
-        p.out_bf16[(size_t)em * p.ldo + n] = f2bf(__fadd_rn(rsd, a));
-      }
-    } else if (EPI == EPI_LOGITS) {
-      float lv = trunc_bf(v);
-      if (valid && p.out_f32) p.out_f32[(size_t)em * p.ldo + n] = lv;
-      unsigned long long key = LNB_ARGMAX_EMPTY;
-      if (valid && em == p.argmax_row && lv > -3.402823466e+38f) key = argmax_key(lv, (uint32_t)(n + p.n_offset));
-      if (p.st) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-          key = other > key ? other : key;
-        }
-        if (lane == 0 && key != LNB_ARGMAX_EMPTY) atomicMax(&p.st->amax_key, key);
-      }
-    } else if (EPI == EPI_QKV_ROPE) {
-      // rows [0,q_dim) = q, [q_dim, q_dim+kv_dim) = k, rest = v.  RoPE pairs (2i,2i+1) are
-      // adjacent rows == adjacent lanes.  Go evaluates complex64*complex64 through float64
-      // (operations_impl.go:414-417), products are exact in f64.
-      const float mine = trunc_bf(v);                                     // t(linear)  (:306-344)
-      const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-      if (valid) {
-        const int pos = *p.pos_ptr + p.m_off + em;
-        if (n < p.q_dim + p.kv_dim) {
-          const int nn = (n < p.q_dim) ? n : n - p.q_dim;
-          const int i = (nn % p.head_dim) >> 1;
-          const float2 fc = *reinterpret_cast<const float2*>(p.cis + ((size_t)pos * (p.head_dim / 2) + i) * 2);
-          const double cc = (double)fc.x, dd = (double)fc.y;
-          float o;
-          if ((n & 1) == 0) {
-            const double a = (double)mine, b = (double)other;
-            o = (float)(a * cc - b * dd);
-          } else {
-            const double a = (double)other, b = (double)mine;
-            o = (float)(a * dd + b * cc);
-          }
-          if (n < p.q_dim) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(o);
-          else p.cache_k[(size_t)pos * p.kv_dim + nn] = f2bf(o);           // SetSlice :402
-        } else {
-          p.cache_v[(size_t)pos * p.kv_dim + (n - p.q_dim - p.kv_dim)] = f2bf(mine);  // :403
-        }
-      }
-    } else if (EPI == EPI_SWIGLU) {
-      // TN == 32: rows 0..15 of the tile are w1 (gate) rows, 16..31 the same rows of w3 (up)
-      const float mine = trunc_bf(v);
-      const float up = __shfl_down_sync(0xffffffffu, mine, 16);
-      if (valid && er < 16) {
-        const uint16_t sg = p.silu_tab[f2bf(mine)];                       // t(TABLE_SILU[bits]) activations.go:38
-        const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
-        p.out_bf16[(size_t)em * p.ldo + (size_t)blockIdx.x * 16 + er] = f2bf(mm);
-      }
-    }
+    gemv_epilogue<EPI>(p, v, n, em, valid, panel0 + er / 16, er, lane);
   }
 
   if (EPI == EPI_LOGITS) {
-    // last CTA done: publish the greedy token and advance the device-side decode state
     if (p.st && p.publish) {
       __threadfence();
       named_bar_sync(1, NCONS);
-      if (c == 0) {
-        const unsigned int done = atomicAdd(&p.st->done_ctr, 1u);
-        if (done == gridDim.x - 1) {
-          __threadfence();
-          const unsigned long long key = atomicExch(&p.st->amax_key, LNB_ARGMAX_EMPTY);
-          const int32_t tok = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
-          p.st->next_token = tok;
-          p.st->done_ctr = 0;
-          if (p.advance) {
-            if (p.tok_out) p.tok_out[p.st->step] = tok;
-            p.st->step += 1;
-            p.st->pos += 1;
-          }
-          __threadfence();
-        }
-      }
+      if (c == 0) logits_publish(p);
     }
   }
 }
+
 
 }  // namespace lnb

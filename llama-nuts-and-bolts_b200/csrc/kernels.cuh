@@ -254,6 +254,60 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint16_t* __restrict
   }
 }
 
+// LNB_ACC_STRICT RMSNorm scale, once per row instead of once per GEMV CTA:
+//   r[m] = f32( 1 / sqrt( f64( (sum_seq_k x[m,k]^2) / D + eps ) ) )     (llamatransformer.go:641-656)
+// The sum is the reference's strictly sequential f32 chain (4 cycles per element on one thread);
+// the squares (exact in f32) are staged in shared memory by the whole CTA first and the chain
+// reads them with double-buffered 128-bit loads so that only the FADD latency is exposed.
+// grid = rows, block = 128, dyn smem = D * 4.
+__global__ void __launch_bounds__(128) rms_scale_kernel(const uint16_t* __restrict__ x, int ldx, float* __restrict__ r,
+                                                        int D, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) float sq[];
+  const uint16_t* xr = x + (size_t)blockIdx.x * ldx;
+  for (int k = threadIdx.x * 2; k < D; k += 256) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(xr + k);
+    const float a = bf_lo(w), b = bf_hi(w);
+    sq[k] = __fmul_rn(a, a);
+    sq[k + 1] = __fmul_rn(b, b);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    const float4* q4 = reinterpret_cast<const float4*>(sq);
+    const int n4 = D / 4;
+    constexpr int B = 8;
+    int i = 0;
+    if (n4 >= 2 * B) {
+      float4 a[B], b[B];
+#pragma unroll
+      for (int u = 0; u < B; u++) a[u] = q4[u];
+      for (; i + 2 * B <= n4; i += 2 * B) {
+#pragma unroll
+        for (int u = 0; u < B; u++) b[u] = q4[i + B + u];
+#pragma unroll
+        for (int u = 0; u < B; u++) {
+          sum = __fadd_rn(sum, a[u].x); sum = __fadd_rn(sum, a[u].y);
+          sum = __fadd_rn(sum, a[u].z); sum = __fadd_rn(sum, a[u].w);
+        }
+        if (i + 3 * B <= n4) {
+#pragma unroll
+          for (int u = 0; u < B; u++) a[u] = q4[i + 2 * B + u];
+        }
+#pragma unroll
+        for (int u = 0; u < B; u++) {
+          sum = __fadd_rn(sum, b[u].x); sum = __fadd_rn(sum, b[u].y);
+          sum = __fadd_rn(sum, b[u].z); sum = __fadd_rn(sum, b[u].w);
+        }
+      }
+    }
+    for (int k = i * 4; k < D; k++) sum = __fadd_rn(sum, sq[k]);
+    const float me = __fadd_rn(__fdiv_rn(sum, (float)D), eps);
+    r[blockIdx.x] = (float)(1.0 / sqrt((double)me));
+  }
+}
+
 // applyRotaryEmbeddings (llamatransformer.go:753-790) standalone: x[S,H,hd]
 __global__ void rope_kernel(const uint16_t* __restrict__ x, const float* __restrict__ cis, uint16_t* __restrict__ out,
                             int S, int H, int hd, int start_pos) {
