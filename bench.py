@@ -271,7 +271,7 @@ def main():
 
     # ---- e2e arm: the reference-facing API with host buffers ----------------------------------
     e2e = None
-    if world == 1:
+    if True:  # every rank runs the same host loop in lock step (the greedy token is identical on all ranks)
         eng = L.inference.InferenceEngine(model, L.model.InferenceArgs(SEQ_LEN), acc_mode=acc)
         saved_stop = model.Vocabulary.StopTokenIds
         model.Vocabulary.StopTokenIds = () if stop_hit else saved_stop
@@ -286,6 +286,10 @@ def main():
         barrier()
         dec = sum(sum(st[1:]) for st in times)
         ndec = sum(len(st) - 1 for st in times)
+        if dist is not None:
+            t = torch.tensor([dec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dec = float(t[0])
         V = args["vocab_size"]
         h2d = N_PROMPT * 4 + N_DECODE * 4 + (N_DECODE + 1) * V * 4        # tokens + ml.Argmax shim re-upload
         d2h = (N_PROMPT + N_DECODE) * V * 4 + (N_DECODE + 1) * 4          # all-row logits + argmax ids

@@ -73,6 +73,11 @@ typedef struct lnb_session lnb_session; /* model.InferenceContext: KV cache + ac
 int lnb_model_create(const lnb_model_args* args, int device, int tp_rank, int tp_size,
                      const void* nccl_unique_id, lnb_model** out);
 int lnb_nccl_unique_id(void* out128);
+/* Host-only arithmetic (no CUDA call): the [row0:row0+rows, col0:col0+cols] window of checkpoint
+ * tensor `name` that rank tp_rank of tp_size keeps (Megatron split: wq/wk/wv/w1/w3/output by rows,
+ * wo/w2 by columns, norms and embeddings replicated). */
+int lnb_tp_shard_window(const lnb_model_args* args, const char* name, int tp_rank, int tp_size,
+                        int64_t* row0, int64_t* col0, int64_t* rows, int64_t* cols);
 
 /* Upload one checkpoint tensor by its reference name ("layers.7.attention.wq.weight",
  * "tok_embeddings.weight", ...; names and shapes: llamatransformer.go:84-105,191,202,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "lnb_device_count": (C.c_int, []),
     "lnb_model_create": (C.c_int, [C.POINTER(ModelArgsC), C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]),
     "lnb_nccl_unique_id": (C.c_int, [vp]),
+    "lnb_tp_shard_window": (C.c_int, [C.POINTER(ModelArgsC), C.c_char_p, C.c_int, C.c_int, i64p, i64p, i64p, i64p]),
     "lnb_model_upload_tensor": (C.c_int, [vp, C.c_char_p, u16p, i64p, C.c_int]),
     "lnb_model_init_synthetic": (C.c_int, [vp, C.c_uint64]),
     "lnb_synth_fill_host": (C.c_int, [C.c_uint64, C.c_char_p, C.c_float, C.c_float, C.c_int64, u16p]),

@@ -199,6 +199,36 @@ static void mark_present(lnb_model* m, int kind, int layer) {
   else m->layers[layer].have |= 1u << kind;
 }
 
+// Pure host arithmetic (no CUDA): which window of checkpoint tensor `name` rank tp_rank owns.
+extern "C" int lnb_tp_shard_window(const lnb_model_args* args, const char* name, int tp_rank, int tp_size,
+                                   int64_t* row0, int64_t* col0, int64_t* rows, int64_t* cols) {
+  if (!args || !name || !row0 || !col0 || !rows || !cols) return fail(LNB_EINVAL, "NULL argument");
+  if (tp_size < 1 || tp_rank < 0 || tp_rank >= tp_size) return fail(LNB_EINVAL, "bad tp rank %d / size %d", tp_rank, tp_size);
+  const lnb_model_args& a = *args;
+  if (a.n_kv_heads % tp_size || a.ffn_dim % tp_size || a.vocab_size % tp_size)
+    return fail(LNB_EINVAL, "tp_size %d must divide n_kv_heads, ffn_dim and vocab_size", tp_size);
+  lnb_model tmp;
+  tmp.a = a;
+  tmp.tp_rank = tp_rank;
+  tmp.tp_size = tp_size;
+  tmp.q_dim = a.n_heads * a.head_dim;
+  tmp.kv_dim = a.n_kv_heads * a.head_dim;
+  tmp.q_l = tmp.q_dim / tp_size;
+  tmp.kv_l = tmp.kv_dim / tp_size;
+  tmp.ffn_l = a.ffn_dim / tp_size;
+  tmp.vocab_l = a.vocab_size / tp_size;
+  tmp.layers.resize(a.n_layers);
+  int kind, layer;
+  if (parse_name(&tmp, name, &kind, &layer)) return fail(LNB_EINVAL, "unknown tensor name \"%s\"", name);
+  Placement p = placement(&tmp, kind, layer);
+  int64_t fr, fc;
+  full_shape(&tmp, kind, &fr, &fc);
+  *row0 = p.row0; *col0 = p.col0;
+  if (fc == 1) { *rows = fr; *cols = 1; }  // 1-D tensors are replicated
+  else { *rows = p.rows; *cols = p.cols; }
+  return 0;
+}
+
 extern "C" int lnb_model_create(const lnb_model_args* args, int device, int tp_rank, int tp_size,
                                 const void* nccl_unique_id, lnb_model** out) {
   if (!args || !out) return fail(LNB_EINVAL, "args/out is NULL");
@@ -1022,11 +1052,57 @@ extern "C" int lnb_session_read(lnb_session* s, int which, int layer, void* host
 
 // ------------------------------------------------------------------------------------------
 // op-level API: host pointers in / out, staged through HBM, same kernels as the model path
+// Device scratch for the op-level calls: a grow-only per-thread arena (cudaMalloc / cudaFree per
+// call cost more than the kernels they serve).  Buffers are carved with 256-byte alignment and
+// the arena is rewound at the start of every op.
+struct OpArena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, used = 0;
+  int dev = -1;
+  std::vector<void*> overflow;  // blocks allocated after the arena filled up in this op
+  void rewind() {
+    for (void* q : overflow) cudaFree(q);
+    overflow.clear();
+    used = 0;
+  }
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d != dev) {  // the calling thread switched devices: start over
+      if (base) cudaFree(base);
+      base = nullptr; cap = used = 0; dev = d;
+    }
+    if (used + bytes > cap) {
+      if (used == 0) {  // nothing handed out yet: regrow the arena itself
+        if (base) cudaFree(base);
+        base = nullptr;
+        const size_t want = bytes * 2 > ((size_t)8 << 20) ? bytes * 2 : ((size_t)8 << 20);
+        if (cudaMalloc((void**)&base, want) != cudaSuccess) { cap = 0; return nullptr; }
+        cap = want;
+      } else {
+        void* q = nullptr;
+        if (cudaMalloc(&q, bytes) != cudaSuccess) return nullptr;
+        overflow.push_back(q);
+        return q;
+      }
+    }
+    void* r = base + used;
+    used += bytes;
+    return r;
+  }
+};
+static thread_local OpArena g_arena;
 struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  cudaError_t alloc(size_t bytes) {
+    p = g_arena.take(bytes ? bytes : 16);
+    return p ? cudaSuccess : cudaErrorMemoryAllocation;
+  }
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+struct OpScope {  // rewinds the arena when an op-level entry point begins
+  OpScope() { g_arena.rewind(); }
 };
 #define OPBUF(buf, bytes)                                                                     \
   DevBuf buf;                                                                                 \
@@ -1041,6 +1117,7 @@ static int op_finish() {
 static int grid_for(int64_t n) { return (int)std::min<int64_t>(148 * 8, (n + 255) / 256); }
 
 extern "C" int lnb_op_linear_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int S, int K, int N, int acc_mode) {
+  OpScope scope_;
   if (!x || !w || !out) return fail(LNB_EINVAL, "NULL argument");
   if (S <= 0 || K <= 0 || N <= 0) return fail(LNB_EINVAL, "non-positive shape");
   if (acc_mode != LNB_ACC_STRICT && acc_mode != LNB_ACC_FAST) return fail(LNB_EINVAL, "bad acc_mode %d", acc_mode);
@@ -1071,6 +1148,7 @@ extern "C" int lnb_op_linear_bf16(const uint16_t* x, const uint16_t* w, uint16_t
 }
 
 extern "C" int lnb_op_matmul_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int B, int M, int K, int N) {
+  OpScope scope_;
   if (!a || !b || !out) return fail(LNB_EINVAL, "NULL argument");
   if (B <= 0 || M <= 0 || K <= 0 || N <= 0) return fail(LNB_EINVAL, "non-positive shape");
   const size_t ab = (size_t)B * M * K * 2, bb = (size_t)B * K * N * 2, ob = (size_t)B * M * N * 2;
@@ -1084,6 +1162,7 @@ extern "C" int lnb_op_matmul_bf16(const uint16_t* a, const uint16_t* b, uint16_t
 }
 
 extern "C" int lnb_op_rmsnorm_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int S, int D, float eps, int acc_mode) {
+  OpScope scope_;
   if (!x || !w || !out) return fail(LNB_EINVAL, "NULL argument");
   if (S <= 0 || D <= 0) return fail(LNB_EINVAL, "non-positive shape");
   const size_t xb = (size_t)S * D * 2;
@@ -1097,6 +1176,7 @@ extern "C" int lnb_op_rmsnorm_bf16(const uint16_t* x, const uint16_t* w, uint16_
 }
 
 extern "C" int lnb_op_rope_bf16(const uint16_t* x, const float* cis, uint16_t* out, int S, int H, int hd, int start_pos) {
+  OpScope scope_;
   if (!x || !cis || !out) return fail(LNB_EINVAL, "NULL argument");
   if (S <= 0 || H <= 0 || hd <= 0 || (hd & 1) || start_pos < 0) return fail(LNB_EINVAL, "bad shape");
   const size_t xb = (size_t)S * H * hd * 2, cb = (size_t)(start_pos + S) * (hd / 2) * 2 * 4;
@@ -1111,6 +1191,7 @@ extern "C" int lnb_op_rope_bf16(const uint16_t* x, const float* cis, uint16_t* o
 
 extern "C" int lnb_op_attention_bf16(const uint16_t* q, const uint16_t* cache_k, const uint16_t* cache_v, uint16_t* out,
                                      int S, int T, int n_heads, int n_kv, int hd, int causal_mask, int acc_mode) {
+  OpScope scope_;
   if (!q || !cache_k || !cache_v || !out) return fail(LNB_EINVAL, "NULL argument");
   if (S <= 0 || T < S || n_heads <= 0 || n_kv <= 0 || n_heads % n_kv || hd <= 0 || hd % 8) return fail(LNB_EINVAL, "bad shape");
   if (causal_mask && T != S) return fail(LNB_EINVAL, "causal mask needs T == S (reference mask is [S,S])");
@@ -1151,6 +1232,7 @@ static int silu_table_device(uint16_t** out) {
 }
 
 extern "C" int lnb_op_silu_bf16(const uint16_t* x, uint16_t* out, int64_t n) {
+  OpScope scope_;
   if (!x || !out || n < 0) return fail(LNB_EINVAL, "bad argument");
   if (n == 0) return 0;
   uint16_t* tab;
@@ -1166,6 +1248,7 @@ extern "C" int lnb_op_silu_bf16(const uint16_t* x, uint16_t* out, int64_t n) {
 }
 
 static int binary_op(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n, bool is_add) {
+  OpScope scope_;
   if (!a || !b || !out || n < 0) return fail(LNB_EINVAL, "bad argument");
   if (n == 0) return 0;
   OPBUF(da, (size_t)n * 2); OPBUF(db, (size_t)n * 2); OPBUF(dout, (size_t)n * 2);
@@ -1181,6 +1264,7 @@ extern "C" int lnb_op_add_bf16(const uint16_t* a, const uint16_t* b, uint16_t* o
 extern "C" int lnb_op_mul_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n) { return binary_op(a, b, out, n, false); }
 
 extern "C" int lnb_op_softmax_f32(const float* x, float* out, int rows, int cols) {
+  OpScope scope_;
   if (!x || !out || rows <= 0 || cols <= 0) return fail(LNB_EINVAL, "bad argument");
   const size_t b = (size_t)rows * cols * 4;
   OPBUF(dx, b); OPBUF(dout, b);
@@ -1193,6 +1277,7 @@ extern "C" int lnb_op_softmax_f32(const float* x, float* out, int rows, int cols
 }
 
 extern "C" int lnb_op_argmax_f32(const float* x, int rows, int cols, int32_t* out) {
+  OpScope scope_;
   if (!x || !out || rows <= 0 || cols <= 0) return fail(LNB_EINVAL, "bad argument");
   const size_t b = (size_t)rows * cols * 4;
   OPBUF(dx, b); OPBUF(dout, (size_t)rows * 4);
@@ -1205,6 +1290,7 @@ extern "C" int lnb_op_argmax_f32(const float* x, int rows, int cols, int32_t* ou
 }
 
 extern "C" int lnb_op_get_rows_bf16(const uint16_t* emb, const int32_t* tokens, uint16_t* out, int S, int vocab, int dim) {
+  OpScope scope_;
   if (!emb || !tokens || !out || S <= 0 || vocab <= 0 || dim <= 0 || dim % 8) return fail(LNB_EINVAL, "bad argument");
   for (int i = 0; i < S; i++)
     if (tokens[i] < 0 || tokens[i] >= vocab) return fail(LNB_EINVAL, "token id %d out of range", tokens[i]);

@@ -73,3 +73,11 @@ def fill_host(args: dict, name: str, seed: int = SEED) -> np.ndarray:
 def batch_prompt(b: int) -> list[int]:
     """prompt of concurrent sequence b"""
     return [PROMPT_8[0]] + [(t + 977 * b) % 128000 for t in PROMPT_8[1:]]
+
+
+def shard_window(args: dict, name: str, tp_rank: int, tp_size: int) -> tuple[int, int, int, int]:
+    """(row0, col0, rows, cols) of the window of tensor `name` owned by a tensor-parallel rank"""
+    r0, c0, r, c = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    _capi.check(_capi.lib.lnb_tp_shard_window(C.byref(args_c(args)), name.encode(), tp_rank, tp_size,
+                                              C.byref(r0), C.byref(c0), C.byref(r), C.byref(c)))
+    return r0.value, c0.value, r.value, c.value

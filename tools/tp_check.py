@@ -1,0 +1,86 @@
+"""Tensor-parallel parity check, one process per GPU (torchrun).  Every rank uploads the FULL host
+tensors of the tiny synthetic model (the library slices them), runs prefill + decode steps, and
+rank 0 compares the gathered logits with (a) the oracle's TP emulation (rank-order fp32 sums) and
+(b) the single-GPU-order oracle.  Prints one JSON line; exits non-zero on failure.
+Usage: torchrun --nproc-per-node N tools/tp_check.py [tiny|8b]"""
+import ctypes
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import lnb_b200 as L
+from tests.helpers import host_tensors, oracle_model
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    raw = ctypes.create_string_buffer(128)
+    L._capi.check(L._capi.lib.lnb_nccl_unique_id(raw))
+    buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).cuda()
+dist.broadcast(buf, 0)
+nccl_id = bytes(buf.cpu().numpy().tobytes())
+
+which = sys.argv[1] if len(sys.argv) > 1 else "tiny"
+if which == "tiny":
+    args = dict(L.synth.TINY)
+    if world > 2:
+        args.update(n_heads=8 * (world // 2), n_kv_heads=world, dim=32 * 8 * (world // 2))   # keep >= 1 kv head / rank
+    args["ffn_dim"] = 512 * world // 2 if world > 2 else 512
+    args["vocab_size"] = 1024
+else:
+    args = dict(L.synth.LLAMA31_8B, n_layers=4)
+tensors = host_tensors(args, 77)
+res = {"world": world, "model": which, "ok": True}
+# one model (an NCCL unique id can bootstrap exactly one communicator), one session per mode
+m = L.model.LoadModelFromTensors(args, tensors, device=local, tp_rank=rank, tp_size=world, nccl_id=nccl_id)
+for mode, acc in (("strict", L._capi.LNB_ACC_STRICT), ("fast", L._capi.LNB_ACC_FAST)):
+    ctx = L.model.InferenceContext(m.Transformer, L.model.InferenceArgs(24), max_rows=8, acc_mode=acc)
+    prompt = np.array([5, 900, 33, 7, 64], np.int32) % args["vocab_size"]
+    outs, pos, cur = [], 0, prompt
+    for _ in range(5):
+        nxt, lg = m.Transformer.forward_argmax(ctx, cur, pos, want_logits="last")
+        outs.append((nxt, lg[0].copy()))
+        pos += len(cur)
+        cur = np.array([nxt], np.int32)
+    first = outs[0][0]
+    toks, ms, graphed = ctx.decode_run(first, len(prompt), 6, use_graph=True)
+    toks2, _, _ = ctx.decode_run(first, len(prompt), 6, use_graph=False)
+    if rank == 0:
+        om = oracle_model(args, tensors)
+        s_tp, s_1 = om.new_session(24), om.new_session(24)
+        pos, cur = 0, prompt
+        exact_tp, max_tp, max_1, agree = 0, 0.0, 0.0, 0
+        for nxt, lg in outs:
+            e_tp = s_tp.forward(cur, pos, all_rows=False, tp=world)[0]
+            e_1 = s_1.forward(cur, pos, all_rows=False)[0]
+            exact_tp += int(np.array_equal(e_tp, lg))
+            max_tp = max(max_tp, float(np.abs(e_tp - lg).max()))
+            max_1 = max(max_1, float(np.abs(e_1 - lg).max()))
+            agree += int(int(np.argmax(e_tp)) == nxt)
+            pos += len(cur)
+            cur = np.array([nxt], np.int32)
+        r = {"bit_exact_vs_oracle_tp_order": f"{exact_tp}/{len(outs)}", "max_abs_vs_oracle_tp_order": max_tp,
+             "max_abs_vs_single_gpu_order": max_1, "argmax_agree": f"{agree}/{len(outs)}",
+             "graph_decode_equals_stream_decode": bool(np.array_equal(toks, toks2)), "graph": bool(graphed),
+             "decode_tokens_follow_forward": bool(list(toks[:4]) == [o[0] for o in outs[1:5]])}
+        res[mode] = r
+        ok = r["graph_decode_equals_stream_decode"] and r["decode_tokens_follow_forward"] and max_tp <= 1e-2
+        if mode == "strict" and world == 2:
+            ok = ok and exact_tp == len(outs)      # a+b is commutative: NCCL's order cannot matter
+        res["ok"] = res["ok"] and ok
+        om.close()
+    ctx.close()
+    dist.barrier()
+m.Free()
+if rank == 0:
+    print(json.dumps(res), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if res["ok"] else 1)
