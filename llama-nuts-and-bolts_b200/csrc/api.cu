@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/lnb.h"
+#include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "kernels.cuh"
 
@@ -603,6 +604,32 @@ static int launch_simple(const Launcher& L, void (*kern)(Args...), dim3 grid, di
   return 0;
 }
 
+// tensor-core GEMM launcher (prefill): grid = (N/128, ceil(M/128))
+template <int EPI>
+static int launch_gemm_tc(const Launcher& L, const GemmTcParams& p) {
+  if (p.N % TC_BN || p.K % TC_KT) return fail(LNB_EINVAL, "gemm_tc: N %d must be a multiple of 128 and K %d of 64", p.N, p.K);
+  auto kern = gemm_tc_kernel<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.N / TC_BN, (p.M + TC_BM - 1) / TC_BM);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.stream = L.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = L.pdl ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, kern, p));
+  if (L.counter) (*L.counter)++;
+  return 0;
+}
+static bool tc_eligible(int M, int N, int K) { return M >= 32 && N % TC_BN == 0 && K % TC_KT == 0; }
+
 // ------------------------------------------------------------------------------------------
 // session
 __global__ void set_state_kernel(LnbDevState* st, int pos, int n_rows, int next_token, int reset_step) {
@@ -1125,6 +1152,22 @@ extern "C" int lnb_op_linear_bf16(const uint16_t* x, const uint16_t* w, uint16_t
   OPBUF(dx, xb); OPBUF(dw, wb); OPBUF(dout, ob);
   H2D(dx, x, xb); H2D(dw, w, wb);
   const bool tileable = (N % 16 == 0) && (K % 8 == 0) && (CfgF1::smem_bytes(K) <= kMaxSmem);
+  if (acc_mode == LNB_ACC_FAST && tc_eligible(S, N, K)) {
+    // prompt-sized inputs: tcgen05 tensor-core tiles (hardware accumulation order)
+    const int Mpad = (S + TC_BM - 1) / TC_BM * TC_BM;
+    OPBUF(dwp, wb); OPBUF(dx8, (size_t)Mpad * K * 2);
+    retile_kernel<<<grid_for((int64_t)N * K / 8), 256>>>(dw.as<uint16_t>(), K, 0, 0, N, K, dwp.as<uint16_t>(), 0, 1);
+    pack_x8_kernel<<<grid_for((int64_t)Mpad * K / 8), 256>>>(dx.as<uint16_t>(), K, S, Mpad, K, dx8.as<uint16_t>());
+    GemmTcParams g{};
+    g.X8 = dx8.as<uint16_t>(); g.W = dwp.as<uint16_t>(); g.M = S; g.N = N; g.K = K; g.out_bf16 = dout.as<uint16_t>(); g.ldo = N;
+    Launcher L{nullptr, false, nullptr};
+    int rc = launch_gemm_tc<TC_EPI_BF16>(L, g);
+    if (rc) return rc;
+    rc = op_finish();
+    if (rc) return rc;
+    D2H(out, dout, ob);
+    return 0;
+  }
   if (!tileable) {
     // shapes outside the panel layout (e.g. the reference's 2x3 . 4x3^T test): reference order, one thread per output
     linear_naive_kernel<<<(int)(((int64_t)S * N + 255) / 256), 256>>>(dx.as<uint16_t>(), dw.as<uint16_t>(), dout.as<uint16_t>(), S, K, N);

@@ -1,0 +1,222 @@
+// gemm_tc.cuh -- the prompt-processing projection: C[M,N] = X[M,K] . W[N,K]^T on the 5th-generation
+// tensor cores (tcgen05.mma, bf16 in, fp32 accumulate in TMEM), operands staged into shared memory by
+// the TMA engine's bulk-async copies.  Replaces ml.LinearTransformation
+// (src/ml/operations_impl.go:427-447 -> operations_lineartransform.go:145-207) when S is large
+// (prefill); the decode path (S = 1..8) uses gemv.cuh.
+//
+// Numerics: products are exact, accumulation is fp32 in the tensor core's own order, the result is
+// truncated to bf16 exactly like the reference's ToBFloat16 (:205).  The accumulation ORDER is the
+// hardware's, so this path belongs to LNB_ACC_FAST; LNB_ACC_STRICT keeps the sequential GEMV.
+//
+// Operand layouts (both "K-major, no swizzle" in UMMA terms: 8-row x 16-byte core matrices):
+//   W  : the same panel-major HBM layout the GEMV streams (16-row panels, gemv.cuh) -- each tcgen05.mma
+//        takes ONE panel as its N=16 B-operand:  core matrices 128 B apart along N (SBO), 256 B along K (LBO).
+//   X  : "X8" activations written by the preceding kernel: [M/8][K/8][8 rows][8 elems]; a 128-row A tile is
+//        16 groups of 8 rows:  LBO = 128 B (next k-chunk), SBO = KT*16 B (next 8 rows) inside a stage.
+// One CTA computes a 128 x 128 tile: 8 accumulators of 128 lanes x 16 columns in TMEM (128 columns).
+// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator,
+// 4..7 = epilogue (tcgen05.ld -> truncate -> global).
+#pragma once
+#include "common.cuh"
+
+namespace lnb {
+
+enum { TC_EPI_BF16 = 0, TC_EPI_RESID = 1, TC_EPI_F32TRUNC = 2, TC_EPI_F32RAW = 3 };
+
+struct GemmTcParams {
+  const uint16_t* X8;   // activations, X8 layout, M padded to a multiple of 128 (padding rows are zero)
+  const uint16_t* W;    // weights, 16-row panel-major
+  int M, N, K;          // M = valid rows; N % 128 == 0; K % 64 == 0
+  uint16_t* out_bf16;   // [M, ldo] row-major (TC_EPI_BF16 / TC_EPI_RESID)
+  float* out_f32;       // [M, ldo] (TC_EPI_F32TRUNC: f32(t(acc)); TC_EPI_F32RAW: acc)
+  const uint16_t* res;  // [M, ldo] residual (TC_EPI_RESID)
+  int ldo;
+};
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_KT = 64, TC_NS = 4;
+constexpr int TC_A_STAGE = TC_BM * TC_KT * 2;  // 16 KB
+constexpr int TC_B_STAGE = TC_BN * TC_KT * 2;  // 16 KB
+constexpr int TC_SMEM = 1024 + TC_NS * (TC_A_STAGE + TC_B_STAGE);
+constexpr int TC_THREADS = 256;
+
+// ---- tcgen05 wrappers (PTX as in /opt/skills/guides/blackwell_cuda_programming.md) ---------------
+LNB_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+LNB_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+LNB_DEVINL void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+LNB_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute/arch/mma_sm100_desc.hpp bit layout)
+LNB_DEVINL uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);            // start address  [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;  // leading byte offset [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;  // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  return d;                                           // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M x N
+LNB_DEVINL constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+LNB_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+LNB_DEVINL void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+LNB_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);  // [NS]
+  uint64_t* empty_bar = full_bar + TC_NS;                  // [NS]
+  uint64_t* acc_bar = empty_bar + TC_NS;                   // accumulators complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint8_t* sA = smem + 1024;
+  uint8_t* sB = sA + TC_NS * TC_A_STAGE;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * TC_BN;   // first weight row of this tile
+  const int m0 = blockIdx.y * TC_BM;   // first activation row
+  const int n_kt = p.K / TC_KT;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_NS; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();  // the activations come from the previous kernel (weights alone could go earlier)
+      const uint64_t pol_w = l2_policy_evict_first();
+      const uint64_t pol_x = l2_policy_evict_last();   // every N-tile re-reads the same activations
+      const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.X8);
+      const uint8_t* wb = reinterpret_cast<const uint8_t*>(p.W);
+      for (int t = 0; t < n_kt; t++) {
+        const int s = t % TC_NS;
+        mbar_wait(&empty_bar[s], (((uint32_t)(t / TC_NS)) & 1u) ^ 1u);
+        mbar_expect_tx(&full_bar[s], TC_A_STAGE + TC_B_STAGE);
+        const size_t k0 = (size_t)t * TC_KT;
+        // A: 16 groups of 8 rows, each (8 rows x KT) = KT*16 contiguous bytes in X8
+        for (int g = 0; g < TC_BM / 8; g++)
+          bulk_g2s(sA + (size_t)s * TC_A_STAGE + (size_t)g * (TC_KT * 16),
+                   xb + ((size_t)(m0 / 8 + g) * p.K + k0) * 16, TC_KT * 16, &full_bar[s], pol_x);
+        // B: 8 panels of 16 rows, each (16 rows x KT) = KT*32 contiguous bytes
+        for (int j = 0; j < TC_BN / 16; j++)
+          bulk_g2s(sB + (size_t)s * TC_B_STAGE + (size_t)j * (TC_KT * 32),
+                   wb + ((size_t)(n0 / 16 + j) * p.K + k0) * 32, TC_KT * 32, &full_bar[s], pol_w);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, 16);
+      for (int t = 0; t < n_kt; t++) {
+        const int s = t % TC_NS;
+        mbar_wait(&full_bar[s], ((uint32_t)(t / TC_NS)) & 1u);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + (size_t)s * TC_A_STAGE);
+        const uint32_t b_base = smem_u32(sB + (size_t)s * TC_B_STAGE);
+#pragma unroll
+        for (int k16 = 0; k16 < TC_KT / 16; k16++) {
+          const uint64_t a_desc = umma_desc(a_base + k16 * 256, 128, TC_KT * 16);
+#pragma unroll
+          for (int j = 0; j < TC_BN / 16; j++) {
+            const uint64_t b_desc = umma_desc(b_base + j * (TC_KT * 32) + k16 * 512, 256, 128);
+            umma_bf16(tmem_base + j * 16, a_desc, b_desc, idesc, (t > 0 || k16 > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(acc_bar);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global ================================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;     // activation row == TMEM lane
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    if (EPI == TC_EPI_RESID) pdl_wait();    // residual operand is written by an earlier kernel
+#pragma unroll 1
+    for (int j = 0; j < TC_BN / 16; j++) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), r);
+      if (row < p.M) {
+        const size_t o = (size_t)row * p.ldo + n0 + j * 16;
+        if (EPI == TC_EPI_BF16 || EPI == TC_EPI_RESID) {
+          uint32_t packed[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            float a = __uint_as_float(r[2 * e]), b = __uint_as_float(r[2 * e + 1]);
+            if (EPI == TC_EPI_RESID) {
+              const uint32_t rw = *reinterpret_cast<const uint32_t*>(p.res + o + 2 * e);
+              a = __fadd_rn(bf_lo(rw), trunc_bf(a));   // ml.Add(x, t(linear))  llamatransformer.go:232,248
+              b = __fadd_rn(bf_hi(rw), trunc_bf(b));
+            }
+            packed[e] = (uint32_t)f2bf(a) | ((uint32_t)f2bf(b) << 16);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + o);
+          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        } else {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + o);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            float4 v;
+            v.x = __uint_as_float(r[4 * e]); v.y = __uint_as_float(r[4 * e + 1]);
+            v.z = __uint_as_float(r[4 * e + 2]); v.w = __uint_as_float(r[4 * e + 3]);
+            if (EPI == TC_EPI_F32TRUNC) { v.x = trunc_bf(v.x); v.y = trunc_bf(v.y); v.z = trunc_bf(v.z); v.w = trunc_bf(v.w); }
+            dst[e] = v;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ---- layout helpers for the tensor-core path -----------------------------------------------------
+// row-major [M, K] bf16 -> X8 ([Mpad/8][K/8][8][8]); rows >= M are written as zeros
+__global__ void pack_x8_kernel(const uint16_t* __restrict__ src, int ld, int M, int Mpad, int K, uint16_t* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t chunks = K / 8, total = (int64_t)Mpad * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / chunks, ch = i % chunks;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < M) v = *reinterpret_cast<const uint4*>(src + row * ld + ch * 8);
+    *reinterpret_cast<uint4*>(dst + (((row / 8) * chunks + ch) * 8 + (row % 8)) * 8) = v;
+  }
+}
+
+}  // namespace lnb

@@ -185,3 +185,34 @@ def test_softmax_argmax_getrows(L):
     assert np.array_equal(got, emb[tok])
     with pytest.raises(L._capi.LnbError):
         ml.Fwd_Get_Rows(ml.Tensor(emb, ml.DT_BF16), ml.Tensor(np.array([64], np.int32), ml.DT_INT32))
+
+
+# ---- tensor-core prefill GEMM (tcgen05) behind ml.LinearTransformation ------------------------
+
+@pytest.mark.parametrize("S,K,N", [(32, 64, 128), (128, 128, 128), (200, 4096, 256), (256, 1024, 1024), (130, 14336, 128)])
+def test_linear_tensor_core_prefill(L, S, K, N):
+    """LNB_ACC_FAST with a prompt-sized S runs gemm_tc_kernel: same products, fp32 accumulation in the
+    tensor core's own order -> at most 1 bf16 ulp away from the reference order (reorder noise only)."""
+    rng = np.random.default_rng(S + K + N)
+    x = rand_bf16(rng, (S, K))
+    w = rand_bf16(rng, (N, K), 1.0 / math.sqrt(K))
+    ml = L.ml
+    ml.ACC_MODE = L._capi.LNB_ACC_FAST
+    try:
+        got = ml.LinearTransformation(ml.Tensor(x, ml.DT_BF16), ml.Tensor(w, ml.DT_BF16)).RawData
+    finally:
+        ml.ACC_MODE = L._capi.LNB_ACC_STRICT
+    exp = O.linear_bf16(x, w)
+    d = bf16_ulp_diff(got, exp)
+    big = np.abs(f32(exp)).reshape(exp.shape) > 1e-2
+    assert d[big].max(initial=0) <= 1, f"max ulp diff {d[big].max()}"
+    assert (d > 0).mean() < 0.03, f"{(d > 0).mean():.4f} of outputs differ"
+    # exactly representable case: small integers -> every accumulation order gives the same bits
+    xi = bf(rng.integers(-3, 4, size=(S, K)).astype(np.float32)).reshape(S, K)
+    wi = bf(rng.integers(-2, 3, size=(N, K)).astype(np.float32)).reshape(N, K)
+    ml.ACC_MODE = L._capi.LNB_ACC_FAST
+    try:
+        got = ml.LinearTransformation(ml.Tensor(xi, ml.DT_BF16), ml.Tensor(wi, ml.DT_BF16)).RawData
+    finally:
+        ml.ACC_MODE = L._capi.LNB_ACC_STRICT
+    assert np.array_equal(got, O.linear_bf16(xi, wi))
