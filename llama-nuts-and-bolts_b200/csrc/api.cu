@@ -663,6 +663,9 @@ struct lnb_session {
   uint16_t *x = nullptr, *h1 = nullptr, *q = nullptr, *o = nullptr, *mbuf = nullptr;
   float* part = nullptr;
   float* rs = nullptr;  // [max_rows] strict-mode RMSNorm scales
+  // tensor-core prefill path (LNB_ACC_FAST, S >= 32): X8-layout activations + raw GEMM outputs
+  uint16_t *xn8 = nullptr, *o8 = nullptr, *m8 = nullptr, *qkv_raw = nullptr, *gu = nullptr;
+  int mpad = 0;
   float* logits = nullptr;
   size_t logits_rows = 0;
   float* logits_full = nullptr;  // tp>1: gathered [rows, vocab]
@@ -689,6 +692,7 @@ extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int a
   if ((size_t)seq_len * 12 + (size_t)m->a.head_dim * 4 > 200 * 1024)
     return fail(LNB_EINVAL, "seq_len %d too long for the decode attention kernel", seq_len);
   CU(cudaSetDevice(m->device));
+  CU(cudaFuncSetAttribute(sdpa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   lnb_session* s = new lnb_session();
   s->m = m;
   s->seq_len = seq_len;
@@ -704,6 +708,14 @@ extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int a
   al((void**)&s->mbuf, (size_t)max_rows * m->ffn_l * 2);
   al((void**)&s->part, (size_t)max_rows * a.dim * 4);
   al((void**)&s->rs, (size_t)max_rows * 4);
+  if (max_rows >= 32 && acc_mode == LNB_ACC_FAST) {
+    s->mpad = (max_rows + TC_BM - 1) / TC_BM * TC_BM;
+    al((void**)&s->xn8, (size_t)s->mpad * a.dim * 2);
+    al((void**)&s->o8, (size_t)s->mpad * m->q_l * 2);
+    al((void**)&s->m8, (size_t)s->mpad * m->ffn_l * 2);
+    al((void**)&s->qkv_raw, (size_t)max_rows * (m->q_l + 2 * m->kv_l) * 2);
+    al((void**)&s->gu, (size_t)max_rows * 2 * m->ffn_l * 2);
+  }
   al((void**)&s->d_tokens, (size_t)max_rows * 4);
   al((void**)&s->st, sizeof(LnbDevState));
   al((void**)&s->d_tok_out, (size_t)seq_len * 4);
@@ -735,6 +747,7 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->graph) cudaGraphExecDestroy(s->graph);
   cudaFree(s->x); cudaFree(s->h1); cudaFree(s->q); cudaFree(s->o); cudaFree(s->mbuf); cudaFree(s->part); cudaFree(s->rs);
+  cudaFree(s->xn8); cudaFree(s->o8); cudaFree(s->m8); cudaFree(s->qkv_raw); cudaFree(s->gu);
   cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
@@ -814,7 +827,7 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
     }
     rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
                        (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
-                       s->o, m->q_l, pos_ptr, 0, S, S > 1 ? 1 : 0, mode == LNB_ACC_STRICT ? 1 : 0, scale);
+                       s->o, m->q_l, pos_ptr, 0, S, S > 1 ? 1 : 0, mode == LNB_ACC_STRICT ? 1 : 0, scale, 0);
     if (rc) return rc;
     {  // wo + residual                                             (:522, :232)
       GemvParams p{};
@@ -882,6 +895,133 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
   return 0;
 }
 
+// Prompt processing on the tensor cores (LNB_ACC_FAST, S >= 32): the same forward pass as
+// enqueue_forward with every projection as a tcgen05 GEMM (gemm_tc.cuh) and the elementwise steps
+// as separate memory-bound kernels that write the next GEMM's X8 operand directly.
+static bool forward_tc_ok(const lnb_session* s, int S) {
+  const lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  return s->mode == LNB_ACC_FAST && s->xn8 && S >= 32 && (m->q_l + 2 * m->kv_l) % TC_BN == 0 && a.dim % TC_BN == 0 &&
+         (2 * m->ffn_l) % TC_BN == 0 && a.dim % TC_KT == 0 && m->q_l % TC_KT == 0 && m->ffn_l % TC_KT == 0;
+}
+static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows) {
+  lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  Launcher L{s->stream, true, &s->launches};
+  const int32_t* pos_ptr = &s->st->pos;
+  const int Mpad = (S + TC_BM - 1) / TC_BM * TC_BM;
+  const int qkv_n = m->q_l + 2 * m->kv_l;
+  int rc;
+  if ((rc = launch_simple(L, gather_rows_kernel, dim3(S), dim3(256), 0, (const uint16_t*)m->tok_embd, (const int32_t*)s->d_tokens,
+                          (const LnbDevState*)s->st, s->x, a.dim)))
+    return rc;
+  const int n_layers = (s->layer_limit > 0 && s->layer_limit < a.n_layers) ? s->layer_limit : a.n_layers;
+  float scale = (float)sqrt((double)a.head_dim);
+  {
+    uint32_t u;
+    memcpy(&u, &scale, 4);
+    u &= 0xffff0000u;
+    memcpy(&scale, &u, 4);
+  }
+  const size_t sdpa_smem = (size_t)s->seq_len * 12 + (size_t)a.head_dim * 4;
+  const int ew_grid = m->sm_count * 8;
+  for (int l = 0; l < n_layers; l++) {
+    LayerW& W = m->layers[l];
+    if ((rc = launch_simple(L, rmsnorm_x8_kernel, dim3(Mpad), dim3(256), 0, (const uint16_t*)s->x, a.dim, (const uint16_t*)W.attn_norm,
+                            s->xn8, S, a.dim, a.norm_eps)))
+      return rc;
+    {
+      GemmTcParams g{};
+      g.X8 = s->xn8; g.W = W.wqkv; g.M = S; g.N = qkv_n; g.K = a.dim; g.out_bf16 = s->qkv_raw; g.ldo = qkv_n;
+      if ((rc = launch_gemm_tc<TC_EPI_BF16>(L, g))) return rc;
+    }
+    if ((rc = launch_simple(L, rope_kv_kernel, dim3(ew_grid), dim3(256), 0, (const uint16_t*)s->qkv_raw, qkv_n, s->q, m->q_l, m->kv_l,
+                            a.head_dim, s->ck[l], s->cv[l], (const float*)m->cis, pos_ptr, S)))
+      return rc;
+    if ((rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
+                            (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
+                            s->o8, m->q_l, pos_ptr, 0, S, 1, 0, scale, 1)))
+      return rc;
+    {
+      GemmTcParams g{};
+      g.X8 = s->o8; g.W = W.wo; g.M = S; g.N = a.dim; g.K = m->q_l; g.ldo = a.dim;
+      if (m->tp_size == 1) {
+        g.out_bf16 = s->h1; g.res = s->x;
+        if ((rc = launch_gemm_tc<TC_EPI_RESID>(L, g))) return rc;
+      } else {
+        g.out_f32 = s->part;
+        if ((rc = launch_gemm_tc<TC_EPI_F32RAW>(L, g))) return rc;
+        NC(g_nccl.AllReduce(s->part, s->part, (size_t)S * a.dim, ncclFloat32_, ncclSum_, m->comm, s->stream));
+        if ((rc = launch_simple(L, resid_from_f32_kernel, dim3(ew_grid), dim3(256), 0, (const float*)s->part, (const uint16_t*)s->x, s->h1,
+                                (int64_t)S * a.dim)))
+          return rc;
+      }
+    }
+    if ((rc = launch_simple(L, rmsnorm_x8_kernel, dim3(Mpad), dim3(256), 0, (const uint16_t*)s->h1, a.dim, (const uint16_t*)W.ffn_norm,
+                            s->xn8, S, a.dim, a.norm_eps)))
+      return rc;
+    {
+      GemmTcParams g{};
+      g.X8 = s->xn8; g.W = W.w13; g.M = S; g.N = 2 * m->ffn_l; g.K = a.dim; g.out_bf16 = s->gu; g.ldo = 2 * m->ffn_l;
+      if ((rc = launch_gemm_tc<TC_EPI_BF16>(L, g))) return rc;
+    }
+    if ((rc = launch_simple(L, swiglu_x8_kernel, dim3(ew_grid), dim3(256), 0, (const uint16_t*)s->gu, 2 * m->ffn_l,
+                            (const uint16_t*)m->silu_tab, s->m8, S, Mpad, m->ffn_l)))
+      return rc;
+    {
+      GemmTcParams g{};
+      g.X8 = s->m8; g.W = W.w2; g.M = S; g.N = a.dim; g.K = m->ffn_l; g.ldo = a.dim;
+      if (m->tp_size == 1) {
+        g.out_bf16 = s->x; g.res = s->h1;
+        if ((rc = launch_gemm_tc<TC_EPI_RESID>(L, g))) return rc;
+      } else {
+        g.out_f32 = s->part;
+        if ((rc = launch_gemm_tc<TC_EPI_F32RAW>(L, g))) return rc;
+        NC(g_nccl.AllReduce(s->part, s->part, (size_t)S * a.dim, ncclFloat32_, ncclSum_, m->comm, s->stream));
+        if ((rc = launch_simple(L, resid_from_f32_kernel, dim3(ew_grid), dim3(256), 0, (const float*)s->part, (const uint16_t*)s->h1, s->x,
+                                (int64_t)S * a.dim)))
+          return rc;
+      }
+    }
+  }
+  // LM head: all rows on the tensor cores when asked for (and the vocabulary shard tiles), then the
+  // last row through the GEMV, which also owns the greedy argmax (identical to the decode path)
+  if (logits_rows > 1 && m->vocab_l % TC_BN == 0) {
+    if ((rc = launch_simple(L, rmsnorm_x8_kernel, dim3(Mpad), dim3(256), 0, (const uint16_t*)s->x, a.dim, (const uint16_t*)m->norm, s->xn8, S,
+                            a.dim, a.norm_eps)))
+      return rc;
+    GemmTcParams g{};
+    g.X8 = s->xn8; g.W = m->output; g.M = S - 1; g.N = m->vocab_l; g.K = a.dim; g.out_f32 = s->logits; g.ldo = m->vocab_l;
+    if (S > 1 && (rc = launch_gemm_tc<TC_EPI_F32TRUNC>(L, g))) return rc;
+  } else if (logits_rows > 1 && S > 1) {
+    GemvParams p{};
+    p.W = m->output; p.N = m->vocab_l; p.K = a.dim; p.x = s->x; p.ldx = a.dim; p.norm_w = m->norm; p.eps = a.norm_eps;
+    p.out_f32 = s->logits; p.ldo = m->vocab_l; p.st = nullptr; p.argmax_row = -1;
+    if ((rc = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(L, s->mode, p, S - 1))) return rc;
+  }
+  {
+    GemvParams p{};
+    p.W = m->output; p.N = m->vocab_l; p.K = a.dim;
+    p.x = s->x + (size_t)(S - 1) * a.dim; p.ldx = a.dim; p.norm_w = m->norm; p.eps = a.norm_eps;
+    p.out_f32 = logits_rows > 0 ? s->logits + (logits_rows > 1 ? (size_t)(S - 1) * m->vocab_l : 0) : nullptr;
+    p.ldo = m->vocab_l; p.n_offset = m->tp_rank * m->vocab_l;
+    p.st = s->st; p.argmax_row = 0; p.publish = (m->tp_size == 1) ? 1 : 0; p.advance = 0; p.tok_out = s->d_tok_out;
+    if ((rc = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(L, s->mode, p, 1))) return rc;
+    if (m->tp_size > 1) {
+      NC(g_nccl.AllReduce(&s->st->amax_key, &s->st->amax_key, 1, ncclUint64_, ncclMax_, m->comm, s->stream));
+      if ((rc = launch_simple(L, publish_kernel, dim3(1), dim3(1), 0, s->st, 0, s->d_tok_out))) return rc;
+      if (logits_rows > 0) {
+        const int rows = logits_rows > 1 ? S : 1;
+        for (int r = 0; r < rows; r++)
+          NC(g_nccl.AllGather(s->logits + (size_t)r * m->vocab_l, s->logits_full + (size_t)r * a.vocab_size, m->vocab_l, ncclFloat32_,
+                              m->comm, s->stream));
+      }
+    }
+  }
+  s->last_rows = S;
+  return 0;
+}
+
 extern "C" int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int start_pos, float* logits, int all_rows,
                            int32_t* argmax_last) {
   if (!s || !tokens) return fail(LNB_EINVAL, "NULL argument");
@@ -905,7 +1045,7 @@ extern "C" int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int sta
   CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)S * 4, cudaMemcpyHostToDevice, s->stream));
   set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, S, -1, 0);
   s->launches++;
-  int rc = enqueue_forward(s, S, false, lrows, false, true);
+  int rc = forward_tc_ok(s, S) ? enqueue_forward_tc(s, S, lrows) : enqueue_forward(s, S, false, lrows, false, true);
   if (rc) return rc;
   if (lrows) {
     const float* src = (m->tp_size > 1) ? s->logits_full : s->logits;
@@ -1251,7 +1391,7 @@ extern "C" int lnb_op_attention_bf16(const uint16_t* q, const uint16_t* cache_k,
   memcpy(&f, &u, 4);
   sdpa_kernel<<<dim3(n_heads, S), 128, smem>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(), dv.as<uint16_t>(), n_kv * hd,
                                                 n_heads / n_kv, hd, dout.as<uint16_t>(), n_heads * hd, nullptr, T - S, S,
-                                                causal_mask ? 1 : 0, acc_mode == LNB_ACC_STRICT ? 1 : 0, f);
+                                                causal_mask ? 1 : 0, acc_mode == LNB_ACC_STRICT ? 1 : 0, f, 0);
   int rc = op_finish();
   if (rc) return rc;
   D2H(out, dout, qb);

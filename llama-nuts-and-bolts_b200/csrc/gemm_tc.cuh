@@ -219,4 +219,97 @@ __global__ void pack_x8_kernel(const uint16_t* __restrict__ src, int ld, int M, 
   }
 }
 
+// X8 address of element (row, col) of a [*, K] activation matrix
+LNB_DEVINL size_t x8_index(int row, int col, int K) {
+  return ((((size_t)(row >> 3) * (K >> 3) + (col >> 3)) << 3) + (row & 7)) * 8 + (col & 7);
+}
+
+// RMSNorm.Forward (llamatransformer.go:633-660) for the prefill path: one CTA (256 threads) per row,
+// LNB_ACC_FAST reduction order (256 interleaved partial sums, butterfly, then over warps -- the same
+// order as gemv.cuh's prologue), output written straight into the X8 layout the tensor-core GEMM reads.
+// Rows in [M, Mpad) are zero-filled (grid = Mpad).
+__global__ void __launch_bounds__(256) rmsnorm_x8_kernel(const uint16_t* __restrict__ x, int ldx, const uint16_t* __restrict__ w,
+                                                         uint16_t* __restrict__ out_x8, int M, int D, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float wsum[8];
+  __shared__ float rs;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  if (row >= M) {
+    for (int k = tid; k < D; k += 256) out_x8[x8_index(row, k, D)] = 0;
+    return;
+  }
+  const uint16_t* xr = x + (size_t)row * ldx;
+  float sum = 0.f;
+  for (int k = tid; k < D; k += 256) {
+    const float v = bf2f(xr[k]);
+    sum = __fmaf_rn(v, v, sum);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+  if ((tid & 31) == 0) wsum[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; i++) tot = __fadd_rn(tot, wsum[i]);
+    const float me = __fadd_rn(__fdiv_rn(tot, (float)D), eps);
+    rs = (float)(1.0 / sqrt((double)me));
+  }
+  __syncthreads();
+  const float r = rs;
+  for (int k = tid; k < D; k += 256) {
+    const float n1 = trunc_bf(__fmul_rn(bf2f(xr[k]), r));
+    out_x8[x8_index(row, k, D)] = f2bf(__fmul_rn(n1, bf2f(w[k])));
+  }
+}
+
+// After the fused wq|wk|wv GEMM of the prefill path: RoPE on q and k (f64 intermediates, see
+// gemv.cuh EPI_QKV_ROPE), q -> q_out [S, q_dim], k -> cacheK[pos0+s], v -> cacheV[pos0+s]
+// (llamatransformer.go:374-403).  One thread per (row, pair of columns).
+__global__ void rope_kv_kernel(const uint16_t* __restrict__ qkv, int ld, uint16_t* __restrict__ q_out, int q_dim, int kv_dim,
+                               int head_dim, uint16_t* __restrict__ cache_k, uint16_t* __restrict__ cache_v,
+                               const float* __restrict__ cis, const int32_t* __restrict__ pos_ptr, int S) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int pairs = (q_dim + 2 * kv_dim) / 2;
+  const int64_t total = (int64_t)S * pairs;
+  const int pos0 = *pos_ptr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i / pairs), n = (int)(i % pairs) * 2;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(qkv + (size_t)s * ld + n);
+    const int pos = pos0 + s;
+    if (n < q_dim + kv_dim) {
+      const int nn = (n < q_dim) ? n : n - q_dim;
+      const int ii = (nn % head_dim) >> 1;
+      const float2 fc = *reinterpret_cast<const float2*>(cis + ((size_t)pos * (head_dim / 2) + ii) * 2);
+      const double a = (double)bf_lo(w), b = (double)bf_hi(w), c = (double)fc.x, d = (double)fc.y;
+      const uint32_t o = (uint32_t)f2bf((float)(a * c - b * d)) | ((uint32_t)f2bf((float)(a * d + b * c)) << 16);
+      if (n < q_dim) *reinterpret_cast<uint32_t*>(q_out + (size_t)s * q_dim + n) = o;
+      else *reinterpret_cast<uint32_t*>(cache_k + (size_t)pos * kv_dim + nn) = o;
+    } else {
+      *reinterpret_cast<uint32_t*>(cache_v + (size_t)pos * kv_dim + (n - q_dim - kv_dim)) = w;
+    }
+  }
+}
+
+// After the fused w1|w3 GEMM (columns follow the panel-interleaved row order of the stacked matrix:
+// 16 gate columns, then the 16 up columns of the same rows): m = t( t(TABLE_SILU[g]) * u )
+// (llamatransformer.go:601-614), written in X8 layout for the w2 GEMM.  Rows in [M, Mpad) -> 0.
+__global__ void swiglu_x8_kernel(const uint16_t* __restrict__ gu, int ld, const uint16_t* __restrict__ silu_tab,
+                                 uint16_t* __restrict__ out_x8, int M, int Mpad, int ffn) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = (int64_t)Mpad * ffn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / ffn), c = (int)(i % ffn);
+    uint16_t o = 0;
+    if (row < M) {
+      const size_t base = (size_t)row * ld + (size_t)(c >> 4) * 32 + (c & 15);
+      const uint16_t sg = silu_tab[gu[base]];
+      o = f2bf(__fmul_rn(bf2f(sg), bf2f(gu[base + 16])));
+    }
+    out_x8[x8_index(row, c, ffn)] = o;
+  }
+}
+
 }  // namespace lnb

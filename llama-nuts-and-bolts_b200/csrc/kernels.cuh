@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(128) sdpa_kernel(const uint16_t* __restrict__ 
                                                    const uint16_t* __restrict__ cache_v, int kv_dim, int n_rep,
                                                    int hd, uint16_t* __restrict__ out, int ldo,
                                                    const int32_t* __restrict__ pos_ptr, int pos_fixed, int S,
-                                                   int causal, int strict, float scale_bf16_as_f32) {
+                                                   int causal, int strict, float scale_bf16_as_f32, int out_x8) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) uint8_t sm[];
@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(128) sdpa_kernel(const uint16_t* __restrict__ 
     const uint16_t* vc = cache_v + (size_t)h * hd + d;
     float acc = 0.f;
     for (int t = 0; t < Teff; t++) acc = __fmaf_rn(pf[t], bf2f(vc[(size_t)t * kv_dim]), acc);
-    out[(size_t)s * ldo + (size_t)H * hd + d] = f2bf(acc);  // Transpose(0,1)+Reshape :508-514
+    const int col = H * hd + d;  // Transpose(0,1)+Reshape :508-514
+    if (out_x8) out[((((size_t)(s >> 3) * (ldo >> 3) + (col >> 3)) << 3) + (s & 7)) * 8 + (col & 7)] = f2bf(acc);
+    else out[(size_t)s * ldo + col] = f2bf(acc);
   }
 }
 

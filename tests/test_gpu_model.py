@@ -182,3 +182,52 @@ def test_device_resident_decode_equals_host_loop(L, tiny, use_graph):
         assert ctx.launch_count() > 0
     finally:
         ctx.close()
+
+
+def test_prefill_tensor_core_path(L, tiny):
+    """LNB_ACC_FAST with a prompt of >= 32 tokens runs the tcgen05 prefill path (gemm_tc.cuh + X8
+    elementwise kernels); it must agree with the oracle up to fp32 summation order, and the KV cache it
+    leaves must drive the ordinary decode path."""
+    args, _, om, gm = tiny
+    rng = np.random.default_rng(40)
+    S, seq = 40, 48
+    toks = rng.integers(0, args["vocab_size"], size=seq).astype(np.int32)
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(seq), max_rows=S, acc_mode=L._capi.LNB_ACC_FAST)
+    osess = om.new_session(seq)
+    try:
+        exp, tr = osess.forward(toks[:S], 0, all_rows=True, trace=True)
+        nxt, got = gm.Transformer.forward_argmax(ctx, toks[:S], 0, want_logits="all")
+        assert got.shape == exp.shape
+        assert np.abs(got - exp).max() <= 1e-2
+        assert (np.argmax(got, -1) == np.argmax(exp, -1)).mean() >= 0.95
+        assert nxt == int(np.argmax(got[-1]))
+        from tests.helpers import f32
+        r_got, r_exp = f32(ctx.residual(S)).reshape(S, -1), f32(tr[-1]).reshape(S, -1)
+        assert np.abs(r_got - r_exp).max() <= 2.0 ** -5 * max(1.0, np.abs(r_exp).max())   # a few bf16 ulps of the largest entry
+        assert (r_got != r_exp).mean() < 0.3
+        for layer in range(args["n_layers"]):
+            ok, ov = osess.cache(layer)
+            for got_c, exp_c in ((ctx.CacheK(layer).RawData[:S], ok[:S]), (ctx.CacheV(layer).RawData[:S], ov[:S])):
+                g_, e_ = f32(got_c).reshape(-1), f32(exp_c).reshape(-1)
+                assert np.abs(g_ - e_).max() <= 2.0 ** -6 * max(1.0, np.abs(e_).max())
+        for pos in range(S, S + 4):     # decode continues on the cache written by the prefill kernels
+            e = osess.forward(toks[pos:pos + 1], pos)
+            g = gm.Transformer.Forward(ctx, L.ml.Tensor(toks[pos:pos + 1], L.ml.DT_INT32), pos).RawData
+            assert np.abs(g - e).max() <= 1e-2
+    finally:
+        ctx.close(); osess.close()
+
+
+def test_prefill_strict_stays_bit_exact_for_long_prompts(L, tiny):
+    args, _, om, gm = tiny
+    rng = np.random.default_rng(41)
+    S = 36
+    toks = rng.integers(0, args["vocab_size"], size=S).astype(np.int32)
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(40), max_rows=S, acc_mode=L._capi.LNB_ACC_STRICT)
+    osess = om.new_session(40)
+    try:
+        exp = osess.forward(toks, 0, all_rows=True)
+        got = gm.Transformer.Forward(ctx, L.ml.Tensor(toks, L.ml.DT_INT32), 0).RawData
+        assert np.array_equal(got, exp)
+    finally:
+        ctx.close(); osess.close()
