@@ -133,6 +133,15 @@ int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int start_pos,
 int lnb_decode_run(lnb_session* s, int32_t first_token, int start_pos, int n_steps, int use_graph,
                    int32_t* tokens_out, float* ms_out);
 
+/* Fused collective for tensor-parallel decode: instead of ncclAllReduce after Wo / w2, every rank's GEMV
+ * epilogue stores its fp32 partials straight into all peers' memory over NVLink and a small kernel
+ * reduces the N slots in rank order (bit-identical on every rank).  Setup: every rank exports the 64-byte
+ * CUDA IPC handle of its session region, the host gathers the tp_size handles, every rank imports them
+ * (index = rank).  Sessions must be created and driven identically on all ranks.  Without this call the
+ * session uses NCCL (exactly one all-reduce after Wo and one after w2, as north_star prescribes). */
+int lnb_session_p2p_export(lnb_session* s, void* handle64);
+int lnb_session_p2p_import(lnb_session* s, const void* handles /* tp_size x 64 bytes */, int n);
+
 /* debugging / parity probes */
 enum { LNB_BUF_RESIDUAL = 0, LNB_BUF_CACHE_K = 1, LNB_BUF_CACHE_V = 2, LNB_BUF_LOGITS = 3 };
 /* copies a device buffer of the session to host: RESIDUAL [S,dim] bf16 (after the last

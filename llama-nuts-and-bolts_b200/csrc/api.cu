@@ -640,6 +640,11 @@ __global__ void set_state_kernel(LnbDevState* st, int pos, int n_rows, int next_
   if (next_token >= 0) st->next_token = next_token;
   if (reset_step) st->step = 0;
 }
+__global__ void set_p2p_epoch_kernel(LnbDevState* st, uint32_t e) {
+  st->ar_epoch = e;
+  st->ar_done = 0;
+  st->ar_done2 = 0;
+}
 // tensor-parallel tail of the LM head: decode the reduced key, advance the decode state
 __global__ void publish_kernel(LnbDevState* st, int advance, int32_t* tok_out) {
   pdl_launch_dependents();
@@ -666,6 +671,12 @@ struct lnb_session {
   // tensor-core prefill path (LNB_ACC_FAST, S >= 32): X8-layout activations + raw GEMM outputs
   uint16_t *xn8 = nullptr, *o8 = nullptr, *m8 = nullptr, *qkv_raw = nullptr, *gu = nullptr;
   int mpad = 0;
+  // peer-memory all-reduce (tp_size > 1, optional): own region + the peers' mapped regions
+  uint8_t* p2p_region = nullptr;
+  size_t p2p_bytes = 0;
+  void* p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  LnbP2P p2p{};
+  bool p2p_ready = false;
   float* logits = nullptr;
   size_t logits_rows = 0;
   float* logits_full = nullptr;  // tp>1: gathered [rows, vocab]
@@ -748,6 +759,9 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   if (s->graph) cudaGraphExecDestroy(s->graph);
   cudaFree(s->x); cudaFree(s->h1); cudaFree(s->q); cudaFree(s->o); cudaFree(s->mbuf); cudaFree(s->part); cudaFree(s->rs);
   cudaFree(s->xn8); cudaFree(s->o8); cudaFree(s->m8); cudaFree(s->qkv_raw); cudaFree(s->gu);
+  for (int r = 0; r < 8; r++)
+    if (s->p2p_peer[r]) cudaIpcCloseMemHandle(s->p2p_peer[r]);
+  cudaFree(s->p2p_region);
   cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
@@ -756,6 +770,62 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
+  return 0;
+}
+
+// Peer-memory all-reduce setup.  Step 1 on every rank: export (allocates this session's region and
+// returns its 64-byte CUDA IPC handle).  The host gathers the tp_size handles (any channel).  Step 2 on
+// every rank: import all handles (index = rank).  From then on the decode path of this session pushes
+// its Wo / w2 partials and argmax keys straight into the peers' memory instead of calling NCCL.
+extern "C" int lnb_session_p2p_export(lnb_session* s, void* handle64) {
+  if (!s || !handle64) return fail(LNB_EINVAL, "NULL argument");
+  lnb_model* m = s->m;
+  if (m->tp_size < 2 || m->tp_size > 8) return fail(LNB_EINVAL, "peer all-reduce needs 2..8 ranks");
+  CU(cudaSetDevice(m->device));
+  if (!s->p2p_region) {
+    const size_t slot = (size_t)s->max_rows * m->a.dim;
+    s->p2p_bytes = LNB_P2P_DATA_OFFSET + (size_t)2 * m->tp_size * slot * sizeof(float);
+    CU(cudaMalloc((void**)&s->p2p_region, s->p2p_bytes));
+    CU(cudaMemset(s->p2p_region, 0, s->p2p_bytes));
+    CU(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, s->p2p_region));
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+extern "C" int lnb_session_p2p_import(lnb_session* s, const void* handles, int n) {
+  if (!s || !handles) return fail(LNB_EINVAL, "NULL argument");
+  lnb_model* m = s->m;
+  if (n != m->tp_size) return fail(LNB_EINVAL, "expected %d handles, got %d", m->tp_size, n);
+  if (!s->p2p_region) return fail(LNB_ESTATE, "call lnb_session_p2p_export first");
+  CU(cudaSetDevice(m->device));
+  std::lock_guard<std::mutex> lk(s->mu);
+  for (int r = 0; r < n; r++) {
+    uint8_t* base;
+    if (r == m->tp_rank) {
+      base = s->p2p_region;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const uint8_t*)handles + (size_t)r * 64, 64);
+      void* q = nullptr;
+      CU(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+      s->p2p_peer[r] = q;
+      base = (uint8_t*)q;
+    }
+    s->p2p.flag[r] = reinterpret_cast<uint32_t*>(base);
+    s->p2p.data[r] = reinterpret_cast<float*>(base + LNB_P2P_DATA_OFFSET);
+  }
+  s->p2p.rank = m->tp_rank;
+  s->p2p.n = n;
+  s->p2p.slot_elems = s->max_rows * m->a.dim;
+  // epochs start at 1 (flags are zero-initialised)
+  set_p2p_epoch_kernel<<<1, 1, 0, s->stream>>>(s->st, 1u);
+  CU(cudaStreamSynchronize(s->stream));
+  if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+  s->graph_tried = false;
+  s->p2p_ready = true;
   return 0;
 }
 
@@ -836,12 +906,20 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
         p.out_bf16 = s->h1; p.res = s->x;
         if ((rc = launch_gemv<PRO_PLAIN, EPI_RESID>(L, mode, p, S))) return rc;
       } else {
-        p.out_f32 = s->part;
-        if ((rc = launch_gemv<PRO_PLAIN, EPI_F32RAW>(L, mode, p, S))) return rc;
-        NC(g_nccl.AllReduce(s->part, s->part, (size_t)S * a.dim, ncclFloat32_, ncclSum_, m->comm, s->stream));
-        if ((rc = launch_simple(L, resid_from_f32_kernel, dim3(std::min(148, (S * a.dim + 255) / 256)), dim3(256), 0,
-                                (const float*)s->part, (const uint16_t*)s->x, s->h1, (int64_t)S * a.dim)))
-          return rc;
+        if (s->p2p_ready) {
+          p.p2p = s->p2p; p.st = s->st;
+          if ((rc = launch_gemv<PRO_PLAIN, EPI_P2P>(L, mode, p, S))) return rc;
+          if ((rc = launch_simple(L, p2p_reduce_resid_kernel, dim3(std::min(16, (S * a.dim + 255) / 256)), dim3(256), 0, s->p2p, s->st,
+                                  (const uint16_t*)s->x, s->h1, S * a.dim)))
+            return rc;
+        } else {
+          p.out_f32 = s->part;
+          if ((rc = launch_gemv<PRO_PLAIN, EPI_F32RAW>(L, mode, p, S))) return rc;
+          NC(g_nccl.AllReduce(s->part, s->part, (size_t)S * a.dim, ncclFloat32_, ncclSum_, m->comm, s->stream));
+          if ((rc = launch_simple(L, resid_from_f32_kernel, dim3(std::min(148, (S * a.dim + 255) / 256)), dim3(256), 0,
+                                  (const float*)s->part, (const uint16_t*)s->x, s->h1, (int64_t)S * a.dim)))
+            return rc;
+        }
       }
     }
     if ((rc = strict_scale(s->h1, S))) return rc;
@@ -859,12 +937,20 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
         p.out_bf16 = s->x; p.res = s->h1;
         if ((rc = launch_gemv<PRO_PLAIN, EPI_RESID>(L, mode, p, S))) return rc;
       } else {
-        p.out_f32 = s->part;
-        if ((rc = launch_gemv<PRO_PLAIN, EPI_F32RAW>(L, mode, p, S))) return rc;
-        NC(g_nccl.AllReduce(s->part, s->part, (size_t)S * a.dim, ncclFloat32_, ncclSum_, m->comm, s->stream));
-        if ((rc = launch_simple(L, resid_from_f32_kernel, dim3(std::min(148, (S * a.dim + 255) / 256)), dim3(256), 0,
-                                (const float*)s->part, (const uint16_t*)s->h1, s->x, (int64_t)S * a.dim)))
-          return rc;
+        if (s->p2p_ready) {
+          p.p2p = s->p2p; p.st = s->st;
+          if ((rc = launch_gemv<PRO_PLAIN, EPI_P2P>(L, mode, p, S))) return rc;
+          if ((rc = launch_simple(L, p2p_reduce_resid_kernel, dim3(std::min(16, (S * a.dim + 255) / 256)), dim3(256), 0, s->p2p, s->st,
+                                  (const uint16_t*)s->h1, s->x, S * a.dim)))
+            return rc;
+        } else {
+          p.out_f32 = s->part;
+          if ((rc = launch_gemv<PRO_PLAIN, EPI_F32RAW>(L, mode, p, S))) return rc;
+          NC(g_nccl.AllReduce(s->part, s->part, (size_t)S * a.dim, ncclFloat32_, ncclSum_, m->comm, s->stream));
+          if ((rc = launch_simple(L, resid_from_f32_kernel, dim3(std::min(148, (S * a.dim + 255) / 256)), dim3(256), 0,
+                                  (const float*)s->part, (const uint16_t*)s->h1, s->x, (int64_t)S * a.dim)))
+            return rc;
+        }
       }
     }
   }
@@ -883,8 +969,12 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
     p.advance = advance ? 1 : 0; p.tok_out = s->d_tok_out;
     if ((rc = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(L, mode, p, rows))) return rc;
     if (m->tp_size > 1) {
-      NC(g_nccl.AllReduce(&s->st->amax_key, &s->st->amax_key, 1, ncclUint64_, ncclMax_, m->comm, s->stream));
-      if ((rc = launch_simple(L, publish_kernel, dim3(1), dim3(1), 0, s->st, advance ? 1 : 0, s->d_tok_out))) return rc;
+      if (s->p2p_ready) {
+        if ((rc = launch_simple(L, p2p_argmax_kernel, dim3(1), dim3(32), 0, s->p2p, s->st, advance ? 1 : 0, s->d_tok_out))) return rc;
+      } else {
+        NC(g_nccl.AllReduce(&s->st->amax_key, &s->st->amax_key, 1, ncclUint64_, ncclMax_, m->comm, s->stream));
+        if ((rc = launch_simple(L, publish_kernel, dim3(1), dim3(1), 0, s->st, advance ? 1 : 0, s->d_tok_out))) return rc;
+      }
       if (logits_rows > 0)
         for (int r = 0; r < rows; r++)
           NC(g_nccl.AllGather(s->logits + (size_t)r * m->vocab_l, s->logits_full + (size_t)r * a.vocab_size, m->vocab_l,

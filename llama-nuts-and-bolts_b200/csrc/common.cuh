@@ -102,4 +102,21 @@ struct LnbDevState {
   int32_t next_token;            // greedy token of the last row
   int32_t step;                  // decode-run step counter
   int32_t pad;
+  uint32_t ar_epoch;             // sequence number of the next peer all-reduce (same on every rank)
+  uint32_t ar_done;              // CTAs of the producing kernel that have pushed their partials
+  uint32_t ar_done2;             // CTAs of the reducing kernel that have finished
+  uint32_t pad2;
 };
+
+// One-shot all-reduce over NVLink peer memory (tensor-parallel decode).  Every rank owns a region
+//   [flags: 2 parities x 8 ranks x u32][pad to 4096 B][data: 2 parities x N ranks x slot_elems f32]
+// that all peers map (CUDA IPC).  Producer: each CTA stores its fp32 partials straight into slot
+// `rank` of EVERY peer's region (st.global over NVLink), the last CTA raises flag[parity][rank] = epoch on
+// every peer.  Reducer: waits for the N local flags, sums the N local slots IN RANK ORDER (so every rank
+// gets the same bits), applies the residual add.  parity = epoch & 1 double-buffers the region.
+struct LnbP2P {
+  float* data[8];      // peer r's data base (device pointers valid on this GPU)
+  uint32_t* flag[8];   // peer r's flag base
+  int rank, n, slot_elems;
+};
+#define LNB_P2P_DATA_OFFSET 4096

@@ -33,7 +33,8 @@ enum {
   EPI_RESID = 2,     // out_bf16[m,n] = t(res[m,n] + t(acc))                    (ml.Add, llamatransformer.go:232,248)
   EPI_LOGITS = 3,    // out_f32[m,n] = f32(t(acc)); greedy argmax of row n_rows-1 (llamatransformer.go:170-175; inference.go:207-216)
   EPI_QKV_ROPE = 4,  // q -> rope -> q_out ; k -> rope -> cacheK[pos+m] ; v -> cacheV[pos+m]   (llamatransformer.go:374-403)
-  EPI_SWIGLU = 5     // panels alternate w1/w3: out[m,i] = t( silu_tab[t(g)] * t(u) )          (llamatransformer.go:601-614)
+  EPI_SWIGLU = 5,    // panels alternate w1/w3: out[m,i] = t( silu_tab[t(g)] * t(u) )          (llamatransformer.go:601-614)
+  EPI_P2P = 6        // tensor-parallel partial pushed into every peer's all-reduce slot over NVLink (fused collective)
 };
 
 struct GemvParams {
@@ -68,6 +69,7 @@ struct GemvParams {
   int32_t* tok_out;        // device [n_steps] (advance mode)
   const int32_t* pos_ptr;  // == &st->pos (kept separate so op-level calls can pass a plain int buffer)
   int m_off;               // index of activation row 0 of this launch inside the forward call (row blocking)
+  LnbP2P p2p;              // EPI_P2P: peer regions (st must be set: epoch / done counters live in the device state)
 };
 
 template <int TN, int KS, int MB, int KT, int NST>
@@ -99,6 +101,13 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
     if (valid) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(v);
   } else if (EPI == EPI_F32RAW) {
     if (valid) p.out_f32[(size_t)em * p.ldo + n] = v;
+  } else if (EPI == EPI_P2P) {
+    if (valid) {
+      const uint32_t par = p.st->ar_epoch & 1u;
+      const size_t off = ((size_t)(par * p.p2p.n + p.p2p.rank)) * p.p2p.slot_elems + (size_t)(p.m_off + em) * p.ldo + n;
+#pragma unroll 1
+      for (int r = 0; r < p.p2p.n; r++) p.p2p.data[r][off] = v;   // 32 lanes -> 128 contiguous bytes per peer
+    }
   } else if (EPI == EPI_RESID) {
     if (valid) {
       float a = trunc_bf(v);
@@ -155,6 +164,23 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
       const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
       p.out_bf16[(size_t)em * p.ldo + (size_t)(panel >> 1) * 16 + (er & 15)] = f2bf(mm);
     }
+  }
+}
+
+// EPI_P2P: called by one thread per CTA after that CTA's partials are fenced; the last CTA of the grid
+// raises this rank's flag on every peer.
+LNB_DEVINL void p2p_signal(const GemvParams& p) {
+  const unsigned int done = atomicAdd(&p.st->ar_done, 1u);
+  if (done == gridDim.x - 1) {
+    p.st->ar_done = 0;
+    __threadfence_system();
+    const uint32_t epoch = p.st->ar_epoch;
+    const uint32_t par = epoch & 1u;
+    for (int r = 0; r < p.p2p.n; r++) {
+      volatile uint32_t* f = p.p2p.flag[r] + par * 8 + p.p2p.rank;
+      *f = epoch;
+    }
+    __threadfence_system();
   }
 }
 
@@ -422,6 +448,11 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
       named_bar_sync(1, NCONS);
       if (c == 0) logits_publish(p);
     }
+  }
+  if (EPI == EPI_P2P) {
+    __threadfence_system();              // this CTA's peer stores are visible system-wide ...
+    named_bar_sync(1, NCONS);
+    if (c == 0) p2p_signal(p);           // ... before the last CTA raises the flags
   }
 }
 

@@ -183,6 +183,89 @@ __global__ void resid_from_f32_kernel(const float* __restrict__ sum, const uint1
 }
 
 // ------------------------------------------------------------------------------------------
+// Reducer of the peer-memory all-reduce (see LnbP2P in common.cuh): waits until all N ranks have
+// pushed their partials of this epoch, sums the N local slots in rank order and applies the residual:
+// out = t( res + t( ((p0 + p1) + p2) + ... ) )   (ml.Add after Wo / w2, llamatransformer.go:232,248).
+// The last CTA advances the epoch.  L1 is bypassed for peer-written data (ld.global.cg).
+__global__ void __launch_bounds__(256) p2p_reduce_resid_kernel(LnbP2P pp, LnbDevState* st, const uint16_t* __restrict__ res,
+                                                               uint16_t* __restrict__ out, int n_elems) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t epoch = st->ar_epoch;
+  const uint32_t par = epoch & 1u;
+  if (threadIdx.x < pp.n) {
+    volatile uint32_t* f = pp.flag[pp.rank] + par * 8 + threadIdx.x;
+    while (*f != epoch) __nanosleep(32);
+  }
+  __syncthreads();
+  __threadfence_system();
+  const float* base = pp.data[pp.rank] + (size_t)par * pp.n * pp.slot_elems;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += gridDim.x * blockDim.x) {
+    float sum = __ldcg(base + i);
+    for (int r = 1; r < pp.n; r++) sum = __fadd_rn(sum, __ldcg(base + (size_t)r * pp.slot_elems + i));
+    out[i] = f2bf(__fadd_rn(bf2f(res[i]), trunc_bf(sum)));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(&st->ar_done2, 1u);
+    if (done == gridDim.x - 1) {
+      st->ar_done2 = 0;
+      st->ar_epoch = epoch + 1;
+      __threadfence();
+    }
+  }
+}
+
+// Tensor-parallel greedy argmax over peer memory: every rank pushes its (value, index) key to all peers,
+// takes the maximum of the N keys (same on every rank), publishes the token and advances the decode state.
+// One warp.
+__global__ void p2p_argmax_kernel(LnbP2P pp, LnbDevState* st, int advance, int32_t* tok_out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t epoch = st->ar_epoch;
+  const uint32_t par = epoch & 1u;
+  const int lane = threadIdx.x;
+  const unsigned long long mykey = st->amax_key;
+  const size_t off = ((size_t)(par * pp.n + pp.rank)) * pp.slot_elems;
+  if (lane < pp.n) {
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(pp.data[lane] + off);
+    *dst = mykey;
+    __threadfence_system();
+    volatile uint32_t* f = pp.flag[lane] + par * 8 + pp.rank;
+    *f = epoch;
+    __threadfence_system();
+  }
+  __syncwarp();
+  unsigned long long key = LNB_ARGMAX_EMPTY;
+  if (lane < pp.n) {
+    volatile uint32_t* f = pp.flag[pp.rank] + par * 8 + lane;
+    while (*f != epoch) __nanosleep(32);
+    __threadfence_system();
+    const unsigned long long* src =
+        reinterpret_cast<const unsigned long long*>(pp.data[pp.rank] + ((size_t)(par * pp.n + lane)) * pp.slot_elems);
+    key = __ldcg(src);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if (lane == 0) {
+    const int32_t tok = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+    st->next_token = tok;
+    st->amax_key = LNB_ARGMAX_EMPTY;
+    st->done_ctr = 0;
+    st->ar_epoch = epoch + 1;
+    if (advance) {
+      if (tok_out) tok_out[st->step] = tok;
+      st->step += 1;
+      st->pos += 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic-shape kernels behind the op-level C-ABI (any S, K, N): one thread per output,
 // reference order.  Used when a shape does not meet the panel GEMV's constraints
 // (e.g. the reference's own 2x3 . 4x3^T golden case).

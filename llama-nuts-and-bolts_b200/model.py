@@ -186,6 +186,15 @@ class InferenceContext:
                                       ptr(toks, _capi.i32p), C.byref(ms)))
         return toks, ms.value, bool(rc)
 
+    def enable_peer_allreduce(self, all_gather_bytes):
+        """Switch this session from NCCL to the fused peer-memory all-reduce.  `all_gather_bytes(b: bytes) ->
+        list[bytes]` must return every rank's contribution ordered by rank (e.g. torch.distributed)."""
+        buf = C.create_string_buffer(64)
+        check(lib.lnb_session_p2p_export(self.h, buf))
+        handles = all_gather_bytes(buf.raw)
+        blob = b"".join(handles)
+        check(lib.lnb_session_p2p_import(self.h, C.create_string_buffer(blob, len(blob)), len(handles)))
+
     def bench_kernel(self, kind: int, reps: int = 3):
         """(ms per launch, algorithmic weight bytes per launch, launches timed) -- bench.py roofline"""
         ms, nb, nl = C.c_float(0), C.c_int64(0), C.c_int32(0)

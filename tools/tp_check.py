@@ -40,8 +40,18 @@ tensors = host_tensors(args, 77)
 res = {"world": world, "model": which, "ok": True}
 # one model (an NCCL unique id can bootstrap exactly one communicator), one session per mode
 m = L.model.LoadModelFromTensors(args, tensors, device=local, tp_rank=rank, tp_size=world, nccl_id=nccl_id)
-for mode, acc in (("strict", L._capi.LNB_ACC_STRICT), ("fast", L._capi.LNB_ACC_FAST)):
+def all_gather_bytes(b: bytes):
+    t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+
+for mode, acc, p2p in (("strict", L._capi.LNB_ACC_STRICT, False), ("fast", L._capi.LNB_ACC_FAST, False),
+                       ("strict_p2p", L._capi.LNB_ACC_STRICT, True), ("fast_p2p", L._capi.LNB_ACC_FAST, True)):
     ctx = L.model.InferenceContext(m.Transformer, L.model.InferenceArgs(24), max_rows=8, acc_mode=acc)
+    if p2p:
+        ctx.enable_peer_allreduce(all_gather_bytes)
     prompt = np.array([5, 900, 33, 7, 64], np.int32) % args["vocab_size"]
     outs, pos, cur = [], 0, prompt
     for _ in range(5):
@@ -74,6 +84,8 @@ for mode, acc in (("strict", L._capi.LNB_ACC_STRICT), ("fast", L._capi.LNB_ACC_F
         ok = r["graph_decode_equals_stream_decode"] and r["decode_tokens_follow_forward"] and max_tp <= 1e-2
         if mode == "strict" and world == 2:
             ok = ok and exact_tp == len(outs)      # a+b is commutative: NCCL's order cannot matter
+        if mode == "strict_p2p":
+            ok = ok and exact_tp == len(outs)      # the peer all-reduce sums in rank order by construction
         res["ok"] = res["ok"] and ok
         om.close()
     ctx.close()
