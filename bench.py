@@ -158,6 +158,9 @@ def main():
     ap.add_argument("--acc", default=os.environ.get("LNB_BENCH_ACC", "auto"), choices=["auto", "fast", "strict"],
                     help="accumulation order: strict = the reference's k order (bit-identical logits; headline at 1 GPU), "
                          "fast = interleaved partial sums (tensor-parallel runs reorder the sums anyway)")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="tensor-parallel reduction after Wo / w2: fused peer-memory all-reduce over NVLink (default) "
+                         "or ncclAllReduce; the other one is timed too and reported under other_collective")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-decode", type=int, default=6, help="decode steps in the cpu_baseline sample")
     a = ap.parse_args()
@@ -207,8 +210,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_gather_bytes(b: bytes):
+        t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
     # ---- device-resident arm (`value`) -----------------------------------------------------
     ctx = L.model.InferenceContext(tf, L.model.InferenceArgs(SEQ_LEN), max_rows=8, acc_mode=acc)
+    if world > 1 and a.collective == "p2p":
+        ctx.enable_peer_allreduce(all_gather_bytes)
 
     def one_generation():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -303,6 +314,23 @@ def main():
         e2e["fused_call_tokens_per_s"] = round((len(st) - 1) / sum(st[1:]), 2)
         model.Vocabulary.StopTokenIds = saved_stop
 
+    # ---- the other collective, same session parameters (TP only) ----------------------------------
+    other_coll = None
+    if world > 1:
+        c4 = L.model.InferenceContext(tf, L.model.InferenceArgs(SEQ_LEN), max_rows=8, acc_mode=acc)
+        if a.collective != "p2p":
+            c4.enable_peer_allreduce(all_gather_bytes)
+        f4, _ = tf.forward_argmax(c4, prompt, 0)
+        c4.decode_run(f4, N_PROMPT, N_DECODE, use_graph=True)
+        f4, _ = tf.forward_argmax(c4, prompt, 0)
+        barrier()
+        t4, ms4, _ = c4.decode_run(f4, N_PROMPT, N_DECODE, use_graph=True)
+        tt = torch.tensor([ms4], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        other_coll = {"collective": "nccl" if a.collective == "p2p" else "p2p", "value": round(N_DECODE / (float(tt[0]) / 1e3), 2),
+                      "unit": "tokens/s", "tokens_equal": [int(f4)] + [int(t) for t in t4] == gen_tokens}
+        c4.close()
+
     # ---- strict-mode number (bit-exact arm) for the record ------------------------------------
     other = None
     if world == 1:
@@ -356,6 +384,7 @@ def main():
                                    "over KV cache (BASELINE.json configs[1]%s)" % ("" if world == 1 else f", tensor-parallel x{world}"),
                        "seq_len": SEQ_LEN, "prompt_tokens": N_PROMPT, "decode_steps_per_generation": N_DECODE,
                        "parallelism": "tp%d" % world, "acc": a.acc, "cuda_graph": bool(graphed),
+                       "collective": (a.collective if world > 1 else None),
                        "l2": "working set 15 GB per token >> 126 MB L2 (no flush needed)",
                        "stop_id_generated": stop_hit},
             "decode_ms_per_token": round(dec_ms / (a.steps * N_DECODE), 4),
@@ -363,7 +392,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline, "roofline_step": roofline_step, "kernels_alone": kern,
-            "e2e": e2e, "other_acc_mode": other, "cpu_baseline": cpu, "parity": parity,
+            "e2e": e2e, "other_acc_mode": other, "other_collective": other_coll, "cpu_baseline": cpu, "parity": parity,
             "model_load_s": round(t_load, 2),
         }
         print(json.dumps(line), flush=True)

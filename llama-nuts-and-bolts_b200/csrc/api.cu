@@ -784,7 +784,7 @@ extern "C" int lnb_session_p2p_export(lnb_session* s, void* handle64) {
   CU(cudaSetDevice(m->device));
   if (!s->p2p_region) {
     const size_t slot = (size_t)s->max_rows * m->a.dim;
-    s->p2p_bytes = LNB_P2P_DATA_OFFSET + (size_t)2 * m->tp_size * slot * sizeof(float);
+    s->p2p_bytes = (size_t)2 * m->tp_size * slot * sizeof(uint2);
     CU(cudaMalloc((void**)&s->p2p_region, s->p2p_bytes));
     CU(cudaMemset(s->p2p_region, 0, s->p2p_bytes));
     CU(cudaDeviceSynchronize());
@@ -814,13 +814,12 @@ extern "C" int lnb_session_p2p_import(lnb_session* s, const void* handles, int n
       s->p2p_peer[r] = q;
       base = (uint8_t*)q;
     }
-    s->p2p.flag[r] = reinterpret_cast<uint32_t*>(base);
-    s->p2p.data[r] = reinterpret_cast<float*>(base + LNB_P2P_DATA_OFFSET);
+    s->p2p.data[r] = reinterpret_cast<uint2*>(base);
   }
   s->p2p.rank = m->tp_rank;
   s->p2p.n = n;
   s->p2p.slot_elems = s->max_rows * m->a.dim;
-  // epochs start at 1 (flags are zero-initialised)
+  // epochs start at 1 (the region is zero-initialised, so no word carries a live epoch)
   set_p2p_epoch_kernel<<<1, 1, 0, s->stream>>>(s->st, 1u);
   CU(cudaStreamSynchronize(s->stream));
   if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }

@@ -103,20 +103,20 @@ struct LnbDevState {
   int32_t step;                  // decode-run step counter
   int32_t pad;
   uint32_t ar_epoch;             // sequence number of the next peer all-reduce (same on every rank)
-  uint32_t ar_done;              // CTAs of the producing kernel that have pushed their partials
+  uint32_t ar_done;              // (unused)
   uint32_t ar_done2;             // CTAs of the reducing kernel that have finished
   uint32_t pad2;
 };
 
-// One-shot all-reduce over NVLink peer memory (tensor-parallel decode).  Every rank owns a region
-//   [flags: 2 parities x 8 ranks x u32][pad to 4096 B][data: 2 parities x N ranks x slot_elems f32]
-// that all peers map (CUDA IPC).  Producer: each CTA stores its fp32 partials straight into slot
-// `rank` of EVERY peer's region (st.global over NVLink), the last CTA raises flag[parity][rank] = epoch on
-// every peer.  Reducer: waits for the N local flags, sums the N local slots IN RANK ORDER (so every rank
-// gets the same bits), applies the residual add.  parity = epoch & 1 double-buffers the region.
+// One-shot all-reduce over NVLink peer memory (tensor-parallel decode), "LL" style: every value travels
+// as an 8-byte word {fp32 bits, epoch}; an 8-byte store is delivered atomically, so the receiver needs no
+// fence, flag or barrier -- it polls the word until its epoch field matches.  Every rank owns a region
+//   [2 parities][N ranks][slot_elems] x 8 bytes
+// that all peers map (CUDA IPC).  Producer (GEMV epilogue): each thread stores its fp32 partial into slot
+// `rank` of EVERY peer's region (st.global.v2 over NVLink).  Reducer: polls the N local slots and adds them
+// IN RANK ORDER (every rank gets the same bits), then applies the residual add.
+// parity = epoch & 1 double-buffers the region (a rank can be at most one all-reduce ahead of a peer).
 struct LnbP2P {
-  float* data[8];      // peer r's data base (device pointers valid on this GPU)
-  uint32_t* flag[8];   // peer r's flag base
+  uint2* data[8];      // peer r's region base (device pointers valid on this GPU)
   int rank, n, slot_elems;
 };
-#define LNB_P2P_DATA_OFFSET 4096

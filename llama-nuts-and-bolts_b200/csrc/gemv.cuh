@@ -103,10 +103,12 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
     if (valid) p.out_f32[(size_t)em * p.ldo + n] = v;
   } else if (EPI == EPI_P2P) {
     if (valid) {
-      const uint32_t par = p.st->ar_epoch & 1u;
-      const size_t off = ((size_t)(par * p.p2p.n + p.p2p.rank)) * p.p2p.slot_elems + (size_t)(p.m_off + em) * p.ldo + n;
-#pragma unroll 1
-      for (int r = 0; r < p.p2p.n; r++) p.p2p.data[r][off] = v;   // 32 lanes -> 128 contiguous bytes per peer
+      const uint32_t epoch = p.st->ar_epoch;
+      const size_t off = ((size_t)((epoch & 1u) * p.p2p.n + p.p2p.rank)) * p.p2p.slot_elems + (size_t)(p.m_off + em) * p.ldo + n;
+      const uint2 w = make_uint2(__float_as_uint(v), epoch);
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (r < p.p2p.n) p.p2p.data[r][off] = w;   // 32 lanes -> 256 contiguous bytes per peer, one 8-byte word each
     }
   } else if (EPI == EPI_RESID) {
     if (valid) {
@@ -164,23 +166,6 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
       const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
       p.out_bf16[(size_t)em * p.ldo + (size_t)(panel >> 1) * 16 + (er & 15)] = f2bf(mm);
     }
-  }
-}
-
-// EPI_P2P: called by one thread per CTA after that CTA's partials are fenced; the last CTA of the grid
-// raises this rank's flag on every peer.
-LNB_DEVINL void p2p_signal(const GemvParams& p) {
-  const unsigned int done = atomicAdd(&p.st->ar_done, 1u);
-  if (done == gridDim.x - 1) {
-    p.st->ar_done = 0;
-    __threadfence_system();
-    const uint32_t epoch = p.st->ar_epoch;
-    const uint32_t par = epoch & 1u;
-    for (int r = 0; r < p.p2p.n; r++) {
-      volatile uint32_t* f = p.p2p.flag[r] + par * 8 + p.p2p.rank;
-      *f = epoch;
-    }
-    __threadfence_system();
   }
 }
 
@@ -448,11 +433,6 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
       named_bar_sync(1, NCONS);
       if (c == 0) logits_publish(p);
     }
-  }
-  if (EPI == EPI_P2P) {
-    __threadfence_system();              // this CTA's peer stores are visible system-wide ...
-    named_bar_sync(1, NCONS);
-    if (c == 0) p2p_signal(p);           // ... before the last CTA raises the flags
   }
 }
 

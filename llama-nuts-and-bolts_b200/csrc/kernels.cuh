@@ -183,26 +183,29 @@ __global__ void resid_from_f32_kernel(const float* __restrict__ sum, const uint1
 }
 
 // ------------------------------------------------------------------------------------------
-// Reducer of the peer-memory all-reduce (see LnbP2P in common.cuh): waits until all N ranks have
-// pushed their partials of this epoch, sums the N local slots in rank order and applies the residual:
+// Reducer of the peer-memory all-reduce (see LnbP2P in common.cuh): polls the N local slots until the
+// words of this epoch have arrived, adds them in rank order and applies the residual:
 // out = t( res + t( ((p0 + p1) + p2) + ... ) )   (ml.Add after Wo / w2, llamatransformer.go:232,248).
-// The last CTA advances the epoch.  L1 is bypassed for peer-written data (ld.global.cg).
+// The last CTA advances the epoch (local counter only).
+LNB_DEVINL uint2 ld_volatile_u2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __global__ void __launch_bounds__(256) p2p_reduce_resid_kernel(LnbP2P pp, LnbDevState* st, const uint16_t* __restrict__ res,
                                                                uint16_t* __restrict__ out, int n_elems) {
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t epoch = st->ar_epoch;
-  const uint32_t par = epoch & 1u;
-  if (threadIdx.x < pp.n) {
-    volatile uint32_t* f = pp.flag[pp.rank] + par * 8 + threadIdx.x;
-    while (*f != epoch) __nanosleep(32);
-  }
-  __syncthreads();
-  __threadfence_system();
-  const float* base = pp.data[pp.rank] + (size_t)par * pp.n * pp.slot_elems;
+  const uint2* base = pp.data[pp.rank] + (size_t)(epoch & 1u) * pp.n * pp.slot_elems;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += gridDim.x * blockDim.x) {
-    float sum = __ldcg(base + i);
-    for (int r = 1; r < pp.n; r++) sum = __fadd_rn(sum, __ldcg(base + (size_t)r * pp.slot_elems + i));
+    float sum = 0.f;
+    for (int r = 0; r < pp.n; r++) {
+      const uint2* src = base + (size_t)r * pp.slot_elems + i;
+      uint2 w = ld_volatile_u2(src);
+      while (w.y != epoch) w = ld_volatile_u2(src);
+      sum = (r == 0) ? __uint_as_float(w.x) : __fadd_rn(sum, __uint_as_float(w.x));
+    }
     out[i] = f2bf(__fadd_rn(bf2f(res[i]), trunc_bf(sum)));
   }
   __syncthreads();
@@ -217,34 +220,27 @@ __global__ void __launch_bounds__(256) p2p_reduce_resid_kernel(LnbP2P pp, LnbDev
   }
 }
 
-// Tensor-parallel greedy argmax over peer memory: every rank pushes its (value, index) key to all peers,
-// takes the maximum of the N keys (same on every rank), publishes the token and advances the decode state.
-// One warp.
+// Tensor-parallel greedy argmax over peer memory: every rank pushes its 64-bit (value, index) key as two
+// LL words to all peers, takes the maximum of the N keys (same on every rank), publishes the token and
+// advances the decode state.  One warp.
 __global__ void p2p_argmax_kernel(LnbP2P pp, LnbDevState* st, int advance, int32_t* tok_out) {
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t epoch = st->ar_epoch;
-  const uint32_t par = epoch & 1u;
   const int lane = threadIdx.x;
   const unsigned long long mykey = st->amax_key;
-  const size_t off = ((size_t)(par * pp.n + pp.rank)) * pp.slot_elems;
+  const size_t myoff = ((size_t)((epoch & 1u) * pp.n + pp.rank)) * pp.slot_elems;
   if (lane < pp.n) {
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(pp.data[lane] + off);
-    *dst = mykey;
-    __threadfence_system();
-    volatile uint32_t* f = pp.flag[lane] + par * 8 + pp.rank;
-    *f = epoch;
-    __threadfence_system();
+    pp.data[lane][myoff] = make_uint2((uint32_t)(mykey & 0xffffffffull), epoch);
+    pp.data[lane][myoff + 1] = make_uint2((uint32_t)(mykey >> 32), epoch);
   }
-  __syncwarp();
   unsigned long long key = LNB_ARGMAX_EMPTY;
   if (lane < pp.n) {
-    volatile uint32_t* f = pp.flag[pp.rank] + par * 8 + lane;
-    while (*f != epoch) __nanosleep(32);
-    __threadfence_system();
-    const unsigned long long* src =
-        reinterpret_cast<const unsigned long long*>(pp.data[pp.rank] + ((size_t)(par * pp.n + lane)) * pp.slot_elems);
-    key = __ldcg(src);
+    const uint2* src = pp.data[pp.rank] + ((size_t)((epoch & 1u) * pp.n + lane)) * pp.slot_elems;
+    uint2 lo = ld_volatile_u2(src), hi = ld_volatile_u2(src + 1);
+    while (lo.y != epoch) lo = ld_volatile_u2(src);
+    while (hi.y != epoch) hi = ld_volatile_u2(src + 1);
+    key = ((unsigned long long)hi.x << 32) | lo.x;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
