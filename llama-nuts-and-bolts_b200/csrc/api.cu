@@ -686,6 +686,8 @@ struct lnb_session {
   int32_t* d_tok_out = nullptr;
   int32_t* h_pin = nullptr;
   int layer_limit = 0;
+  bool sdpa_smem_decode = false;  // the whole K/V history of one KV head fits in shared memory
+  size_t sdpa_decode_smem = 0;
   int64_t launches = 0;
   cudaGraphExec_t graph = nullptr;
   bool graph_tried = false;
@@ -710,6 +712,15 @@ extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int a
   s->max_rows = max_rows;
   s->mode = acc_mode;
   const lnb_model_args& a = m->a;
+  {
+    const int n_rep = a.n_heads / a.n_kv_heads;
+    const size_t need = (size_t)seq_len * ((a.head_dim + 8) + a.head_dim) * 2 + (size_t)n_rep * ((size_t)a.head_dim * 4 + (size_t)seq_len * 12 + 5 * 8) + 256;
+    if (need <= 200 * 1024 && n_rep <= 8 && a.head_dim <= 128 && a.head_dim % 8 == 0) {
+      s->sdpa_smem_decode = true;
+      s->sdpa_decode_smem = need;
+      CU(cudaFuncSetAttribute(sdpa_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+  }
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   auto al = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
   al((void**)&s->x, (size_t)max_rows * a.dim * 2);
@@ -894,9 +905,16 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
       p.cache_k = s->ck[l]; p.cache_v = s->cv[l]; p.cis = m->cis; p.pos_ptr = pos_ptr;
       if ((rc = launch_gemv<PRO_RMSNORM, EPI_QKV_ROPE>(L, mode, p, S))) return rc;
     }
-    rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
-                       (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
-                       s->o, m->q_l, pos_ptr, 0, S, S > 1 ? 1 : 0, mode == LNB_ACC_STRICT ? 1 : 0, scale, 0);
+    if (S == 1 && s->sdpa_smem_decode) {
+      const int n_rep = a.n_heads / a.n_kv_heads;
+      rc = launch_simple(L, sdpa_decode_kernel, dim3(m->kv_l / a.head_dim), dim3(128 * n_rep), s->sdpa_decode_smem, (const uint16_t*)s->q,
+                         (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, n_rep, a.head_dim, s->o, pos_ptr, s->seq_len,
+                         mode == LNB_ACC_STRICT ? 1 : 0, scale);
+    } else {
+      rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
+                         (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
+                         s->o, m->q_l, pos_ptr, 0, S, S > 1 ? 1 : 0, mode == LNB_ACC_STRICT ? 1 : 0, scale, 0);
+    }
     if (rc) return rc;
     {  // wo + residual                                             (:522, :232)
       GemvParams p{};

@@ -172,6 +172,117 @@ __global__ void __launch_bounds__(128) sdpa_kernel(const uint16_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// Decode attention (S == 1), one CTA per KV head serving its n_rep query heads (GQA: K and V are read
+// once per KV head instead of once per query head; attentionRepeatKV :529-559 is pure indexing).
+// Same arithmetic, truncation points and summation orders as sdpa_kernel.  The K / V rows of EARLIER
+// positions do not depend on the previous kernel, so they are staged into shared memory with cp.async
+// BEFORE griddepcontrol.wait (overlapping the QKV projection's tail); only the row of the current
+// position and q are fetched after it.  K rows are padded to hd+8 elements (bank-conflict-free
+// 128-bit reads for "one thread = one key").  block = 128 * n_rep threads (thread = (query head, key or d)).
+// dyn smem = T_max * ((hd + 8) + hd) * 2  +  n_rep * (hd * 4 + T_max * 12) + 64
+LNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+LNB_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(1024) sdpa_decode_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ cache_k,
+                                                           const uint16_t* __restrict__ cache_v, int kv_dim, int n_rep, int hd,
+                                                           uint16_t* __restrict__ out, const int32_t* __restrict__ pos_ptr,
+                                                           int T_max, int strict, float scale_bf16_as_f32) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int kstride = hd + 8;
+  uint16_t* sK = reinterpret_cast<uint16_t*>(sm);                       // [T_max][hd + 8]
+  uint16_t* sV = sK + (size_t)T_max * kstride;                          // [T_max][hd]
+  double* sE = reinterpret_cast<double*>(sV + (size_t)T_max * hd);      // [n_rep][T_max]
+  float* sP = reinterpret_cast<float*>(sE + (size_t)n_rep * T_max);     // [n_rep][T_max]
+  float* sQ = sP + (size_t)n_rep * T_max;                               // [n_rep][hd]
+  double* sZ = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sQ + (size_t)n_rep * hd) + 15) & ~(uintptr_t)15);  // [n_rep][4] + [n_rep]
+  const int h = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int hh = tid / 128, tt = tid % 128;
+  const int cpr = hd / 8;  // 16-byte chunks per row
+
+  pdl_launch_dependents();
+  // positions < pos were written by earlier decode steps; pos itself (read below) is only known after the
+  // wait, but the cache is append-only, so rows [0, pos_old] are a safe prefix: stage rows [0, T_max) that
+  // exist is NOT known yet -> read pos first (cheap), rows < pos are immutable for this step
+  // (with programmatic dependent launch this kernel may start before the kernel that advances pos has
+  //  finished: pos_early may be stale; it is only used as a hint -- rows >= min(pos_early, pos) are
+  //  (re)loaded after the wait)
+  const int pos_early = max(0, min(*reinterpret_cast<const volatile int32_t*>(pos_ptr), T_max - 1));
+  for (int i = tid; i < pos_early * cpr; i += nthr) {
+    const int t = i / cpr, c = i % cpr;
+    cp_async16(sK + (size_t)t * kstride + c * 8, cache_k + (size_t)t * kv_dim + (size_t)h * hd + c * 8);
+    cp_async16(sV + (size_t)t * hd + c * 8, cache_v + (size_t)t * kv_dim + (size_t)h * hd + c * 8);
+  }
+  pdl_wait();
+  const int pos = *pos_ptr;
+  const int T = pos + 1;
+  const int lo = min(pos_early, pos);
+  for (int i = tid; i < (T - lo) * cpr; i += nthr) {  // the row(s) written by this step's QKV kernel (+ any not staged yet)
+    const int t = lo + i / cpr, c = i % cpr;
+    cp_async16(sK + (size_t)t * kstride + c * 8, cache_k + (size_t)t * kv_dim + (size_t)h * hd + c * 8);
+    cp_async16(sV + (size_t)t * hd + c * 8, cache_v + (size_t)t * kv_dim + (size_t)h * hd + c * 8);
+  }
+  for (int i = tid; i < n_rep * hd; i += nthr) sQ[i] = bf2f(q[(size_t)(h * n_rep) * hd + i]);
+  cp_async_wait_all();
+  __syncthreads();
+
+  // scores: sc_t = t( t(sum_seq_d q_d k_td) / t(sqrt(hd)) ); e_t = exp_f64(sc_t)      (:459-464, :484-490)
+  const float* qh = sQ + hh * hd;
+  for (int t = tt; t < T; t += 128) {
+    const uint16_t* kr = sK + (size_t)t * kstride;
+    float acc = 0.f;
+    for (int d = 0; d < hd; d += 8) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
+      acc = __fmaf_rn(qh[d + 0], bf_lo(kv.x), acc);
+      acc = __fmaf_rn(qh[d + 1], bf_hi(kv.x), acc);
+      acc = __fmaf_rn(qh[d + 2], bf_lo(kv.y), acc);
+      acc = __fmaf_rn(qh[d + 3], bf_hi(kv.y), acc);
+      acc = __fmaf_rn(qh[d + 4], bf_lo(kv.z), acc);
+      acc = __fmaf_rn(qh[d + 5], bf_hi(kv.z), acc);
+      acc = __fmaf_rn(qh[d + 6], bf_lo(kv.w), acc);
+      acc = __fmaf_rn(qh[d + 7], bf_hi(kv.w), acc);
+    }
+    float sc = trunc_bf(acc);
+    sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
+    sE[(size_t)hh * T_max + t] = exp((double)sc);
+  }
+  __syncthreads();
+  // Z = sum_seq_t e_t (f64): reference order (strict) or a tree (fast)
+  double* eh = sE + (size_t)hh * T_max;
+  if (strict) {
+    if (tt == 0) {
+      double z = 0.0;
+      for (int t = 0; t < T; t++) z = __dadd_rn(z, eh[t]);
+      sZ[n_rep * 4 + hh] = z;
+    }
+  } else {
+    double z = 0.0;
+    for (int t = tt; t < T; t += 128) z = __dadd_rn(z, eh[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, o));
+    if ((tt & 31) == 0) sZ[hh * 4 + (tt >> 5)] = z;
+  }
+  __syncthreads();
+  if (!strict && tt == 0)
+    sZ[n_rep * 4 + hh] = __dadd_rn(__dadd_rn(__dadd_rn(sZ[hh * 4 + 0], sZ[hh * 4 + 1]), sZ[hh * 4 + 2]), sZ[hh * 4 + 3]);
+  __syncthreads();
+  const double Z = sZ[n_rep * 4 + hh];
+  float* ph = sP + (size_t)hh * T_max;
+  for (int t = tt; t < T; t += 128) ph[t] = trunc_bf((float)__ddiv_rn(eh[t], Z));   // t(f32(e/Z))  :493
+  __syncthreads();
+  // o_d = t( sum_seq_t p_t v_td )                                                      (:504)
+  if (tt < hd) {
+    const uint16_t* vc = sV + tt;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int t = 0; t < T; t++) acc = __fmaf_rn(ph[t], bf2f(vc[(size_t)t * hd]), acc);
+    out[(size_t)(h * n_rep + hh) * hd + tt] = f2bf(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Tensor-parallel tail of Wo / w2: h[m,n] = t( res[m,n] + t(sum[m,n]) ) after the fp32
 // allreduce (ml.Add, llamatransformer.go:232,248, on the reduced partials).
 __global__ void resid_from_f32_kernel(const float* __restrict__ sum, const uint16_t* __restrict__ res,
