@@ -284,6 +284,8 @@ def main():
     e2e = None
     if True:  # every rank runs the same host loop in lock step (the greedy token is identical on all ranks)
         eng = L.inference.InferenceEngine(model, L.model.InferenceArgs(SEQ_LEN), acc_mode=acc)
+        if world > 1 and a.collective == "p2p":
+            eng.context_hook = lambda c: c.enable_peer_allreduce(all_gather_bytes)   # same collective as the device arm
         saved_stop = model.Vocabulary.StopTokenIds
         model.Vocabulary.StopTokenIds = () if stop_hit else saved_stop
         for _ in range(2):

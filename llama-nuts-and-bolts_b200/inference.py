@@ -22,10 +22,14 @@ class InferenceEngine:
         self.logFn = logFn
         self.acc_mode = acc_mode
         self.max_rows = max_rows
+        self.context_hook = None  # optional callable(InferenceContext), e.g. to enable the peer all-reduce
 
     def CreateInferenceContext(self) -> "model_mod.InferenceContext":  # inference.go:256-258
-        return model_mod.InferenceContext(self.model.Transformer, self.inferenceArgs, self.logFn,
-                                          max_rows=self.max_rows, acc_mode=self.acc_mode)
+        ctx = model_mod.InferenceContext(self.model.Transformer, self.inferenceArgs, self.logFn,
+                                         max_rows=self.max_rows, acc_mode=self.acc_mode)
+        if self.context_hook is not None:
+            self.context_hook(ctx)
+        return ctx
 
     def GenerateTokens(self, promptTokens, use_reference_api: bool = False, step_times: list | None = None):
         """Generator over (state, token id) exactly like generatedTokensCh.
