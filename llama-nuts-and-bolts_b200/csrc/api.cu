@@ -607,7 +607,7 @@ static int launch_simple(const Launcher& L, void (*kern)(Args...), dim3 grid, di
 // tensor-core GEMM launcher (prefill): grid = (N/128, ceil(M/128))
 template <int EPI>
 static int launch_gemm_tc(const Launcher& L, const GemmTcParams& p) {
-  if (p.N % TC_BN || p.K % TC_KT) return fail(LNB_EINVAL, "gemm_tc: N %d must be a multiple of 128 and K %d of 64", p.N, p.K);
+  if (p.N % TC_BN || p.K % TC_KT) return fail(LNB_EINVAL, "gemm_tc: N %d and K %d must be multiples of 128", p.N, p.K);
   auto kern = gemm_tc_kernel<EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -615,7 +615,7 @@ static int launch_gemm_tc(const Launcher& L, const GemmTcParams& p) {
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.N / TC_BN, (p.M + TC_BM - 1) / TC_BM);
+  cfg.gridDim = dim3((p.M + TC_BM - 1) / TC_BM, p.N / TC_BN);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TC_SMEM;
   cfg.stream = L.stream;
@@ -706,6 +706,7 @@ extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int a
     return fail(LNB_EINVAL, "seq_len %d too long for the decode attention kernel", seq_len);
   CU(cudaSetDevice(m->device));
   CU(cudaFuncSetAttribute(sdpa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute(sdpa_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
   lnb_session* s = new lnb_session();
   s->m = m;
   s->seq_len = seq_len;
@@ -1045,9 +1046,14 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows) {
     if ((rc = launch_simple(L, rope_kv_kernel, dim3(ew_grid), dim3(256), 0, (const uint16_t*)s->qkv_raw, qkv_n, s->q, m->q_l, m->kv_l,
                             a.head_dim, s->ck[l], s->cv[l], (const float*)m->cis, pos_ptr, S)))
       return rc;
-    if ((rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
-                            (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
-                            s->o8, m->q_l, pos_ptr, 0, S, 1, 0, scale, 1)))
+    if (a.head_dim == SP_HD) {
+      if ((rc = launch_simple(L, sdpa_prefill_kernel, dim3(m->q_l / a.head_dim, (S + SP_QB - 1) / SP_QB), dim3(256), (size_t)SP_SMEM,
+                              (const uint16_t*)s->q, m->q_l, (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l,
+                              a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale)))
+        return rc;
+    } else if ((rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
+                                   (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
+                                   s->o8, m->q_l, pos_ptr, 0, S, 1, 0, scale, 1)))
       return rc;
     {
       GemmTcParams g{};
@@ -1496,6 +1502,21 @@ extern "C" int lnb_op_attention_bf16(const uint16_t* q, const uint16_t* cache_k,
   memcpy(&u, &f, 4);
   u &= 0xffff0000u;
   memcpy(&f, &u, 4);
+  if (acc_mode == LNB_ACC_FAST && S > 1 && causal_mask && hd == SP_HD && (n_heads * hd) % 128 == 0) {
+    // the prefill path's tiled two-pass kernel (writes the X8 operand of the Wo GEMM; unpacked here)
+    const int Mpad = (S + 127) / 128 * 128;
+    OPBUF(d8, (size_t)Mpad * n_heads * hd * 2); OPBUF(dpos, 16);
+    CU(cudaMemset(dpos.p, 0, 16));
+    CU(cudaFuncSetAttribute(sdpa_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+    sdpa_prefill_kernel<<<dim3(n_heads, (S + SP_QB - 1) / SP_QB), 256, SP_SMEM>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(),
+                                                                                  dv.as<uint16_t>(), n_kv * hd, n_heads / n_kv,
+                                                                                  d8.as<uint16_t>(), n_heads * hd, dpos.as<int32_t>(), S, f);
+    unpack_x8_kernel<<<grid_for((int64_t)S * n_heads * hd / 8), 256>>>(d8.as<uint16_t>(), S, n_heads * hd, dout.as<uint16_t>(), n_heads * hd);
+    int rc2 = op_finish();
+    if (rc2) return rc2;
+    D2H(out, dout, qb);
+    return 0;
+  }
   sdpa_kernel<<<dim3(n_heads, S), 128, smem>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(), dv.as<uint16_t>(), n_kv * hd,
                                                 n_heads / n_kv, hd, dout.as<uint16_t>(), n_heads * hd, nullptr, T - S, S,
                                                 causal_mask ? 1 : 0, acc_mode == LNB_ACC_STRICT ? 1 : 0, f, 0);

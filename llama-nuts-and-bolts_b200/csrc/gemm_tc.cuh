@@ -11,8 +11,9 @@
 // Operand layouts (both "K-major, no swizzle" in UMMA terms: 8-row x 16-byte core matrices):
 //   W  : the same panel-major HBM layout the GEMV streams (16-row panels, gemv.cuh) -- each tcgen05.mma
 //        takes ONE panel as its N=16 B-operand:  core matrices 128 B apart along N (SBO), 256 B along K (LBO).
-//   X  : "X8" activations written by the preceding kernel: [M/8][K/8][8 rows][8 elems]; a 128-row A tile is
-//        16 groups of 8 rows:  LBO = 128 B (next k-chunk), SBO = KT*16 B (next 8 rows) inside a stage.
+//   X  : "X8" activations written by the preceding kernel, tile-major: [M/128][K/128] tiles of
+//        [16 row-groups][16 k-chunks][8 rows][8 elems] = 32 KB contiguous -> ONE bulk copy per stage;
+//        LBO = 128 B (next k-chunk), SBO = 2048 B (next 8 rows).
 // One CTA computes a 128 x 128 tile: 8 accumulators of 128 lanes x 16 columns in TMEM (128 columns).
 // Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator,
 // 4..7 = epilogue (tcgen05.ld -> truncate -> global).
@@ -33,9 +34,9 @@ struct GemmTcParams {
   int ldo;
 };
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_KT = 64, TC_NS = 4;
-constexpr int TC_A_STAGE = TC_BM * TC_KT * 2;  // 16 KB
-constexpr int TC_B_STAGE = TC_BN * TC_KT * 2;  // 16 KB
+constexpr int TC_BM = 128, TC_BN = 128, TC_KT = 128, TC_NS = 3;
+constexpr int TC_A_STAGE = TC_BM * TC_KT * 2;  // 32 KB
+constexpr int TC_B_STAGE = TC_BN * TC_KT * 2;  // 32 KB
 constexpr int TC_SMEM = 1024 + TC_NS * (TC_A_STAGE + TC_B_STAGE);
 constexpr int TC_THREADS = 256;
 
@@ -95,8 +96,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
   uint8_t* sB = sA + TC_NS * TC_A_STAGE;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * TC_BN;   // first weight row of this tile
-  const int m0 = blockIdx.y * TC_BM;   // first activation row
+  // blockIdx.x walks the M tiles: consecutive CTAs share one weight tile (read from HBM once, then L2 hits)
+  const int m0 = blockIdx.x * TC_BM;   // first activation row
+  const int n0 = blockIdx.y * TC_BN;   // first weight row of this tile
   const int n_kt = p.K / TC_KT;
 
   if (tid == 0) {
@@ -123,10 +125,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
         mbar_wait(&empty_bar[s], (((uint32_t)(t / TC_NS)) & 1u) ^ 1u);
         mbar_expect_tx(&full_bar[s], TC_A_STAGE + TC_B_STAGE);
         const size_t k0 = (size_t)t * TC_KT;
-        // A: 16 groups of 8 rows, each (8 rows x KT) = KT*16 contiguous bytes in X8
-        for (int g = 0; g < TC_BM / 8; g++)
-          bulk_g2s(sA + (size_t)s * TC_A_STAGE + (size_t)g * (TC_KT * 16),
-                   xb + ((size_t)(m0 / 8 + g) * p.K + k0) * 16, TC_KT * 16, &full_bar[s], pol_x);
+        // A: one contiguous 128 x 128 tile of the tile-major X8 layout
+        bulk_g2s(sA + (size_t)s * TC_A_STAGE, xb + ((size_t)(m0 / TC_BM) * (p.K / TC_KT) + t) * TC_A_STAGE, TC_A_STAGE,
+                 &full_bar[s], pol_x);
         // B: 8 panels of 16 rows, each (16 rows x KT) = KT*32 contiguous bytes
         for (int j = 0; j < TC_BN / 16; j++)
           bulk_g2s(sB + (size_t)s * TC_B_STAGE + (size_t)j * (TC_KT * 32),
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
         const uint32_t b_base = smem_u32(sB + (size_t)s * TC_B_STAGE);
 #pragma unroll
         for (int k16 = 0; k16 < TC_KT / 16; k16++) {
-          const uint64_t a_desc = umma_desc(a_base + k16 * 256, 128, TC_KT * 16);
+          const uint64_t a_desc = umma_desc(a_base + k16 * 256, 128, TC_KT * 16);  // SBO = 16 chunks * 128 B
 #pragma unroll
           for (int j = 0; j < TC_BN / 16; j++) {
             const uint64_t b_desc = umma_desc(b_base + j * (TC_KT * 32) + k16 * 512, 256, 128);
@@ -205,7 +206,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
   }
 }
 
-// ---- layout helpers for the tensor-core path -----------------------------------------------------
+// ---- layout helpers for the tensor-core path (X8 = tile-major activations, see the header comment)
+// X8 address of element (row, col) of a [*, K] activation matrix
+LNB_DEVINL size_t x8_index(int row, int col, int K) {
+  const size_t tile = (size_t)(row >> 7) * (K >> 7) + (col >> 7);                 // [M/128][K/128]
+  const int g = (row >> 3) & 15, ch = (col >> 3) & 15;                            // [16 groups][16 chunks]
+  return (((tile * 16 + g) * 16 + ch) * 8 + (row & 7)) * 8 + (col & 7);
+}
+
+// ---- -----------------------------------------------------
 // row-major [M, K] bf16 -> X8 ([Mpad/8][K/8][8][8]); rows >= M are written as zeros
 __global__ void pack_x8_kernel(const uint16_t* __restrict__ src, int ld, int M, int Mpad, int K, uint16_t* __restrict__ dst) {
   pdl_launch_dependents();
@@ -215,13 +224,17 @@ __global__ void pack_x8_kernel(const uint16_t* __restrict__ src, int ld, int M, 
     const int64_t row = i / chunks, ch = i % chunks;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (row < M) v = *reinterpret_cast<const uint4*>(src + row * ld + ch * 8);
-    *reinterpret_cast<uint4*>(dst + (((row / 8) * chunks + ch) * 8 + (row % 8)) * 8) = v;
+    *reinterpret_cast<uint4*>(dst + x8_index((int)row, (int)ch * 8, K)) = v;
   }
 }
 
-// X8 address of element (row, col) of a [*, K] activation matrix
-LNB_DEVINL size_t x8_index(int row, int col, int K) {
-  return ((((size_t)(row >> 3) * (K >> 3) + (col >> 3)) << 3) + (row & 7)) * 8 + (col & 7);
+// X8 -> row-major [M, K] (tests / op-level API)
+__global__ void unpack_x8_kernel(const uint16_t* __restrict__ src, int M, int K, uint16_t* __restrict__ dst, int ld) {
+  const int64_t chunks = K / 8, total = (int64_t)M * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / chunks, ch = i % chunks;
+    *reinterpret_cast<uint4*>(dst + row * ld + ch * 8) = *reinterpret_cast<const uint4*>(src + x8_index((int)row, (int)ch * 8, K));
+  }
 }
 
 // RMSNorm.Forward (llamatransformer.go:633-660) for the prefill path: one CTA (256 threads) per row,

@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(128) sdpa_kernel(const uint16_t* __restrict__ 
     float acc = 0.f;
     for (int t = 0; t < Teff; t++) acc = __fmaf_rn(pf[t], bf2f(vc[(size_t)t * kv_dim]), acc);
     const int col = H * hd + d;  // Transpose(0,1)+Reshape :508-514
-    if (out_x8) out[((((size_t)(s >> 3) * (ldo >> 3) + (col >> 3)) << 3) + (s & 7)) * 8 + (col & 7)] = f2bf(acc);
+    if (out_x8) {  // tile-major X8 (gemm_tc.cuh x8_index)
+      const size_t tile = (size_t)(s >> 7) * (ldo >> 7) + (col >> 7);
+      out[(((tile * 16 + ((s >> 3) & 15)) * 16 + ((col >> 3) & 15)) * 8 + (s & 7)) * 8 + (col & 7)] = f2bf(acc);
+    }
     else out[(size_t)s * ldo + col] = f2bf(acc);
   }
 }
@@ -279,6 +282,169 @@ __global__ void __launch_bounds__(1024) sdpa_decode_kernel(const uint16_t* __res
 #pragma unroll 4
     for (int t = 0; t < T; t++) acc = __fmaf_rn(ph[t], bf2f(vc[(size_t)t * hd]), acc);
     out[(size_t)(h * n_rep + hh) * hd + tt] = f2bf(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Prompt attention (S > 1, LNB_ACC_FAST prefill path): one CTA per (query head, block of 32 query rows),
+// keys streamed through shared memory in tiles of 64, two passes like the reference's data flow demands
+// (P must be t(f32(e / Z)) with the FINAL Z, so an online-softmax rescale is not an option):
+//   pass 1: sc = t(t(sum_seq_d q k)/t(sqrt(hd))), e = exp_f64(sc), Z_row = sum of e   (f64, tile order)
+//   pass 2: the same scores again, p = t(f32(e / Z)), o_d += p_t * v_td  with t ascending
+// Every score dot runs d = 0..hd-1 sequentially and every (row, d) output accumulates t = 0,1,2,...
+// sequentially, i.e. in the reference's order; only the f64 row sum Z is reordered.  Causal mask
+// (llamatransformer.go:128-136): keys t > pos0 + s contribute exactly 0 and whole tiles beyond the block
+// are skipped.  Output goes straight into the tile-major X8 operand of the Wo GEMM.  hd must be 128.
+constexpr int SP_QB = 32, SP_TK = 64, SP_HD = 128, SP_KS = SP_HD + 8;
+constexpr int SP_SMEM = SP_QB * SP_HD * 4 + SP_TK * SP_KS * 2 + SP_TK * SP_HD * 2 + SP_QB * SP_TK * 4 + SP_QB * 8;
+
+LNB_DEVINL void sp_scores(const float* __restrict__ Qs, const uint16_t* __restrict__ Ks, int r2, int kq, float (&acc)[2][4]) {
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+  const float* q0 = Qs + (size_t)(2 * r2) * SP_HD;
+  const float* q1 = q0 + SP_HD;
+#pragma unroll 2
+  for (int d = 0; d < SP_HD; d += 8) {
+    const float4 a0 = *reinterpret_cast<const float4*>(q0 + d), a1 = *reinterpret_cast<const float4*>(q0 + d + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(q1 + d), b1 = *reinterpret_cast<const float4*>(q1 + d + 4);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(Ks + (size_t)(kq + 16 * j) * SP_KS + d);
+      const float k0 = bf_lo(kv.x), k1 = bf_hi(kv.x), k2 = bf_lo(kv.y), k3 = bf_hi(kv.y);
+      const float k4 = bf_lo(kv.z), k5 = bf_hi(kv.z), k6 = bf_lo(kv.w), k7 = bf_hi(kv.w);
+      float x = acc[0][j], y = acc[1][j];
+      x = __fmaf_rn(a0.x, k0, x); y = __fmaf_rn(b0.x, k0, y);
+      x = __fmaf_rn(a0.y, k1, x); y = __fmaf_rn(b0.y, k1, y);
+      x = __fmaf_rn(a0.z, k2, x); y = __fmaf_rn(b0.z, k2, y);
+      x = __fmaf_rn(a0.w, k3, x); y = __fmaf_rn(b0.w, k3, y);
+      x = __fmaf_rn(a1.x, k4, x); y = __fmaf_rn(b1.x, k4, y);
+      x = __fmaf_rn(a1.y, k5, x); y = __fmaf_rn(b1.y, k5, y);
+      x = __fmaf_rn(a1.z, k6, x); y = __fmaf_rn(b1.z, k6, y);
+      x = __fmaf_rn(a1.w, k7, x); y = __fmaf_rn(b1.w, k7, y);
+      acc[0][j] = x; acc[1][j] = y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sdpa_prefill_kernel(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ cache_k,
+                                                           const uint16_t* __restrict__ cache_v, int kv_dim, int n_rep,
+                                                           uint16_t* __restrict__ out_x8, int ldo, const int32_t* __restrict__ pos_ptr,
+                                                           int S, float scale_bf16_as_f32) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* Qs = reinterpret_cast<float*>(sm);                                   // [32][128]
+  uint16_t* Ks = reinterpret_cast<uint16_t*>(Qs + SP_QB * SP_HD);             // [64][136]
+  uint16_t* Vs = Ks + SP_TK * SP_KS;                                          // [64][128]
+  float* Ps = reinterpret_cast<float*>(Vs + SP_TK * SP_HD);                   // [32][64]
+  double* Zs = reinterpret_cast<double*>(Ps + SP_QB * SP_TK);                 // [32]
+  const int H = blockIdx.x, s0 = blockIdx.y * SP_QB, h = H / n_rep;
+  const int tid = threadIdx.x;
+  const int pos0 = *pos_ptr;
+  const int t_end = min(pos0 + S, pos0 + s0 + SP_QB);   // keys this row block can see
+  const int n_tiles = (t_end + SP_TK - 1) / SP_TK;
+
+  for (int i = tid; i < SP_QB * SP_HD; i += 256) {
+    const int r = i / SP_HD, d = i % SP_HD;
+    Qs[i] = (s0 + r < S) ? bf2f(q[(size_t)(s0 + r) * ldq + (size_t)H * SP_HD + d]) : 0.f;
+  }
+  const int r2 = tid / 16, kq = tid % 16;   // score block: rows 2*r2, 2*r2+1 ; keys kq + 16*j
+  double z0 = 0.0, z1 = 0.0;
+  auto load_tile = [&](int tile, bool with_v) {
+    const int t0 = tile * SP_TK;
+    for (int i = tid; i < SP_TK * (SP_HD / 8); i += 256) {
+      const int t = i / (SP_HD / 8), c = i % (SP_HD / 8);
+      uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (t0 + t < t_end) {
+        kk = *reinterpret_cast<const uint4*>(cache_k + (size_t)(t0 + t) * kv_dim + (size_t)h * SP_HD + c * 8);
+        if (with_v) vv = *reinterpret_cast<const uint4*>(cache_v + (size_t)(t0 + t) * kv_dim + (size_t)h * SP_HD + c * 8);
+      }
+      *reinterpret_cast<uint4*>(Ks + (size_t)t * SP_KS + c * 8) = kk;
+      if (with_v) *reinterpret_cast<uint4*>(Vs + (size_t)t * SP_HD + c * 8) = vv;
+    }
+  };
+  // ---------------- pass 1: row sums of exp ----------------------------------------------------
+  for (int tile = 0; tile < n_tiles; tile++) {
+    __syncthreads();
+    load_tile(tile, false);
+    __syncthreads();
+    float acc[2][4];
+    sp_scores(Qs, Ks, r2, kq, acc);
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int t = tile * SP_TK + kq + 16 * j, srow = s0 + 2 * r2 + a;
+        if (t <= pos0 + srow && t < t_end) {
+          float sc = trunc_bf(acc[a][j]);
+          sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
+          const double e = exp((double)sc);
+          if (a == 0) z0 = __dadd_rn(z0, e); else z1 = __dadd_rn(z1, e);
+        }
+      }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {   // the 16 threads that share a row pair are 16 consecutive lanes
+    z0 = __dadd_rn(z0, __shfl_xor_sync(0xffffffffu, z0, o));
+    z1 = __dadd_rn(z1, __shfl_xor_sync(0xffffffffu, z1, o));
+  }
+  if (kq == 0) { Zs[2 * r2] = z0; Zs[2 * r2 + 1] = z1; }
+  // ---------------- pass 2: p = t(f32(e/Z)), o += p v ------------------------------------------
+  const int pr = tid / 8, dg = (tid % 8) * 16;   // PV block: row pr, columns dg .. dg+15
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) o[i] = 0.f;
+  for (int tile = 0; tile < n_tiles; tile++) {
+    __syncthreads();
+    load_tile(tile, true);
+    __syncthreads();
+    float acc[2][4];
+    sp_scores(Qs, Ks, r2, kq, acc);
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      const double Z = Zs[2 * r2 + a];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int t = tile * SP_TK + kq + 16 * j, srow = s0 + 2 * r2 + a;
+        float pv = 0.f;
+        if (t <= pos0 + srow && t < t_end) {
+          float sc = trunc_bf(acc[a][j]);
+          sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
+          pv = trunc_bf((float)__ddiv_rn(exp((double)sc), Z));
+        }
+        Ps[(size_t)(2 * r2 + a) * SP_TK + kq + 16 * j] = pv;
+      }
+    }
+    __syncthreads();
+    const int tn = min(SP_TK, t_end - tile * SP_TK);
+    const float* prow = Ps + (size_t)pr * SP_TK;
+    for (int t = 0; t < tn; t++) {
+      const float pt = prow[t];
+      const uint4 v0 = *reinterpret_cast<const uint4*>(Vs + (size_t)t * SP_HD + dg);
+      const uint4 v1 = *reinterpret_cast<const uint4*>(Vs + (size_t)t * SP_HD + dg + 8);
+      o[0] = __fmaf_rn(pt, bf_lo(v0.x), o[0]);   o[1] = __fmaf_rn(pt, bf_hi(v0.x), o[1]);
+      o[2] = __fmaf_rn(pt, bf_lo(v0.y), o[2]);   o[3] = __fmaf_rn(pt, bf_hi(v0.y), o[3]);
+      o[4] = __fmaf_rn(pt, bf_lo(v0.z), o[4]);   o[5] = __fmaf_rn(pt, bf_hi(v0.z), o[5]);
+      o[6] = __fmaf_rn(pt, bf_lo(v0.w), o[6]);   o[7] = __fmaf_rn(pt, bf_hi(v0.w), o[7]);
+      o[8] = __fmaf_rn(pt, bf_lo(v1.x), o[8]);   o[9] = __fmaf_rn(pt, bf_hi(v1.x), o[9]);
+      o[10] = __fmaf_rn(pt, bf_lo(v1.y), o[10]); o[11] = __fmaf_rn(pt, bf_hi(v1.y), o[11]);
+      o[12] = __fmaf_rn(pt, bf_lo(v1.z), o[12]); o[13] = __fmaf_rn(pt, bf_hi(v1.z), o[13]);
+      o[14] = __fmaf_rn(pt, bf_lo(v1.w), o[14]); o[15] = __fmaf_rn(pt, bf_hi(v1.w), o[15]);
+    }
+  }
+  const int srow = s0 + pr;
+  if (srow < S) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 8) {
+      uint4 w;
+      w.x = (uint32_t)f2bf(o[i + 0]) | ((uint32_t)f2bf(o[i + 1]) << 16);
+      w.y = (uint32_t)f2bf(o[i + 2]) | ((uint32_t)f2bf(o[i + 3]) << 16);
+      w.z = (uint32_t)f2bf(o[i + 4]) | ((uint32_t)f2bf(o[i + 5]) << 16);
+      w.w = (uint32_t)f2bf(o[i + 6]) | ((uint32_t)f2bf(o[i + 7]) << 16);
+      *reinterpret_cast<uint4*>(out_x8 + x8_index(srow, H * SP_HD + dg + i, ldo)) = w;   // 8 consecutive columns = one chunk
+    }
   }
 }
 

@@ -130,7 +130,8 @@ def test_rope_bit_exact(L):
         assert np.array_equal(out, O.rope_apply(x, cis, pos))
 
 
-@pytest.mark.parametrize("S,T,causal", [(1, 1, 0), (1, 37, 0), (1, 135, 0), (5, 5, 1), (8, 8, 1), (1, 300, 0)])
+@pytest.mark.parametrize("S,T,causal", [(1, 1, 0), (1, 37, 0), (1, 135, 0), (5, 5, 1), (8, 8, 1), (1, 300, 0), (70, 70, 1),
+                                        (200, 200, 1)])
 def test_attention_strict_bit_exact(L, S, T, causal):
     rng = np.random.default_rng(S * 31 + T)
     nh, nkv, hd = 32, 8, 128
