@@ -182,11 +182,11 @@ static Placement placement(lnb_model* m, int kind, int layer) {
     case T_NORM: p.dst = m->norm; p.rows = 1; p.cols = a.dim; p.panel_major = false; break;
     case T_EMBD: p.dst = m->tok_embd; p.rows = a.vocab_size; p.cols = a.dim; p.panel_major = false; break;
     case T_WQ: p.dst = L->wqkv; p.row0 = (int64_t)r * m->q_l; p.rows = m->q_l; p.cols = a.dim; break;
-    case T_WK: p.dst = L->wqkv; p.row0 = (int64_t)r * m->kv_l; p.rows = m->kv_l; p.cols = a.dim; p.dpanel0 = m->q_l / 16; break;
-    case T_WV: p.dst = L->wqkv; p.row0 = (int64_t)r * m->kv_l; p.rows = m->kv_l; p.cols = a.dim; p.dpanel0 = (m->q_l + m->kv_l) / 16; break;
+    case T_WK: p.dst = L->wqkv; p.row0 = (int64_t)r * m->kv_l; p.rows = m->kv_l; p.cols = a.dim; p.dpanel0 = m->q_l / 8; break;
+    case T_WV: p.dst = L->wqkv; p.row0 = (int64_t)r * m->kv_l; p.rows = m->kv_l; p.cols = a.dim; p.dpanel0 = (m->q_l + m->kv_l) / 8; break;
     case T_WO: p.dst = L->wo; p.col0 = (int64_t)r * m->q_l; p.rows = a.dim; p.cols = m->q_l; break;
     case T_W1: p.dst = L->w13; p.row0 = (int64_t)r * m->ffn_l; p.rows = m->ffn_l; p.cols = a.dim; p.dpanel0 = 0; p.dpanel_stride = 2; break;
-    case T_W3: p.dst = L->w13; p.row0 = (int64_t)r * m->ffn_l; p.rows = m->ffn_l; p.cols = a.dim; p.dpanel0 = 1; p.dpanel_stride = 2; break;
+    case T_W3: p.dst = L->w13; p.row0 = (int64_t)r * m->ffn_l; p.rows = m->ffn_l; p.cols = a.dim; p.dpanel0 = 2; p.dpanel_stride = 2; break;
     case T_W2: p.dst = L->w2; p.col0 = (int64_t)r * m->ffn_l; p.rows = a.dim; p.cols = m->ffn_l; break;
     case T_OUTPUT: p.dst = m->output; p.row0 = (int64_t)r * m->vocab_l; p.rows = m->vocab_l; p.cols = a.dim; break;
   }
@@ -522,7 +522,7 @@ static int launch_gemv_cfg(const Launcher& L, const GemvParams& p) {
     attr_smem = kMaxSmem;
   }
   cudaLaunchConfig_t cfg{};
-  const int n_panels = p.N / 16;
+  const int n_panels = p.N / 8;
   cfg.gridDim = dim3((n_panels + Cfg::kP - 1) / Cfg::kP);
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = smem;
@@ -540,7 +540,7 @@ static int launch_gemv_cfg(const Launcher& L, const GemvParams& p) {
 // picks the row-block size: largest MB in {8,2,1} that is useful for M and whose smem fits
 template <int PRO, int EPI>
 static int launch_gemv(const Launcher& L, int mode, GemvParams p, int M_total) {
-  if (p.N % 16 || p.K % 8) return fail(LNB_EINVAL, "gemv: N %d must be a multiple of 16 and K %d of 8", p.N, p.K);
+  if (p.N % 16 || p.K % 8) return fail(LNB_EINVAL, "gemv: N %d must be a multiple of 16 and K %d of 8", p.N, p.K);  // 16: panel pairs
   if ((EPI == EPI_QKV_ROPE || EPI == EPI_SWIGLU) && p.N % 32) return fail(LNB_EINVAL, "gemv: N %d must be a multiple of 32", p.N);
   const bool strict = (mode == LNB_ACC_STRICT);
   p.strict_norm = strict ? 1 : 0;

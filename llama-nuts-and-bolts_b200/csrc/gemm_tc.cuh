@@ -9,8 +9,9 @@
 // hardware's, so this path belongs to LNB_ACC_FAST; LNB_ACC_STRICT keeps the sequential GEMV.
 //
 // Operand layouts (both "K-major, no swizzle" in UMMA terms: 8-row x 16-byte core matrices):
-//   W  : the same panel-major HBM layout the GEMV streams (16-row panels, gemv.cuh) -- each tcgen05.mma
-//        takes ONE panel as its N=16 B-operand:  core matrices 128 B apart along N (SBO), 256 B along K (LBO).
+//   W  : the same panel-major HBM layout the GEMV streams (8-row panels = core matrices, gemv.cuh): the 16
+//        panels of a 128-row tile are copied panel by panel (KT*16 B each) and form ONE N=128 B operand:
+//        LBO = 128 B (next k-chunk), SBO = KT*16 B (next panel).
 //   X  : "X8" activations written by the preceding kernel, tile-major: [M/128][K/128] tiles of
 //        [16 row-groups][16 k-chunks][8 rows][8 elems] = 32 KB contiguous -> ONE bulk copy per stage;
 //        LBO = 128 B (next k-chunk), SBO = 2048 B (next 8 rows).
@@ -71,6 +72,23 @@ LNB_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Optional A operand from TMEM (".ts" form, -DLNB_TC_A_IN_TMEM=1): the 128 x 16 activation slice of a k16
+// step is copied shared -> tensor memory (tcgen05.cp, 128 lanes x 256 bit) and the MMA reads it from there.
+// Verified correct on B200; not faster than the SS form for this tile shape, so it is off by default.
+LNB_DEVINL void tmem_cp_128x256b(uint32_t taddr, uint64_t s_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(s_desc) : "memory");
+}
+LNB_DEVINL void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+#ifndef LNB_TC_A_IN_TMEM
+#define LNB_TC_A_IN_TMEM 0
+#endif
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 LNB_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -106,7 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
     mbar_init(acc_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 128);
+  if (warp == 2) tmem_alloc(tmem_slot, LNB_TC_A_IN_TMEM ? 256 : 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -128,15 +146,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
         // A: one contiguous 128 x 128 tile of the tile-major X8 layout
         bulk_g2s(sA + (size_t)s * TC_A_STAGE, xb + ((size_t)(m0 / TC_BM) * (p.K / TC_KT) + t) * TC_A_STAGE, TC_A_STAGE,
                  &full_bar[s], pol_x);
-        // B: 8 panels of 16 rows, each (16 rows x KT) = KT*32 contiguous bytes
-        for (int j = 0; j < TC_BN / 16; j++)
-          bulk_g2s(sB + (size_t)s * TC_B_STAGE + (size_t)j * (TC_KT * 32),
-                   wb + ((size_t)(n0 / 16 + j) * p.K + k0) * 32, TC_KT * 32, &full_bar[s], pol_w);
+        // B: 16 panels of 8 rows, each (8 rows x KT) = KT*16 contiguous bytes
+        for (int j = 0; j < TC_BN / 8; j++)
+          bulk_g2s(sB + (size_t)s * TC_B_STAGE + (size_t)j * (TC_KT * 16),
+                   wb + ((size_t)(n0 / 8 + j) * p.K + k0) * 16, TC_KT * 16, &full_bar[s], pol_w);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, 16);
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
       for (int t = 0; t < n_kt; t++) {
         const int s = t % TC_NS;
         mbar_wait(&full_bar[s], ((uint32_t)(t / TC_NS)) & 1u);
@@ -146,11 +164,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
 #pragma unroll
         for (int k16 = 0; k16 < TC_KT / 16; k16++) {
           const uint64_t a_desc = umma_desc(a_base + k16 * 256, 128, TC_KT * 16);  // SBO = 16 chunks * 128 B
-#pragma unroll
-          for (int j = 0; j < TC_BN / 16; j++) {
-            const uint64_t b_desc = umma_desc(b_base + j * (TC_KT * 32) + k16 * 512, 256, 128);
-            umma_bf16(tmem_base + j * 16, a_desc, b_desc, idesc, (t > 0 || k16 > 0) ? 1u : 0u);
-          }
+          const uint64_t b_desc = umma_desc(b_base + k16 * 256, 128, TC_KT * 16);
+#if LNB_TC_A_IN_TMEM
+          const uint32_t a_tmem = tmem_base + 128 + (uint32_t)(k16 & 1) * 8;   // 8 columns = 16 bf16 per lane, double-buffered
+          tmem_cp_128x256b(a_tmem, a_desc);
+          umma_bf16_ts(tmem_base, a_tmem, b_desc, idesc, (t > 0 || k16 > 0) ? 1u : 0u);
+#else
+          umma_bf16(tmem_base, a_desc, b_desc, idesc, (t > 0 || k16 > 0) ? 1u : 0u);   // 128 x 128 x 16 per instruction
+#endif
         }
         umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
       }
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, LNB_TC_A_IN_TMEM ? 256 : 128);
   }
 }
 

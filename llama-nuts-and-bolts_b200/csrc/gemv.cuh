@@ -8,12 +8,14 @@
 // truncation point; see the EPI_* / PRO_* notes).
 //
 // HBM layout of a weight matrix W[N,K] ("panel-major", built once at upload):
-//   panel p = rows 16p..16p+15;  chunk c = k 8c..8c+7;
-//   address(p, c, r, e) = ((p * K/8 + c) * 16 + r) * 8 + e        (bf16 elements)
-// so a (panel, k-range) block is ONE contiguous byte range -> a single bulk-async copy
-// (TMA engine, cp.async.bulk + mbarrier complete_tx) per panel per stage, and inside shared
-// memory the 16 rows of a chunk are 256 contiguous bytes -> conflict-free 128-bit LDS
-// for "one thread = one output row".
+//   panel p = rows 8p..8p+7;  chunk c = k 8c..8c+7;
+//   address(p, c, r, e) = ((p * K/8 + c) * 8 + r) * 8 + e        (bf16 elements)
+// i.e. the matrix is stored as 8-row x 16-byte "core matrices" (128 B each), k-chunks of a panel
+// back to back.  A (panel, k-range) block is ONE contiguous byte range -> a single bulk-async copy
+// (TMA engine, cp.async.bulk + mbarrier complete_tx) per panel per stage; in shared memory the 8 rows
+// of a chunk are 128 contiguous bytes -> conflict-free 128-bit LDS for "one thread = one output row"
+// (each quarter-warp reads one core matrix), and any number of consecutive panels forms a tcgen05
+// K-major / no-swizzle operand with a uniform 8-row-group stride (gemm_tc.cuh reads the SAME bytes).
 //
 // Thread roles: warp 0 = producer (one lane issues bulk copies into an NST-stage ring);
 // the other TN*KS threads are consumers.  Consumer (r, j): output row r of the CTA's TN
@@ -39,7 +41,7 @@ enum {
 
 struct GemvParams {
   const uint16_t* W;       // panel-major weights
-  int N, K;                // N = rows of W (multiple of 16), K multiple of 8
+  int N, K;                // N = rows of W (multiple of 8), K multiple of 8
   int M;                   // activation rows in this launch (<= MB)
   // prologue
   const uint16_t* x;       // [M, ldx] bf16 activations (PRO_PLAIN) / residual stream (PRO_RMSNORM)
@@ -75,7 +77,7 @@ struct GemvParams {
 template <int TN, int KS, int MB, int KT, int NST>
 struct GemvCfg {
   static constexpr int kTN = TN, kKS = KS, kMB = MB, kKT = KT, kNST = NST;
-  static constexpr int kP = TN / 16;                   // panels per CTA
+  static constexpr int kP = TN / 8;                    // 8-row panels per CTA
   static constexpr int kNCons = TN * KS;               // consumer threads
   static constexpr int kThreads = kNCons + 32;         // + producer warp
   static constexpr int kStageBytes = TN * KT * 2;
@@ -157,14 +159,15 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
       }
     }
   } else if (EPI == EPI_SWIGLU) {
-    // panels alternate: even panel = 16 w1 (gate) rows, odd panel = the same 16 rows of w3 (up);
-    // the partner of tile row er (er % 32 < 16) is er + 16 == lane + 16 of the same warp
+    // the stacked w1|w3 matrix alternates 16 gate rows (two panels) with the same 16 up rows (next two
+    // panels); `panel` = first panel of this row; the partner of tile row er (er % 32 < 16) is er + 16 ==
+    // lane + 16 of the same warp
     const float mine = trunc_bf(v);
     const float up = __shfl_down_sync(0xffffffffu, mine, 16);
     if (valid && (er & 16) == 0) {
       const uint16_t sg = p.silu_tab[f2bf(mine)];                       // t(TABLE_SILU[bits]) activations.go:38
       const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
-      p.out_bf16[(size_t)em * p.ldo + (size_t)(panel >> 1) * 16 + (er & 15)] = f2bf(mm);
+      p.out_bf16[(size_t)em * p.ldo + (size_t)(panel >> 2) * 16 + (er & 15)] = f2bf(mm);
     }
   }
 }
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
   const int K = p.K;
   const int n_tiles = (K + KT - 1) / KT;
   const int panel0 = blockIdx.x * P;
-  const int n_panels_total = p.N / 16;
+  const int n_panels_total = p.N / 8;
   const int my_panels = min(P, n_panels_total - panel0);
 
   if (tid == 0) {
@@ -234,11 +237,11 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
         mbar_wait(&empty_bar[s], ph ^ 1u);
         const int k0 = t * KT;
         const int kt = min(KT, K - k0);
-        const uint32_t bytes_per_panel = (uint32_t)kt * 32u;  // kt/8 chunks * 256 B
+        const uint32_t bytes_per_panel = (uint32_t)kt * 16u;  // kt/8 chunks * 128 B
         mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)my_panels);
         for (int pp = 0; pp < my_panels; pp++) {
-          const uint8_t* src = wbase + ((size_t)(panel0 + pp) * (size_t)K + (size_t)k0) * 32u;
-          bulk_g2s(s_stage + (size_t)s * STAGE + (size_t)pp * (KT * 32), src, bytes_per_panel, &full_bar[s], pol);
+          const uint8_t* src = wbase + ((size_t)(panel0 + pp) * (size_t)K + (size_t)k0) * 16u;
+          bulk_g2s(s_stage + (size_t)s * STAGE + (size_t)pp * (KT * 16), src, bytes_per_panel, &full_bar[s], pol);
         }
       }
     }
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
   const int c = tid - 32;
   const int r = c % TN;        // row within the CTA tile
   const int j = c / TN;        // k-stream
-  const int pp = r / 16, rr = r % 16;
+  const int pp = r / 8, rr = r % 8;
   const int cw = c / 32;       // consumer warp index
   const int lane = tid & 31;
 
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
     mbar_wait(&full_bar[s], ph);
     const int k0 = t * KT;
     const int nchunks = min(KT, K - k0) / 8;
-    const uint8_t* tile = s_stage + (size_t)s * STAGE + (size_t)pp * (KT * 32) + rr * 16;
+    const uint8_t* tile = s_stage + (size_t)s * STAGE + (size_t)pp * (KT * 16) + rr * 16;
     if (MB == 1 && NI % 4 == 0 && nchunks == CPT) {
       // Full tile, one activation row: groups of 4 chunks with register double buffering, so the
       // shared-memory loads of group g+1 are in flight while the 32 dependent FMAs of group g
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
 #define LNB_LOAD_GROUP(gi, W_, X0_, X1_)                                      \
   _Pragma("unroll") for (int q_ = 0; q_ < G; q_++) {                          \
     const int ch_ = j + KS * ((gi) * G + q_);                                 \
-    W_[q_] = *reinterpret_cast<const uint4*>(tile + ch_ * 256);               \
+    W_[q_] = *reinterpret_cast<const uint4*>(tile + ch_ * 128);               \
     X0_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8);                 \
     X1_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8 + 4);             \
   }
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
     } else {
 #pragma unroll 4
       for (int ch = j; ch < nchunks; ch += KS) {
-        const uint4 wv = *reinterpret_cast<const uint4*>(tile + ch * 256);
+        const uint4 wv = *reinterpret_cast<const uint4*>(tile + ch * 128);
         const float w0 = bf_lo(wv.x), w1 = bf_hi(wv.x), w2 = bf_lo(wv.y), w3 = bf_hi(wv.y);
         const float w4 = bf_lo(wv.z), w5 = bf_hi(wv.z), w6 = bf_lo(wv.w), w7 = bf_hi(wv.w);
         const float* xk = s_x + k0 + ch * 8;
@@ -422,9 +425,9 @@ __global__ void __launch_bounds__(Cfg::kThreads) gemv_kernel(const GemvParams p)
       for (int m = 0; m < MB; m++)
         if (m == em) v = acc[m];
     }
-    const int n = (panel0 + er / 16) * 16 + (er % 16);  // global row of W
-    const bool valid = (em < p.M) && (er / 16 < my_panels);
-    gemv_epilogue<EPI>(p, v, n, em, valid, panel0 + er / 16, er, lane);
+    const int n = (panel0 + er / 8) * 8 + (er % 8);  // global row of W
+    const bool valid = (em < p.M) && (er / 8 < my_panels);
+    gemv_epilogue<EPI>(p, v, n, em, valid, panel0 + er / 8, er, lane);
   }
 
   if (EPI == EPI_LOGITS) {

@@ -8,8 +8,9 @@ namespace lnb {
 
 // ------------------------------------------------------------------------------------------
 // Upload-time layout change: row-major W[rows x ld] (a [row0.., col0..] window of it) ->
-// panel-major (see gemv.cuh).  dst panel index of source panel q is
-// dpanel0 + q * dpanel_stride (w1/w3 are interleaved panel-wise for the fused SwiGLU).
+// panel-major (8-row panels, see gemv.cuh).  Source panel q lands in destination panel
+// dpanel0 + (q / 2) * 2 * dpanel_stride + (q % 2): dpanel_stride == 1 keeps the order; w1 / w3 use
+// stride 2 with dpanel0 = 0 / 2 so that 16 gate rows alternate with the same 16 up rows (fused SwiGLU).
 // One thread moves one 16-byte chunk (8 bf16).
 __global__ void retile_kernel(const uint16_t* __restrict__ src, int64_t ld, int64_t row0, int64_t col0, int rows,
                               int K, uint16_t* __restrict__ dst, int dpanel0, int dpanel_stride) {
@@ -18,9 +19,9 @@ __global__ void retile_kernel(const uint16_t* __restrict__ src, int64_t ld, int6
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / chunks_per_row, ch = i % chunks_per_row;
     const uint4 v = *reinterpret_cast<const uint4*>(src + (row0 + row) * ld + col0 + ch * 8);
-    const int64_t q = row / 16, rr = row % 16;
-    const int64_t dp = dpanel0 + q * dpanel_stride;
-    *reinterpret_cast<uint4*>(dst + ((dp * chunks_per_row + ch) * 16 + rr) * 8) = v;
+    const int64_t q = row / 8, rr = row % 8;
+    const int64_t dp = dpanel0 + (q / 2) * 2 * dpanel_stride + (q % 2);
+    *reinterpret_cast<uint4*>(dst + ((dp * chunks_per_row + ch) * 8 + rr) * 8) = v;
   }
 }
 
@@ -31,10 +32,10 @@ __global__ void untile_kernel(const uint16_t* __restrict__ src, int rows, int K,
   const int64_t total = (int64_t)rows * chunks_per_row;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / chunks_per_row, ch = i % chunks_per_row;
-    const int64_t q = row / 16, rr = row % 16;
-    const int64_t sp = spanel0 + q * spanel_stride;
+    const int64_t q = row / 8, rr = row % 8;
+    const int64_t sp = spanel0 + (q / 2) * 2 * spanel_stride + (q % 2);
     *reinterpret_cast<uint4*>(dst + row * K + ch * 8) =
-        *reinterpret_cast<const uint4*>(src + ((sp * chunks_per_row + ch) * 16 + rr) * 8);
+        *reinterpret_cast<const uint4*>(src + ((sp * chunks_per_row + ch) * 8 + rr) * 8);
   }
 }
 
@@ -63,9 +64,9 @@ __global__ void synth_fill_kernel(uint64_t seed, float scale, float offset, int6
     const int64_t row = i / K, col = i % K;
     const uint16_t v = synth_value(seed, (uint64_t)((row0 + row) * ld + col0 + col), scale, offset);
     if (panel_major) {
-      const int64_t q = row / 16, rr = row % 16, ch = col / 8, e = col % 8;
-      const int64_t dp = dpanel0 + q * dpanel_stride;
-      dst[((dp * (K / 8) + ch) * 16 + rr) * 8 + e] = v;
+      const int64_t q = row / 8, rr = row % 8, ch = col / 8, e = col % 8;
+      const int64_t dp = dpanel0 + (q / 2) * 2 * dpanel_stride + (q % 2);
+      dst[((dp * (K / 8) + ch) * 8 + rr) * 8 + e] = v;
     } else {
       dst[i] = v;
     }
