@@ -119,17 +119,24 @@ def run_reference(a):
     if rank != 0:
         return
     from oracle import oracle as O
+    t_begin = time.perf_counter()
     om, _, t_setup, np = cpu_oracle_setup()
+    print(f"[reference arm] host weights ready in {t_setup:.1f} s, {O.lib().orc_num_threads()} threads", file=sys.stderr, flush=True)
     n_dec = 4
-    for _ in range(max(0, a.warmup - 2)):  # CPU steps cost seconds; one warm-up sample is plenty
-        break
-    cpu_sample(om, np, 1)
+    cpu_sample(om, np, 1)   # CPU steps cost seconds: one warm-up sample regardless of --warmup
     t_dec_total, t_pre_total = 0.0, 0.0
     t0 = time.perf_counter()
+    done = 0
     for _ in range(a.steps):
         tp, td, _, _ = cpu_sample(om, np, n_dec)
         t_dec_total += td
         t_pre_total += tp
+        done += 1
+        print(f"[reference arm] step {done}/{a.steps}: prefill {tp:.2f} s, {n_dec} decode tokens {td:.2f} s", file=sys.stderr, flush=True)
+        if time.perf_counter() - t_begin > 150 and done < a.steps:   # keep the whole arm within a few minutes
+            print("[reference arm] time budget reached, stopping early", file=sys.stderr, flush=True)
+            break
+    a.steps = done
     wall = time.perf_counter() - t0
     val = a.steps * n_dec / t_dec_total
     cores = O.lib().orc_num_threads()

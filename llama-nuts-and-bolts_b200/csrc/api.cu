@@ -499,6 +499,7 @@ using CfgS1W = GemvCfg<128, 1, 1, 256, 3>;  // larger N (w1|w3, LM head): severa
 using CfgS2 = GemvCfg<32, 1, 2, 256, 4>;
 using CfgS8 = GemvCfg<32, 1, 8, 256, 4>;
 using CfgF1 = GemvCfg<32, 8, 1, 256, 4>;
+using CfgF1L = GemvCfg<32, 8, 1, 512, 3>;  // at most one CTA per SM (wo, w2): larger bulk copies
 using CfgF2 = GemvCfg<32, 8, 2, 256, 4>;
 using CfgF8 = GemvCfg<32, 8, 8, 256, 4>;
 
@@ -580,6 +581,7 @@ static int launch_gemv(const Launcher& L, int mode, GemvParams p, int M_total) {
     } else {
       if (mb == 8) rc = launch_gemv_cfg<CfgF8, PRO, EPI>(L, p);
       else if (mb == 2) rc = launch_gemv_cfg<CfgF2, PRO, EPI>(L, p);
+      else if (p.N <= 32 * 148 && CfgF1L::smem_bytes(p.K) <= kMaxSmem) rc = launch_gemv_cfg<CfgF1L, PRO, EPI>(L, p);
       else rc = launch_gemv_cfg<CfgF1, PRO, EPI>(L, p);
     }
     if (rc) return rc;

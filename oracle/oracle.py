@@ -27,12 +27,35 @@ def build(force: bool = False) -> str:
 _lib = None
 
 
+def usable_cpus() -> int:
+    """CPUs this process may really use: affinity mask, capped by the cgroup CPU quota (containers often
+    expose all host cores in nproc while granting only a few; an OpenMP team larger than that spends its
+    time spinning at barriers)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def lib():
     global _lib
     if _lib is None:
         build()
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # idle team members sleep instead of spinning
         _lib = C.CDLL(_SO)
         _declare(_lib)
+        want = int(os.environ.get("LNB_ORACLE_THREADS", "0")) or min(usable_cpus(), 64)
+        _lib.orc_set_num_threads(want)
     return _lib
 
 
