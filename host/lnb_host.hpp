@@ -1,0 +1,176 @@
+// lnb_host.hpp -- C++ host mirror of the reference's Go packages above the C-ABI (include/lnb.h).
+//
+// The reference is compiled Go; the build image has no Go toolchain, so this header restates, in C++17,
+// the host-side types and call sequence a Go build would keep: ml::Tensor + the ml ops on the forward
+// path, model::ModelArgs / LlamaTransformer / InferenceContext, and inference::InferenceEngine with the
+// generate loop of src/inference/inference.go:173-254.  Same names, argument meaning and error texts as
+// the Go code (errors are exceptions instead of `(nil, error)`).  Header-only; links against liblnb.so.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/lnb.h"
+
+namespace lnb_host {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+inline void check(int rc) {
+  if (rc < 0) throw Error(std::string("lnb: ") + lnb_last_error());
+}
+
+namespace ml {  // ---- src/ml ---------------------------------------------------------------------------
+enum class DataType { BF16, F32, INT32 };  // datatype.go:11-34
+inline size_t item_size(DataType t) { return t == DataType::BF16 ? 2 : 4; }
+
+struct Tensor {  // tensor.go:11-19 (contiguous row-major, Size + RawData)
+  std::vector<int> Size;
+  DataType DT = DataType::BF16;
+  std::vector<uint8_t> RawData;
+  std::string Name;
+  Tensor() = default;
+  Tensor(std::vector<int> size, DataType dt) : Size(std::move(size)), DT(dt) { RawData.assign(GetElementCount() * item_size(dt), 0); }
+  size_t GetElementCount() const {
+    size_t n = 1;
+    for (int d : Size) n *= (size_t)d;
+    return n;
+  }
+  template <class T> T* data() { return reinterpret_cast<T*>(RawData.data()); }
+  template <class T> const T* data() const { return reinterpret_cast<const T*>(RawData.data()); }
+};
+
+inline uint16_t Float32ToBFloat16bits(float f) {  // src/dtype/bfloat16.go:59-61 (truncation)
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return (uint16_t)(u >> 16);
+}
+inline float BFloat16bitsToFloat32(uint16_t b) {  // :55-57
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+inline int AccMode = LNB_ACC_STRICT;
+
+inline Tensor LinearTransformation(const Tensor& input, const Tensor& weights) {  // operations_impl.go:427-447
+  if (input.DT != weights.DT) throw Error("tensors are not in same data type");
+  if (input.Size.size() != 2 || weights.Size.size() != 2) throw Error("LinearTransformation needs two matrices");
+  if (input.Size[1] != weights.Size[1])
+    throw Error("columns size " + std::to_string(input.Size[1]) + " of input tensor should be equal with " +
+                std::to_string(weights.Size[1]) + " input features count of weights tensor");
+  if (input.DT != DataType::BF16) throw Error("unsupported tensor datatype");
+  Tensor dst({input.Size[0], weights.Size[0]}, DataType::BF16);
+  check(lnb_op_linear_bf16(input.data<uint16_t>(), weights.data<uint16_t>(), dst.data<uint16_t>(), input.Size[0], input.Size[1],
+                           weights.Size[0], AccMode));
+  return dst;
+}
+
+inline Tensor Argmax(const Tensor& input) {  // operations_impl.go:513-548 (last dimension)
+  if (input.DT != DataType::F32) throw Error("unsupported tensor datatype");
+  const int cols = input.Size.back();
+  const int rows = (int)(input.GetElementCount() / cols);
+  Tensor dst(std::vector<int>(input.Size.begin(), input.Size.end() - 1), DataType::INT32);
+  if (dst.Size.empty()) dst = Tensor({1}, DataType::INT32);
+  check(lnb_op_argmax_f32(input.data<float>(), rows, cols, dst.data<int32_t>()));
+  return dst;
+}
+}  // namespace ml
+
+namespace model {  // ---- src/model ------------------------------------------------------------------------
+struct ModelArgs : lnb_model_args {  // modelargs.go:10-44 (+ derived HeadDim / FFN width, llamatransformer.go:569-577)
+  static ModelArgs Llama31_8B() {
+    ModelArgs a{};
+    a.dim = 4096; a.n_layers = 32; a.n_heads = 32; a.n_kv_heads = 8; a.head_dim = 128; a.ffn_dim = 14336;
+    a.vocab_size = 128256; a.max_seq_len = 2048; a.norm_eps = 1e-5f; a.rope_theta = 500000.0; a.use_scaled_rope = 1;
+    return a;
+  }
+};
+struct Vocabulary {  // vocabulary.go (ids only)
+  int32_t PadId = -1;
+  std::vector<int32_t> StopTokenIds{128008, 128009};  // src/tiktoken/tiktokenreader.go:81
+};
+
+class LlamaTransformer {  // llamatransformer.go:16-113
+ public:
+  ModelArgs args;
+  LlamaTransformer(const ModelArgs& a, int device = 0) : args(a) { check(lnb_model_create(&args, device, 0, 1, nullptr, &h_)); }
+  ~LlamaTransformer() { lnb_model_destroy(h_); }
+  LlamaTransformer(const LlamaTransformer&) = delete;
+  // getTensor + upload (loader.go:183-197)
+  void UploadTensor(const std::string& name, const uint16_t* data, const std::vector<int64_t>& shape) {
+    check(lnb_model_upload_tensor(h_, name.c_str(), data, shape.data(), (int)shape.size()));
+  }
+  void InitSynthetic(uint64_t seed) { check(lnb_model_init_synthetic(h_, seed)); }
+  void Finalize() { check(lnb_model_finalize(h_)); }
+  lnb_model* handle() { return h_; }
+
+ private:
+  lnb_model* h_ = nullptr;
+};
+
+class InferenceContext {  // inferencecontext.go:8-46 (KV cache in HBM)
+ public:
+  int SequenceLength;
+  InferenceContext(LlamaTransformer& t, int sequenceLength, int accMode = LNB_ACC_STRICT, int maxRows = 8)
+      : SequenceLength(sequenceLength > 0 ? sequenceLength : t.args.max_seq_len), vocab_(t.args.vocab_size) {
+    check(lnb_session_create(t.handle(), SequenceLength, maxRows, accMode, &h_));
+  }
+  ~InferenceContext() { lnb_session_destroy(h_); }
+  InferenceContext(const InferenceContext&) = delete;
+  // LlamaTransformer.Forward (llamatransformer.go:145-180): tokens [S] -> f32 logits [S, vocab]
+  ml::Tensor Forward(const ml::Tensor& inputTokens, int startPos) {
+    if (inputTokens.DT != ml::DataType::INT32 || inputTokens.Size.size() != 1) throw Error("inputTokens must be a 1-D Int32 tensor");
+    const int S = inputTokens.Size[0];
+    if (S == 0) throw Error("empty token array");
+    ml::Tensor logits({S, vocab_}, ml::DataType::F32);
+    check(lnb_forward(h_, inputTokens.data<int32_t>(), S, startPos, logits.data<float>(), 1, nullptr));
+    return logits;
+  }
+  lnb_session* handle() { return h_; }
+
+ private:
+  lnb_session* h_ = nullptr;
+  int vocab_;
+};
+}  // namespace model
+
+namespace inference {  // ---- src/inference ------------------------------------------------------------------
+enum GenerationState { GSInProgress = 0, GSFinishedByReachingEOS = 1, GSFinishedByReachingSeqLen = 2 };
+
+// generateTokensInternal (inference.go:173-254); `emit` plays generatedTokensCh
+inline void GenerateTokens(model::LlamaTransformer& transformer, const model::Vocabulary& vocab, int sequenceLength, int accMode,
+                           const std::vector<int32_t>& promptTokens, const std::function<void(GenerationState, int32_t)>& emit) {
+  model::InferenceContext infContext(transformer, sequenceLength, accMode);
+  const int promptLength = (int)promptTokens.size();
+  if (promptLength >= infContext.SequenceLength)
+    throw Error("context SequenceLength " + std::to_string(infContext.SequenceLength) + " must be higher than prompt tokens length " +
+                std::to_string(promptLength));
+  std::vector<int32_t> tokens(infContext.SequenceLength, vocab.PadId);  // ml.Full(..., PadId) :181
+  std::copy(promptTokens.begin(), promptTokens.end(), tokens.begin());
+  int prevPos = 0;
+  for (int curPos = promptLength; curPos < infContext.SequenceLength; curPos++) {  // :194
+    ml::Tensor slice({curPos - prevPos}, ml::DataType::INT32);                     // tokens.Slice([prevPos],[curPos]) :195
+    std::memcpy(slice.RawData.data(), tokens.data() + prevPos, (size_t)(curPos - prevPos) * 4);
+    ml::Tensor logits = infContext.Forward(slice, prevPos);                        // :202
+    const int rows = logits.Size[0], V = logits.Size[1];
+    ml::Tensor last({1, V}, ml::DataType::F32);                                    // logits.Slice(last row) :207
+    std::memcpy(last.RawData.data(), logits.data<float>() + (size_t)(rows - 1) * V, (size_t)V * 4);
+    int32_t nextTokenId = ml::Argmax(last).data<int32_t>()[0];                     // :211
+    if (tokens[curPos] != vocab.PadId) nextTokenId = tokens[curPos];               // :218-226
+    tokens[curPos] = nextTokenId;
+    bool eos = false;
+    for (int32_t s : vocab.StopTokenIds) eos |= (s == nextTokenId);
+    prevPos = curPos;
+    if (eos) { emit(GSFinishedByReachingEOS, nextTokenId); break; }                 // :233-240
+    if (curPos + 1 == infContext.SequenceLength) { emit(GSFinishedByReachingSeqLen, nextTokenId); break; }
+    emit(GSInProgress, nextTokenId);
+  }
+}
+}  // namespace inference
+}  // namespace lnb_host

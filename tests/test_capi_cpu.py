@@ -147,3 +147,14 @@ def test_ml_tensor_host_ops_match_reference_semantics():
     f = ml.Tensor(np.array([[1.53, -2.0]], np.float32), ml.DT_F32)
     assert f.ToBFloat16().ToFloat32().RawData[0, 0] == np.float32(1.5234375)
     assert ml.Full([3], ml.DT_INT32, -1).RawData.tolist() == [-1, -1, -1]
+
+
+def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu():
+    """the C++ host mirror (host/lnb_host.hpp) compiles against include/lnb.h and links liblnb.so"""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "-s"])
+    exe = os.path.join(ROOT, "host", "lnb_generate")
+    assert os.path.exists(exe)
+    if L._capi.lib.lnb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    out = subprocess.run([exe, "16", "strict", "tiny"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "lnb:" in out.stderr          # no CPU fallback

@@ -231,3 +231,23 @@ def test_prefill_strict_stays_bit_exact_for_long_prompts(L, tiny):
         assert np.array_equal(got, exp)
     finally:
         ctx.close(); osess.close()
+
+
+def test_cpp_host_mirror_generates_the_oracle_tokens(L):
+    """host/lnb_generate: the C++ mirror of src/ml + src/model + src/inference (reference-shaped loop:
+    Forward -> logits to host -> Slice -> ml.Argmax) over the C-ABI, on the device-generated tiny model."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "lnb_generate")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "host"), "-s"])
+    out = subprocess.run([exe, "24", "strict", "tiny"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    line = [l for l in out.stdout.splitlines() if l.startswith("tokens:")][0]
+    got = [int(t) for t in line.split()[1:]]
+    args = dict(L.synth.TINY)
+    om = oracle_model(args, host_tensors(args, 7))
+    exp = list(om.generate([1, 50, 999, 7, 300, 12, 64, 2], 24, stop_ids=(10**9,)))
+    om.close()
+    assert got == exp
