@@ -125,6 +125,17 @@ int lnb_session_destroy(lnb_session* s);
 int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int start_pos,
                 float* logits, int all_rows, int32_t* argmax_last);
 
+/* Batched decode (BASELINE.json configs[4], "concurrent prompts"): a session with n_seq (<= 8) independent
+ * sequences = n_seq reference InferenceContexts sharing one set of weights (the reference has no batch
+ * dimension).  lnb_session_set_active_sequence selects which sequence lnb_forward /
+ * lnb_decode_run / lnb_session_read address (e.g. to prefill each prompt); lnb_forward_batch then advances
+ * all sequences by one token in ONE pass over the weights: row i = sequence i, token tokens[i] at position
+ * positions[i].  Every row gets exactly the arithmetic of its own S=1 Forward. */
+int lnb_session_create_batch(lnb_model* m, int seq_len, int n_seq, int max_rows, int acc_mode, lnb_session** out);
+int lnb_session_set_active_sequence(lnb_session* s, int seq);
+int lnb_forward_batch(lnb_session* s, const int32_t* tokens, const int32_t* positions, int n,
+                      float* logits /* NULL or [n, vocab] */, int32_t* argmax_out /* [n] */);
+
 /* Device-resident greedy decode: runs n_steps consecutive S=1 forwards starting with
  * `first_token` at position start_pos, feeding each argmax back on the device (no host
  * sync inside), optionally as CUDA-graph replays.  tokens_out[n_steps]; ms_out = device

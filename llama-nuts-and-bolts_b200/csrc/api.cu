@@ -636,6 +636,7 @@ static bool tc_eligible(int M, int N, int K) { return M >= 32 && N % TC_BN == 0 
 // session
 __global__ void set_state_kernel(LnbDevState* st, int pos, int n_rows, int next_token, int reset_step) {
   st->pos = pos;
+  st->safe_rows = pos;  // rows before this call's first position come from earlier, synchronised calls
   st->n_rows = n_rows;
   st->amax_key = LNB_ARGMAX_EMPTY;
   st->done_ctr = 0;
@@ -688,6 +689,11 @@ struct lnb_session {
   int32_t* d_tok_out = nullptr;
   int32_t* h_pin = nullptr;
   int layer_limit = 0;
+  // batched decode (BASELINE config 5): n_seq independent sequences share the weights; caches are
+  // [n_seq][seq_len][kv]; single-sequence calls address the cache of `active_seq`
+  int n_seq = 1, active_seq = 0;
+  int32_t* d_pos_arr = nullptr;   // [n_seq] positions of the current batched step
+  int32_t* d_next_arr = nullptr;  // [n_seq] greedy tokens of the current batched step
   bool sdpa_smem_decode = false;  // the whole K/V history of one KV head fits in shared memory
   size_t sdpa_decode_smem = 0;
   int64_t launches = 0;
@@ -698,7 +704,15 @@ struct lnb_session {
   int last_rows = 0;
 };
 
+static int session_create_impl(lnb_model* m, int seq_len, int max_rows, int acc_mode, int n_seq, lnb_session** out);
 extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int acc_mode, lnb_session** out) {
+  return session_create_impl(m, seq_len, max_rows, acc_mode, 1, out);
+}
+extern "C" int lnb_session_create_batch(lnb_model* m, int seq_len, int n_seq, int max_rows, int acc_mode, lnb_session** out) {
+  if (n_seq < 1 || n_seq > 8) return fail(LNB_EINVAL, "n_seq must be 1..8");
+  return session_create_impl(m, seq_len, max_rows < n_seq ? n_seq : max_rows, acc_mode, n_seq, out);
+}
+static int session_create_impl(lnb_model* m, int seq_len, int max_rows, int acc_mode, int n_seq, lnb_session** out) {
   if (!m || !out) return fail(LNB_EINVAL, "NULL argument");
   if (!m->finalized) return fail(LNB_ESTATE, "model is not finalized");
   if (seq_len <= 0 || max_rows <= 0) return fail(LNB_EINVAL, "seq_len and max_rows must be positive");
@@ -714,6 +728,7 @@ extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int a
   s->seq_len = seq_len;
   s->max_rows = max_rows;
   s->mode = acc_mode;
+  s->n_seq = n_seq;
   const lnb_model_args& a = m->a;
   {
     const int n_rep = a.n_heads / a.n_kv_heads;
@@ -746,7 +761,9 @@ extern "C" int lnb_session_create(lnb_model* m, int seq_len, int max_rows, int a
   al((void**)&s->d_tok_out, (size_t)seq_len * 4);
   s->ck.assign(a.n_layers, nullptr);
   s->cv.assign(a.n_layers, nullptr);
-  const size_t cbytes = (size_t)seq_len * m->kv_l * 2;
+  const size_t cbytes = (size_t)n_seq * seq_len * m->kv_l * 2;
+  al((void**)&s->d_pos_arr, 8 * 4);
+  al((void**)&s->d_next_arr, 8 * 4);
   for (int l = 0; l < a.n_layers; l++) {
     al((void**)&s->ck[l], cbytes);
     al((void**)&s->cv[l], cbytes);
@@ -776,7 +793,7 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   for (int r = 0; r < 8; r++)
     if (s->p2p_peer[r]) cudaIpcCloseMemHandle(s->p2p_peer[r]);
   cudaFree(s->p2p_region);
-  cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out);
+  cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out); cudaFree(s->d_pos_arr); cudaFree(s->d_next_arr);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
   if (s->h_pin) cudaFreeHost(s->h_pin);
@@ -870,12 +887,16 @@ static int ensure_logits(lnb_session* s, size_t rows) {
 // Enqueue one LlamaTransformer.Forward (llamatransformer.go:145-180) for S rows on the
 // session stream.  from_state_token: row 0's token is st->next_token (device-driven decode).
 // logits_rows: 0 = none stored, 1 = last row, S = all rows.  advance: decode-loop bookkeeping.
-static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int logits_rows, bool advance, bool pdl) {
+static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int logits_rows, bool advance, bool pdl, bool batch = false) {
   lnb_model* m = s->m;
   const lnb_model_args& a = m->a;
   Launcher L{s->stream, pdl, &s->launches};
   const int mode = s->mode;
   const int32_t* pos_ptr = &s->st->pos;
+  // single-sequence calls work on the cache of the active sequence; a batched step addresses all of them
+  const size_t seq_stride = (size_t)s->seq_len * m->kv_l;
+  const size_t cache_off = batch ? 0 : (size_t)s->active_seq * seq_stride;
+  if (batch && !s->sdpa_smem_decode) return fail(LNB_EINVAL, "batched decode needs SequenceLength small enough for the shared-memory attention kernel");
   int rc;
   rc = launch_simple(L, gather_rows_kernel, dim3(S), dim3(256), 0, (const uint16_t*)m->tok_embd,
                      (const int32_t*)(from_state_token ? nullptr : s->d_tokens), (const LnbDevState*)s->st, s->x, a.dim);
@@ -905,18 +926,21 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
       p.x = s->x; p.ldx = a.dim; p.norm_w = W.attn_norm; p.eps = a.norm_eps;
       p.out_bf16 = s->q; p.ldo = m->q_l;
       p.q_dim = m->q_l; p.kv_dim = m->kv_l; p.head_dim = a.head_dim;
-      p.cache_k = s->ck[l]; p.cache_v = s->cv[l]; p.cis = m->cis; p.pos_ptr = pos_ptr;
+      p.cache_k = s->ck[l] + cache_off; p.cache_v = s->cv[l] + cache_off; p.cis = m->cis; p.pos_ptr = pos_ptr;
+      if (batch) { p.pos_arr = s->d_pos_arr; p.cache_seq_stride = (long long)seq_stride; }
       if ((rc = launch_gemv<PRO_RMSNORM, EPI_QKV_ROPE>(L, mode, p, S))) return rc;
     }
-    if (S == 1 && s->sdpa_smem_decode) {
+    if ((S == 1 || batch) && s->sdpa_smem_decode) {
       const int n_rep = a.n_heads / a.n_kv_heads;
-      rc = launch_simple(L, sdpa_decode_kernel, dim3(m->kv_l / a.head_dim), dim3(128 * n_rep), s->sdpa_decode_smem, (const uint16_t*)s->q,
-                         (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, n_rep, a.head_dim, s->o, pos_ptr, s->seq_len,
-                         mode == LNB_ACC_STRICT ? 1 : 0, scale);
+      rc = launch_simple(L, sdpa_decode_kernel, dim3(m->kv_l / a.head_dim, batch ? S : 1), dim3(128 * n_rep), s->sdpa_decode_smem,
+                         (const uint16_t*)s->q, (const uint16_t*)(s->ck[l] + cache_off), (const uint16_t*)(s->cv[l] + cache_off), m->kv_l,
+                         n_rep, a.head_dim, s->o, pos_ptr, s->seq_len, mode == LNB_ACC_STRICT ? 1 : 0, scale,
+                         (const int32_t*)(batch ? s->d_pos_arr : nullptr), (long long)seq_stride, m->q_l, (const LnbDevState*)s->st);
     } else {
       rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
-                         (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
-                         s->o, m->q_l, pos_ptr, 0, S, S > 1 ? 1 : 0, mode == LNB_ACC_STRICT ? 1 : 0, scale, 0);
+                         (const uint16_t*)(s->ck[l] + cache_off), (const uint16_t*)(s->cv[l] + cache_off), m->kv_l,
+                         a.n_heads / a.n_kv_heads, a.head_dim, s->o, m->q_l, pos_ptr, 0, S, S > 1 ? 1 : 0,
+                         mode == LNB_ACC_STRICT ? 1 : 0, scale, 0);
     }
     if (rc) return rc;
     {  // wo + residual                                             (:522, :232)
@@ -984,11 +1008,19 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
     p.x = s->x + (size_t)row0 * a.dim; p.ldx = a.dim; p.norm_w = m->norm; p.eps = a.norm_eps;
     p.out_f32 = logits_rows > 0 ? s->logits : nullptr; p.ldo = m->vocab_l;
     p.n_offset = m->tp_rank * m->vocab_l;
-    p.st = s->st; p.argmax_row = rows - 1; p.m_off = 0;
+    p.st = batch ? nullptr : s->st; p.argmax_row = batch ? -1 : rows - 1; p.m_off = 0;
     p.publish = (m->tp_size == 1) ? 1 : 0;
     p.advance = advance ? 1 : 0; p.tok_out = s->d_tok_out;
     if ((rc = launch_gemv<PRO_RMSNORM, EPI_LOGITS>(L, mode, p, rows))) return rc;
-    if (m->tp_size > 1) {
+    if (batch) {
+      // every row is the last row of its own sequence: one greedy argmax per row on the (gathered) logits
+      if (m->tp_size > 1)
+        for (int r = 0; r < rows; r++)
+          NC(g_nccl.AllGather(s->logits + (size_t)r * m->vocab_l, s->logits_full + (size_t)r * a.vocab_size, m->vocab_l, ncclFloat32_,
+                              m->comm, s->stream));
+      const float* lg = (m->tp_size > 1) ? s->logits_full : s->logits;
+      if ((rc = launch_simple(L, argmax_f32_kernel, dim3(rows), dim3(256), 0, lg, a.vocab_size, s->d_next_arr))) return rc;
+    } else if (m->tp_size > 1) {
       if (s->p2p_ready) {
         if ((rc = launch_simple(L, p2p_argmax_kernel, dim3(1), dim3(32), 0, s->p2p, s->st, advance ? 1 : 0, s->d_tok_out))) return rc;
       } else {
@@ -1021,6 +1053,7 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows) {
   const int32_t* pos_ptr = &s->st->pos;
   const int Mpad = (S + TC_BM - 1) / TC_BM * TC_BM;
   const int qkv_n = m->q_l + 2 * m->kv_l;
+  const size_t tc_cache_off = (size_t)s->active_seq * s->seq_len * m->kv_l;
   int rc;
   if ((rc = launch_simple(L, gather_rows_kernel, dim3(S), dim3(256), 0, (const uint16_t*)m->tok_embd, (const int32_t*)s->d_tokens,
                           (const LnbDevState*)s->st, s->x, a.dim)))
@@ -1046,16 +1079,16 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows) {
       if ((rc = launch_gemm_tc<TC_EPI_BF16>(L, g))) return rc;
     }
     if ((rc = launch_simple(L, rope_kv_kernel, dim3(ew_grid), dim3(256), 0, (const uint16_t*)s->qkv_raw, qkv_n, s->q, m->q_l, m->kv_l,
-                            a.head_dim, s->ck[l], s->cv[l], (const float*)m->cis, pos_ptr, S)))
+                            a.head_dim, s->ck[l] + tc_cache_off, s->cv[l] + tc_cache_off, (const float*)m->cis, pos_ptr, S)))
       return rc;
     if (a.head_dim == SP_HD) {
       if ((rc = launch_simple(L, sdpa_prefill_kernel, dim3(m->q_l / a.head_dim, (S + SP_QB - 1) / SP_QB), dim3(256), (size_t)SP_SMEM,
-                              (const uint16_t*)s->q, m->q_l, (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l,
-                              a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale)))
+                              (const uint16_t*)s->q, m->q_l, (const uint16_t*)(s->ck[l] + tc_cache_off),
+                              (const uint16_t*)(s->cv[l] + tc_cache_off), m->kv_l, a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale)))
         return rc;
     } else if ((rc = launch_simple(L, sdpa_kernel, dim3(m->q_l / a.head_dim, S), dim3(128), sdpa_smem, (const uint16_t*)s->q, m->q_l,
-                                   (const uint16_t*)s->ck[l], (const uint16_t*)s->cv[l], m->kv_l, a.n_heads / a.n_kv_heads, a.head_dim,
-                                   s->o8, m->q_l, pos_ptr, 0, S, 1, 0, scale, 1)))
+                                   (const uint16_t*)(s->ck[l] + tc_cache_off), (const uint16_t*)(s->cv[l] + tc_cache_off), m->kv_l,
+                                   a.n_heads / a.n_kv_heads, a.head_dim, s->o8, m->q_l, pos_ptr, 0, S, 1, 0, scale, 1)))
       return rc;
     {
       GemmTcParams g{};
@@ -1171,6 +1204,52 @@ extern "C" int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int sta
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
   if (argmax_last) *argmax_last = *tokpin;
+  return 0;
+}
+
+// ---- batched decode (BASELINE config 5: concurrent prompts) --------------------------------------
+extern "C" int lnb_session_set_active_sequence(lnb_session* s, int seq) {
+  if (!s) return fail(LNB_EINVAL, "session is NULL");
+  if (seq < 0 || seq >= s->n_seq) return fail(LNB_EINVAL, "sequence %d out of range (session has %d)", seq, s->n_seq);
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->active_seq = seq;
+  return 0;
+}
+// One decode step for n independent sequences (rows 0..n-1 = sequences 0..n-1): tokens[i] is fed at
+// positions[i] of sequence i.  The weights are streamed ONCE for all rows (the reference would run n
+// separate Forward calls on n InferenceContexts; every row sees exactly the arithmetic of its
+// own S=1 Forward).  logits: NULL or host [n, vocab] f32; argmax_out[n] = greedy token per sequence.
+extern "C" int lnb_forward_batch(lnb_session* s, const int32_t* tokens, const int32_t* positions, int n, float* logits,
+                                 int32_t* argmax_out) {
+  if (!s || !tokens || !positions) return fail(LNB_EINVAL, "NULL argument");
+  if (n < 1 || n > s->n_seq) return fail(LNB_EINVAL, "n %d exceeds the session's %d sequences", n, s->n_seq);
+  for (int i = 0; i < n; i++) {
+    if (tokens[i] < 0 || tokens[i] >= s->m->a.vocab_size) return fail(LNB_EINVAL, "token id %d out of range", tokens[i]);
+    if (positions[i] < 0 || positions[i] >= s->seq_len) return fail(LNB_EINVAL, "position %d exceeds SequenceLength %d", positions[i], s->seq_len);
+  }
+  std::lock_guard<std::mutex> lk(s->mu);
+  lnb_model* m = s->m;
+  CU(cudaSetDevice(m->device));
+  int rc = ensure_logits(s, (size_t)s->max_rows);
+  if (rc) return rc;
+  memcpy(s->h_pin, tokens, (size_t)n * 4);
+  int32_t* ppin = s->h_pin + s->max_rows;
+  memcpy(ppin, positions, (size_t)n * 4);
+  CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_pos_arr, ppin, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, 0, n, -1, 0);
+  s->launches++;
+  rc = enqueue_forward(s, n, false, n > 1 ? n : 2, false, true, true);
+  if (rc) return rc;
+  if (logits) {
+    const float* src = (m->tp_size > 1) ? s->logits_full : s->logits;
+    CU(cudaMemcpyAsync(logits, src, (size_t)n * m->a.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
+  }
+  int32_t* npin = s->h_pin + s->max_rows + 16;
+  if (argmax_out) CU(cudaMemcpyAsync(npin, s->d_next_arr, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  if (argmax_out) memcpy(argmax_out, npin, (size_t)n * 4);
   return 0;
 }
 
@@ -1320,7 +1399,7 @@ extern "C" int lnb_session_read(lnb_session* s, int which, int layer, void* host
     case LNB_BUF_CACHE_K:
     case LNB_BUF_CACHE_V:
       if (layer < 0 || layer >= m->a.n_layers) return fail(LNB_EINVAL, "bad layer %d", layer);
-      src = which == LNB_BUF_CACHE_K ? s->ck[layer] : s->cv[layer];
+      src = (which == LNB_BUF_CACHE_K ? s->ck[layer] : s->cv[layer]) + (size_t)s->active_seq * s->seq_len * m->kv_l;
       avail = (int64_t)s->seq_len * m->kv_l * 2;
       break;
     case LNB_BUF_LOGITS: src = s->logits; avail = (int64_t)s->logits_rows * m->vocab_l * 4; break;

@@ -101,7 +101,7 @@ struct LnbDevState {
   uint32_t done_ctr;             // CTAs of the LM-head kernel that finished
   int32_t next_token;            // greedy token of the last row
   int32_t step;                  // decode-run step counter
-  int32_t pad;
+  int32_t safe_rows;             // KV rows [0, safe_rows) were complete before this call was enqueued (host-synchronised)
   uint32_t ar_epoch;             // sequence number of the next peer all-reduce (same on every rank)
   uint32_t ar_done;              // (unused)
   uint32_t ar_done2;             // CTAs of the reducing kernel that have finished

@@ -57,8 +57,10 @@ struct GemvParams {
   const uint16_t* res;     // EPI_RESID residual [M, ldo]
   // EPI_QKV_ROPE
   int q_dim, kv_dim, head_dim;
-  uint16_t* cache_k;       // [seq_len, kv_dim]
+  uint16_t* cache_k;       // [seq_len, kv_dim]  (batched decode: sequence b at + b * cache_seq_stride)
   uint16_t* cache_v;
+  const int32_t* pos_arr;  // batched decode (one row per independent sequence): position of row m; NULL -> *pos_ptr + m
+  long long cache_seq_stride;  // elements between the caches of consecutive sequences (batched decode)
   const float* cis;        // [rows][head_dim/2][2]
   // EPI_SWIGLU
   const uint16_t* silu_tab;
@@ -138,7 +140,10 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
     const float mine = trunc_bf(v);                                     // t(linear)  (:306-344)
     const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
     if (valid) {
-      const int pos = *p.pos_ptr + p.m_off + em;
+      const int row = p.m_off + em;
+      const int pos = p.pos_arr ? p.pos_arr[row] : *p.pos_ptr + row;
+      uint16_t* ck = p.cache_k + (p.pos_arr ? (size_t)row * (size_t)p.cache_seq_stride : 0);
+      uint16_t* cv = p.cache_v + (p.pos_arr ? (size_t)row * (size_t)p.cache_seq_stride : 0);
       if (n < p.q_dim + p.kv_dim) {
         const int nn = (n < p.q_dim) ? n : n - p.q_dim;
         const int i = (nn % p.head_dim) >> 1;
@@ -153,9 +158,9 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
           o = (float)(a * dd + b * cc);
         }
         if (n < p.q_dim) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(o);
-        else p.cache_k[(size_t)pos * p.kv_dim + nn] = f2bf(o);           // SetSlice :402
+        else ck[(size_t)pos * p.kv_dim + nn] = f2bf(o);                  // SetSlice :402
       } else {
-        p.cache_v[(size_t)pos * p.kv_dim + (n - p.q_dim - p.kv_dim)] = f2bf(mine);  // :403
+        cv[(size_t)pos * p.kv_dim + (n - p.q_dim - p.kv_dim)] = f2bf(mine);         // :403
       }
     }
   } else if (EPI == EPI_SWIGLU) {

@@ -178,10 +178,9 @@ __global__ void __launch_bounds__(128) sdpa_kernel(const uint16_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // Decode attention (S == 1), one CTA per KV head serving its n_rep query heads (GQA: K and V are read
 // once per KV head instead of once per query head; attentionRepeatKV :529-559 is pure indexing).
-// Same arithmetic, truncation points and summation orders as sdpa_kernel.  The K / V rows of EARLIER
-// positions do not depend on the previous kernel, so they are staged into shared memory with cp.async
-// BEFORE griddepcontrol.wait (overlapping the QKV projection's tail); only the row of the current
-// position and q are fetched after it.  K rows are padded to hd+8 elements (bank-conflict-free
+// Same arithmetic, truncation points and summation orders as sdpa_kernel.  The K / V rows that were
+// complete before this call was enqueued (the prompt) are staged into shared memory with cp.async BEFORE
+// griddepcontrol.wait (overlapping the QKV projection's tail); later rows and q are fetched after it.  K rows are padded to hd+8 elements (bank-conflict-free
 // 128-bit reads for "one thread = one key").  block = 128 * n_rep threads (thread = (query head, key or d)).
 // dyn smem = T_max * ((hd + 8) + hd) * 2  +  n_rep * (hd * 4 + T_max * 12) + 64
 LNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc) {
@@ -192,7 +191,9 @@ LNB_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "mem
 __global__ void __launch_bounds__(1024) sdpa_decode_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ cache_k,
                                                            const uint16_t* __restrict__ cache_v, int kv_dim, int n_rep, int hd,
                                                            uint16_t* __restrict__ out, const int32_t* __restrict__ pos_ptr,
-                                                           int T_max, int strict, float scale_bf16_as_f32) {
+                                                           int T_max, int strict, float scale_bf16_as_f32,
+                                                           const int32_t* __restrict__ pos_arr, long long cache_seq_stride, int ldq,
+                                                           const LnbDevState* __restrict__ st) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int kstride = hd + 8;
   uint16_t* sK = reinterpret_cast<uint16_t*>(sm);                       // [T_max][hd + 8]
@@ -205,25 +206,33 @@ __global__ void __launch_bounds__(1024) sdpa_decode_kernel(const uint16_t* __res
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int hh = tid / 128, tt = tid % 128;
   const int cpr = hd / 8;  // 16-byte chunks per row
+  // batched decode: blockIdx.y = independent sequence (own cache, own position, own q / output row)
+  if (pos_arr) {
+    pos_ptr = pos_arr + blockIdx.y;
+    cache_k += (size_t)blockIdx.y * (size_t)cache_seq_stride;
+    cache_v += (size_t)blockIdx.y * (size_t)cache_seq_stride;
+    q += (size_t)blockIdx.y * ldq;
+    out += (size_t)blockIdx.y * ldq;
+  }
 
   pdl_launch_dependents();
-  // positions < pos were written by earlier decode steps; pos itself (read below) is only known after the
-  // wait, but the cache is append-only, so rows [0, pos_old] are a safe prefix: stage rows [0, T_max) that
-  // exist is NOT known yet -> read pos first (cheap), rows < pos are immutable for this step
-  // (with programmatic dependent launch this kernel may start before the kernel that advances pos has
-  //  finished: pos_early may be stale; it is only used as a hint -- rows >= min(pos_early, pos) are
-  //  (re)loaded after the wait)
-  const int pos_early = max(0, min(*reinterpret_cast<const volatile int32_t*>(pos_ptr), T_max - 1));
-  for (int i = tid; i < pos_early * cpr; i += nthr) {
+  // With programmatic dependent launch this code may run while ANY earlier kernel of the stream is still
+  // in flight (a kernel may start once its predecessor has started, not finished -- with small grids a
+  // whole decode step can be resident at once), so only cache rows that were complete before the host
+  // enqueued this call may be touched before the wait: rows [0, safe_rows), fixed by set_state_kernel at
+  // the start of the call.  Everything else -- including rows appended by earlier steps of the same
+  // device-resident decode run -- is loaded after griddepcontrol.wait.
+  const int safe = (pos_arr || !st) ? 0 : max(0, min(st->safe_rows, T_max));
+  for (int i = tid; i < safe * cpr; i += nthr) {
     const int t = i / cpr, c = i % cpr;
     cp_async16(sK + (size_t)t * kstride + c * 8, cache_k + (size_t)t * kv_dim + (size_t)h * hd + c * 8);
     cp_async16(sV + (size_t)t * hd + c * 8, cache_v + (size_t)t * kv_dim + (size_t)h * hd + c * 8);
   }
   pdl_wait();
-  const int pos = *pos_ptr;
+  const int pos = __ldcg(pos_ptr);
   const int T = pos + 1;
-  const int lo = min(pos_early, pos);
-  for (int i = tid; i < (T - lo) * cpr; i += nthr) {  // the row(s) written by this step's QKV kernel (+ any not staged yet)
+  const int lo = min(safe, T);
+  for (int i = tid; i < (T - lo) * cpr; i += nthr) {
     const int t = lo + i / cpr, c = i % cpr;
     cp_async16(sK + (size_t)t * kstride + c * 8, cache_k + (size_t)t * kv_dim + (size_t)h * hd + c * 8);
     cp_async16(sV + (size_t)t * hd + c * 8, cache_v + (size_t)t * kv_dim + (size_t)h * hd + c * 8);
@@ -721,6 +730,8 @@ __global__ void softmax_f32_kernel(const float* __restrict__ x, float* __restric
 // ml.Argmax (operations_impl.go:513-548): first maximum wins, NaN and values <= -MaxFloat32
 // are never selected (-1 if nothing is).
 __global__ void __launch_bounds__(256) argmax_f32_kernel(const float* __restrict__ x, int cols, int32_t* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();  // also used inside the forward chain (batched decode)
   __shared__ unsigned long long best[8];
   const float* xr = x + (size_t)blockIdx.x * cols;
   unsigned long long key = LNB_ARGMAX_EMPTY;

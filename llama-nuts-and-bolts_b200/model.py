@@ -138,15 +138,19 @@ class InferenceContext:
     """model.InferenceContext (inferencecontext.go:8-46): the KV cache (here: in HBM)."""
 
     def __init__(self, transformer: LlamaTransformer, inferenceArgs: InferenceArgs, logFn=None,
-                 max_rows: int = 8, acc_mode: int = LNB_ACC_FAST):
+                 max_rows: int = 8, acc_mode: int = LNB_ACC_FAST, n_seq: int = 1):
         self.transformer = transformer
         self.SequenceLength = inferenceArgs.SequenceLength if inferenceArgs.SequenceLength > 0 \
             else transformer.args.MaxSequenceLength
         self.logFn = logFn
         self.acc_mode = acc_mode
         self.max_rows = max_rows
+        self.n_seq = n_seq
         h = C.c_void_p()
-        check(lib.lnb_session_create(transformer.h, self.SequenceLength, max_rows, acc_mode, C.byref(h)))
+        if n_seq > 1:   # n_seq reference InferenceContexts that share the weights (batched decode)
+            check(lib.lnb_session_create_batch(transformer.h, self.SequenceLength, n_seq, max_rows, acc_mode, C.byref(h)))
+        else:
+            check(lib.lnb_session_create(transformer.h, self.SequenceLength, max_rows, acc_mode, C.byref(h)))
         self.h = h
 
     def Logf(self, fmt, *v):
@@ -171,6 +175,20 @@ class InferenceContext:
         out = np.empty((rows, self.transformer.args.Dim), np.uint16)
         check(lib.lnb_session_read(self.h, _capi.LNB_BUF_RESIDUAL, 0, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
+
+    def set_active_sequence(self, seq: int):
+        check(lib.lnb_session_set_active_sequence(self.h, seq))
+
+    def forward_batch(self, tokens, positions, want_logits: bool = False):
+        """one decode step for len(tokens) independent sequences: (greedy tokens [n], logits [n, vocab] or None)"""
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        positions = np.ascontiguousarray(positions, np.int32)
+        n = tokens.shape[0]
+        nxt = np.empty(n, np.int32)
+        logits = np.empty((n, self.transformer.args.VocabSize), np.float32) if want_logits else None
+        check(lib.lnb_forward_batch(self.h, ptr(tokens, _capi.i32p), ptr(positions, _capi.i32p), n,
+                                    ptr(logits, _capi.f32p) if want_logits else None, ptr(nxt, _capi.i32p)))
+        return nxt, logits
 
     def set_layer_limit(self, n: int):
         check(lib.lnb_session_set_layer_limit(self.h, n))

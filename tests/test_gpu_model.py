@@ -251,3 +251,51 @@ def test_cpp_host_mirror_generates_the_oracle_tokens(L):
     exp = list(om.generate([1, 50, 999, 7, 300, 12, 64, 2], 24, stop_ids=(10**9,)))
     om.close()
     assert got == exp
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_batched_decode_equals_independent_contexts(L, tiny, mode):
+    """config 5: n_seq sequences stepped together through one pass over the weights; STRICT: every sequence is
+    bit-identical to its own oracle InferenceContext (different prompt lengths, different positions)."""
+    args, _, om, gm = tiny
+    acc = L._capi.LNB_ACC_STRICT if mode == "strict" else L._capi.LNB_ACC_FAST
+    rng = np.random.default_rng(55)
+    seq, nseq = 32, 5
+    prompts = [rng.integers(0, args["vocab_size"], size=k).astype(np.int32) for k in (3, 8, 1, 6, 8)]
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(seq), max_rows=8, acc_mode=acc, n_seq=nseq)
+    osess = [om.new_session(seq) for _ in range(nseq)]
+    try:
+        cur, pos = [], []
+        for i, p in enumerate(prompts):                      # prefill every sequence through the ordinary Forward
+            ctx.set_active_sequence(i)
+            nxt, lg = gm.Transformer.forward_argmax(ctx, p, 0, want_logits="last")
+            exp = osess[i].forward(p, 0, all_rows=False)
+            if mode == "strict":
+                assert np.array_equal(lg, exp)
+            cur.append(int(np.argmax(exp[0]))); pos.append(len(p))
+            assert mode != "strict" or nxt == cur[-1]
+        for step in range(6):
+            nxt, lg = ctx.forward_batch(cur, pos, want_logits=True)
+            for i in range(nseq):
+                exp = osess[i].forward(np.array([cur[i]], np.int32), pos[i])
+                if mode == "strict":
+                    assert np.array_equal(lg[i], exp[0]), f"sequence {i} step {step}"
+                    assert nxt[i] == O.argmax_f32(exp[0])
+                else:
+                    assert np.abs(lg[i] - exp[0]).max() <= 1e-2
+                cur[i] = int(np.argmax(exp[0])); pos[i] += 1   # teacher-forced with the oracle's token
+        if mode == "strict":
+            for i in range(nseq):                            # caches of every sequence, all layers
+                ctx.set_active_sequence(i)
+                for layer in range(args["n_layers"]):
+                    ok, ov = osess[i].cache(layer)
+                    assert np.array_equal(ctx.CacheK(layer).RawData[:pos[i]], ok[:pos[i]])
+                    assert np.array_equal(ctx.CacheV(layer).RawData[:pos[i]], ov[:pos[i]])
+        with pytest.raises(L._capi.LnbError):
+            ctx.forward_batch([1] * (nseq + 1), [0] * (nseq + 1))
+        with pytest.raises(L._capi.LnbError):
+            ctx.set_active_sequence(nseq)
+    finally:
+        ctx.close()
+        for o in osess:
+            o.close()
