@@ -182,6 +182,12 @@ int lnb_op_linear_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int 
 int lnb_op_matmul_bf16(const uint16_t* a, const uint16_t* b, uint16_t* out, int B, int M, int K, int N);
 /* RMSNorm.Forward (src/model/llamatransformer.go:633-660) */
 int lnb_op_rmsnorm_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int S, int D, float eps, int acc_mode);
+/* the scale of RMSNorm.Forward alone (llamatransformer.go:641-656: Pow, Mean, AddScalar, RSqrt):
+ * r[s] = f32(1 / sqrt(f64( (sequential fp32 sum_k x[s,k]^2) / D + eps ))), bit-exact.
+ * algo: 0 = what the model path uses (env LNB_RMS_ALGO=chain|scan|seg overrides the built-in choice),
+ * 1 = one-thread FADD chain, 2 = iterative binade scan, 3 = one-pass predict / fold / walk
+ * (csrc/seqsum.cuh; 2 and 3 return LNB_EINVAL when D does not fit their shape).  Identical bits. */
+int lnb_op_rms_scale_f32(const uint16_t* x, float* r, int S, int D, float eps, int algo);
 /* applyRotaryEmbeddings for one tensor (llamatransformer.go:753-790): x[S,H,hd] */
 int lnb_op_rope_bf16(const uint16_t* x, const float* cis, uint16_t* out, int S, int H, int hd, int start_pos);
 /* the attention core of LlamaAttention.Forward (llamatransformer.go:402-514):

@@ -66,6 +66,7 @@ SIGNATURES = {
     "lnb_op_linear_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_matmul_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_rmsnorm_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_float, C.c_int]),
+    "lnb_op_rms_scale_f32": (C.c_int, [u16p, f32p, C.c_int, C.c_int, C.c_float, C.c_int]),
     "lnb_op_rope_bf16": (C.c_int, [u16p, f32p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_attention_bf16": (C.c_int, [u16p, u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_silu_bf16": (C.c_int, [u16p, u16p, C.c_int64]),

@@ -580,14 +580,17 @@ __global__ void matmul_naive_kernel(const uint16_t* __restrict__ a, const uint16
 // RMSNorm.Forward (llamatransformer.go:633-660), one CTA (256 threads) per row.
 // strict: sequential sum; fast: the same 256-way interleave + butterfly as gemv.cuh's prologue.
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w,
-                                                      uint16_t* __restrict__ out, int D, float eps, int strict) {
+                                                      uint16_t* __restrict__ out, int D, float eps, int strict,
+                                                      const float* __restrict__ rscale) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float wsum[8];
   __shared__ float rs;
   const uint16_t* xr = x + (size_t)blockIdx.x * D;
   const int tid = threadIdx.x;
-  if (strict) {
+  if (rscale) {  // 1/rms already computed (rms_scale_kernel / rms_scale_scan_kernel)
+    if (tid == 0) rs = rscale[blockIdx.x];
+  } else if (strict) {
     if (tid == 0) {
       float sum = 0.f;
       for (int k = 0; k < D; k++) {

@@ -278,6 +278,11 @@ static float rms_scale(const uint16_t* xr, int D, float eps) {
   return (float)(1.0 / sqrt((double)me));     /* RSqrt :300 */
 }
 
+/* the scale alone (llamatransformer.go:641-656), for white-box checks of the GPU scale kernels */
+void orc_rms_scale(const uint16_t* x, float* r, int S, int D, float eps) {
+  for (int s = 0; s < S; s++) r[s] = rms_scale(x + (size_t)s * D, D, eps);
+}
+
 void orc_rmsnorm_stage1(const uint16_t* x, uint16_t* out, int S, int D, float eps) {
   for (int s = 0; s < S; s++) {
     const uint16_t* xr = x + (size_t)s * D;

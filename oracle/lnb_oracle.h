@@ -64,6 +64,7 @@ void orc_get_rows_bf16(const uint16_t* emb, const int32_t* tokens, uint16_t* out
 
 /* ---- src/model pieces ---- */
 /* RMSNorm.doNormalization (stage 1 only): llamatransformer.go:641-660 */
+void orc_rms_scale(const uint16_t* x, float* r, int S, int D, float eps);
 void orc_rmsnorm_stage1(const uint16_t* x, uint16_t* out, int S, int D, float eps);
 /* RMSNorm.Forward: llamatransformer.go:633-639 */
 void orc_rmsnorm(const uint16_t* x, const uint16_t* w, uint16_t* out, int S, int D, float eps);

@@ -93,6 +93,7 @@ def _declare(L):
     L.orc_silu_bf16.argtypes = [_u16p, _u16p, C.c_int64]
     L.orc_silu_table_bf16.argtypes = [_u16p]
     L.orc_get_rows_bf16.argtypes = [_u16p, _i32p, _u16p, C.c_int, C.c_int]
+    L.orc_rms_scale.argtypes = [_u16p, _f32p, C.c_int, C.c_int, C.c_float]
     L.orc_rmsnorm_stage1.argtypes = [_u16p, _u16p, C.c_int, C.c_int, C.c_float]
     L.orc_rmsnorm.argtypes = [_u16p, _u16p, _u16p, C.c_int, C.c_int, C.c_float]
     L.orc_rope_table.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, _u16p, _f32p]
@@ -229,6 +230,15 @@ def silu_table_bf16():
     out = np.empty(65536, np.uint16)
     lib().orc_silu_table_bf16(_p(out, _u16p))
     return out
+
+
+def rms_scale(x, eps=1e-5):
+    """r[s] of RMSNorm.Forward (llamatransformer.go:641-656) for x[S, D] bf16 bits"""
+    x = np.ascontiguousarray(x, np.uint16)
+    S, D = x.shape
+    r = np.empty(S, np.float32)
+    lib().orc_rms_scale(_p(x, _u16p), _p(r, _f32p), S, D, eps)
+    return r
 
 
 def rmsnorm_stage1(x, eps=1e-5):

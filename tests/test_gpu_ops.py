@@ -105,6 +105,49 @@ def test_rmsnorm_strict_bit_exact(L, S, D):
     assert np.array_equal(out, O.rmsnorm(x, w, 1e-5))
 
 
+def _adversarial_rows(rng, S, D):
+    rows = []
+    for s in range(S):
+        k = s % 7
+        if k == 0: v = rng.standard_normal(D) * 2.0
+        elif k == 1: v = rng.standard_normal(D) * np.exp(rng.uniform(-20, 20, D))
+        elif k == 2: v = np.where(rng.random(D) < 0.9, 0.0, rng.standard_normal(D))
+        elif k == 3: v = rng.integers(1, 256, D).astype(np.float32) * 2.0 ** rng.integers(-8, 8)   # exact rounding ties
+        elif k == 4: v = np.full(D, rng.uniform(0.1, 3.0))
+        elif k == 5: v = rng.standard_normal(D) * np.linspace(1e-6, 1e3, D)
+        else: v = rng.standard_normal(D) * np.linspace(1e3, 1e-6, D)
+        rows.append(bf(np.asarray(v, np.float32)))
+    return np.stack(rows)
+
+
+@pytest.mark.parametrize("D", [4096, 8192, 256, 128, 64])
+def test_rms_scale_scan_and_chain_bit_exact(L, D):
+    """the two binade-scan kernels (csrc/seqsum.cuh) and the one-thread FADD chain all reproduce the reference's
+    sequential fp32 mean of squares bit for bit, on rows built to hit rounding ties / binade jumps / zeros"""
+    rng = np.random.default_rng(D)
+    S = 28
+    x = _adversarial_rows(rng, S, D)
+    x[-1] = 0                                   # all-zero row: 1/sqrt(eps)
+    exp = O.rms_scale(x, 1e-5)
+    c = L._capi
+    for algo in (3, 2, 1, 0):
+        r = np.empty(S, np.float32)
+        c.check(c.lib.lnb_op_rms_scale_f32(c.ptr(x, c.u16p), c.ptr(r, c.f32p), S, D, 1e-5, algo))
+        assert np.array_equal(r.view(np.uint32), exp.view(np.uint32)), (algo, np.nonzero(r != exp))
+
+
+def test_rms_scale_scan_rejects_unfit_rows(L):
+    c = L._capi
+    x = np.zeros((1, 1000), np.uint16)
+    r = np.empty(1, np.float32)
+    with pytest.raises(c.LnbError):
+        c.check(c.lib.lnb_op_rms_scale_f32(c.ptr(x, c.u16p), c.ptr(r, c.f32p), 1, 1000, 1e-5, 2))
+    with pytest.raises(c.LnbError):
+        c.check(c.lib.lnb_op_rms_scale_f32(c.ptr(x, c.u16p), c.ptr(r, c.f32p), 1, 1000, 1e-5, 3))
+    c.check(c.lib.lnb_op_rms_scale_f32(c.ptr(x, c.u16p), c.ptr(r, c.f32p), 1, 1000, 1e-5, 0))   # falls back to the chain
+    assert r[0] == O.rms_scale(x, 1e-5)[0]
+
+
 def test_rmsnorm_fast_matches_documented_order(L):
     rng = np.random.default_rng(5)
     S, D = 2, 4096
