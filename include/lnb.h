@@ -87,6 +87,45 @@ int lnb_tp_shard_window(const lnb_model_args* args, const char* name, int tp_ran
  * its HBM layout and keeps no reference to `host`. */
 int lnb_model_upload_tensor(lnb_model* m, const char* name, const uint16_t* host, const int64_t* shape, int ndim);
 
+/* ---- checkpoint files --------------------------------------------------------
+ * Native reader / writer for PyTorch ".pth" archives (zip + pickle), host-only.
+ * Replaces: torch.NewTorchModelReader / Load / persistentLoad (src/torch/torchmodelreader.go:21-145),
+ * rebuild_tensor_v2 + TorchStorage.Load (src/torch/types.go:23-56), the unpickler (src/pickle/*.go)
+ * and the read-only mmap (src/common/memorymapper_unix.go:21-45). */
+typedef struct lnb_pth lnb_pth;
+enum { LNB_PTH_BF16 = 0, LNB_PTH_F16 = 1, LNB_PTH_F32 = 2, LNB_PTH_F64 = 3, LNB_PTH_I8 = 4, LNB_PTH_U8 = 5,
+       LNB_PTH_I16 = 6, LNB_PTH_I32 = 7, LNB_PTH_I64 = 8, LNB_PTH_BOOL = 9 };
+/* maps the file, indexes the zip, unpickles the single *.pkl (torchmodelreader.go:39-66) */
+int lnb_pth_open(const char* path, lnb_pth** out);
+int lnb_pth_close(lnb_pth* f);
+/* number of tensors in the top-level dict (pickle.PickleDict keys, torchmodelreader.go:57-63) */
+int lnb_pth_tensor_count(const lnb_pth* f);
+/* name / dtype / shape (<= 8 dims) / byte range inside the file of tensor `index` (dict order).
+ * Returns 0, 1 when the tensor is not contiguous, or a negative error.  Any out pointer may be NULL. */
+int lnb_pth_tensor_info(const lnb_pth* f, int index, const char** name, int* dtype, int* ndim, int64_t* shape,
+                        int64_t* file_offset, int64_t* nbytes);
+/* pointer into the read-only mapping (the reference's Tensor.RawData aliasing the mmap, types.go:51-56);
+ * valid until lnb_pth_close */
+const void* lnb_pth_tensor_data(const lnb_pth* f, int index);
+/* model.LoadModelEx's tensor half (src/model/loader.go:22-41) fused with the by-name binding of
+ * NewLlamaTransformer (llamatransformer.go:84-105): every tensor the architecture names goes from the page
+ * cache to HBM (tp_size>1: only this rank's window); other entries are ignored.  lnb_model_finalize still
+ * reports missing tensors. */
+int lnb_model_load_pth(lnb_model* m, const char* path, int* n_uploaded);
+/* loadModelArgsFromFile (src/model/modelargs.go:52-64) with the defaults of NewModelArgs (:29-44) and the
+ * derived HeadDim / N_KVHeads / FFN width (llamatransformer.go:73-82,569-577).  vocab_size stays -1 when
+ * params.json has none (the reference takes it from the tokenizer, loader.go:106-111). */
+int lnb_model_args_from_params_json(const char* path, int max_seq_len, lnb_model_args* out);
+/* writer: one storage per tensor at offset 0, pickle protocol 2 restricted to the opcodes the reference's
+ * unpickler dispatches (src/pickle/pickledispatch.go:52-77) -- readable by torch.load and by the Go loader */
+typedef struct lnb_pth_writer lnb_pth_writer;
+int lnb_pth_writer_create(const char* path, lnb_pth_writer** out);
+int lnb_pth_writer_add(lnb_pth_writer* w, const char* name, int dtype, const void* data, const int64_t* shape, int ndim);
+/* writes data.pkl + the zip directory and frees the writer (also on failure) */
+int lnb_pth_writer_finish(lnb_pth_writer* w);
+/* the synthetic checkpoint of lnb_model_init_synthetic as a consolidated.00.pth (same bits, host-only) */
+int lnb_pth_write_synthetic(const char* path, const lnb_model_args* args, uint64_t seed);
+
 /* Random-init every tensor directly in HBM with the synthetic generator of DESIGN.md
  * (no checkpoint exists in the build environment).  Same bits as oracle's
  * orc_synth_fill for the same seed. */

@@ -63,6 +63,18 @@ SIGNATURES = {
     "lnb_session_launch_count": (C.c_int64, [vp]),
     "lnb_session_sync": (C.c_int, [vp]),
     "lnb_session_bench_kernel": (C.c_int, [vp, C.c_int, C.c_int, f32p, i64p, i32p]),
+    "lnb_pth_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "lnb_pth_close": (C.c_int, [C.c_void_p]),
+    "lnb_pth_tensor_count": (C.c_int, [C.c_void_p]),
+    "lnb_pth_tensor_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lnb_pth_tensor_data": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "lnb_model_load_pth": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]),
+    "lnb_model_args_from_params_json": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(ModelArgsC)]),
+    "lnb_pth_writer_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "lnb_pth_writer_add": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "lnb_pth_writer_finish": (C.c_int, [C.c_void_p]),
+    "lnb_pth_write_synthetic": (C.c_int, [C.c_char_p, C.POINTER(ModelArgsC), C.c_uint64]),
     "lnb_op_linear_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_matmul_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_rmsnorm_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_float, C.c_int]),

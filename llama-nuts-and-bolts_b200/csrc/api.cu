@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cerrno>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -16,6 +17,7 @@
 #include "gemv.cuh"
 #include "kernels.cuh"
 #include "seqsum.cuh"
+#include "pth.hpp"
 
 namespace lnb {
 void build_rope_table(int dim, int end, double theta, bool use_scaled, std::vector<float>& out);
@@ -343,6 +345,140 @@ extern "C" int lnb_model_upload_tensor(lnb_model* m, const char* name, const uin
   return 0;
 }
 
+// ---- checkpoint files: .pth reader / writer, params.json --------------------------
+struct lnb_pth {
+  lnb::PthFile f;
+};
+struct lnb_pth_writer {
+  lnb::PthWriter w;
+};
+
+extern "C" int lnb_pth_open(const char* path, lnb_pth** out) {
+  if (!path || !out) return fail(LNB_EINVAL, "NULL argument");
+  lnb_pth* h = new lnb_pth();
+  std::string err;
+  if (!h->f.open(path, err)) {
+    delete h;
+    return fail(LNB_EINVAL, "%s", err.c_str());
+  }
+  *out = h;
+  return 0;
+}
+extern "C" int lnb_pth_close(lnb_pth* f) {
+  delete f;
+  return 0;
+}
+extern "C" int lnb_pth_tensor_count(const lnb_pth* f) {
+  if (!f) return fail(LNB_EINVAL, "NULL argument");
+  return (int)f->f.tensors().size();
+}
+extern "C" int lnb_pth_tensor_info(const lnb_pth* f, int index, const char** name, int* dtype, int* ndim, int64_t* shape,
+                                   int64_t* file_offset, int64_t* nbytes) {
+  if (!f) return fail(LNB_EINVAL, "NULL argument");
+  if (index < 0 || index >= (int)f->f.tensors().size()) return fail(LNB_EINVAL, "tensor index %d out of range", index);
+  const lnb::PthTensor& t = f->f.tensors()[index];
+  if (t.shape.size() > 8) return fail(LNB_EINVAL, "tensor \"%s\" has more than 8 dimensions", t.name.c_str());
+  if (name) *name = t.name.c_str();
+  if (dtype) *dtype = t.dtype;
+  if (ndim) *ndim = (int)t.shape.size();
+  if (shape) for (size_t i = 0; i < t.shape.size(); i++) shape[i] = t.shape[i];
+  if (file_offset) *file_offset = t.file_offset;
+  if (nbytes) *nbytes = t.nbytes;
+  return t.contiguous ? 0 : 1;
+}
+extern "C" const void* lnb_pth_tensor_data(const lnb_pth* f, int index) {
+  if (!f || index < 0 || index >= (int)f->f.tensors().size()) {
+    fail(LNB_EINVAL, "tensor index %d out of range", index);
+    return nullptr;
+  }
+  return f->f.data(f->f.tensors()[index]);
+}
+
+// torch.NewTorchModelReader + Load + the name / shape binding of NewLlamaTransformer, in one pass over the
+// mapping: every tensor the architecture names is copied (TP: sliced) from the page cache into HBM.
+extern "C" int lnb_model_load_pth(lnb_model* m, const char* path, int* n_uploaded) {
+  if (!m || !path) return fail(LNB_EINVAL, "NULL argument");
+  if (m->finalized) return fail(LNB_ESTATE, "model is finalized");
+  lnb::PthFile f;
+  std::string err;
+  if (!f.open(path, err)) return fail(LNB_EINVAL, "%s", err.c_str());
+  int n = 0;
+  for (const lnb::PthTensor& t : f.tensors()) {
+    int kind, layer;
+    if (parse_name(m, t.name.c_str(), &kind, &layer)) continue;   // e.g. "rope.freqs": the reference never asks for it either
+    if (t.dtype != lnb::PTH_BF16)
+      return fail(LNB_EINVAL, "tensor \"%s\" is %s; the reference reads torch.BFloat16Storage only (src/torch/types.go:9-21)", t.name.c_str(),
+                  lnb::pth_dtype_name(t.dtype));
+    if (!t.contiguous) return fail(LNB_EINVAL, "tensor \"%s\" is not contiguous", t.name.c_str());
+    if (t.shape.size() > 2) return fail(LNB_EINVAL, "tensor \"%s\": unexpected rank %zu", t.name.c_str(), t.shape.size());
+    int rc = lnb_model_upload_tensor(m, t.name.c_str(), (const uint16_t*)f.data(t), t.shape.data(), (int)t.shape.size());
+    if (rc) return rc;
+    n++;
+  }
+  if (n_uploaded) *n_uploaded = n;
+  return 0;
+}
+
+// loadModelArgsFromFile (src/model/modelargs.go:52-64) + the derived fields (llamatransformer.go:73-82,569-577)
+extern "C" int lnb_model_args_from_params_json(const char* path, int max_seq_len, lnb_model_args* out) {
+  if (!path || !out) return fail(LNB_EINVAL, "NULL argument");
+  FILE* fp = fopen(path, "rb");
+  if (!fp) return fail(LNB_EINVAL, "open %s: %s", path, strerror(errno));
+  std::string text;
+  char buf[4096];
+  size_t k;
+  while ((k = fread(buf, 1, sizeof(buf), fp)) > 0) text.append(buf, k);
+  fclose(fp);
+  lnb::ParamsJson pj;
+  std::string err;
+  if (!lnb::parse_params_json(text, pj, err)) return fail(LNB_EINVAL, "%s", err.c_str());
+  if (pj.dim <= 0 || pj.n_heads <= 0 || pj.multiple_of <= 0) return fail(LNB_EINVAL, "params.json: non-positive dimension");
+  lnb_model_args a{};
+  a.dim = pj.dim;
+  a.n_layers = pj.n_layers;
+  a.n_heads = pj.n_heads;
+  a.n_kv_heads = pj.n_kv_heads < 0 ? pj.n_heads : pj.n_kv_heads;
+  a.head_dim = pj.dim / pj.n_heads;
+  int hidden = 4 * pj.dim;
+  hidden = (int)(2 * hidden / 3);
+  if (pj.ffn_dim_multiplier > -1) hidden = (int)(pj.ffn_dim_multiplier * (double)hidden);
+  a.ffn_dim = pj.multiple_of * ((hidden + pj.multiple_of - 1) / pj.multiple_of);
+  a.vocab_size = pj.vocab_size;          // -1 when absent: the reference takes it from the tokenizer (loader.go:108-110)
+  a.max_seq_len = max_seq_len > 0 ? max_seq_len : 2048;
+  a.norm_eps = pj.norm_eps;
+  a.rope_theta = pj.rope_theta > 0 ? pj.rope_theta : 500000.0;
+  a.use_scaled_rope = pj.use_scaled_rope ? 1 : 0;
+  *out = a;
+  return 0;
+}
+
+extern "C" int lnb_pth_writer_create(const char* path, lnb_pth_writer** out) {
+  if (!path || !out) return fail(LNB_EINVAL, "NULL argument");
+  lnb_pth_writer* w = new lnb_pth_writer();
+  std::string err;
+  if (!w->w.open(path, err)) {
+    delete w;
+    return fail(LNB_EINVAL, "%s", err.c_str());
+  }
+  *out = w;
+  return 0;
+}
+extern "C" int lnb_pth_writer_add(lnb_pth_writer* w, const char* name, int dtype, const void* data, const int64_t* shape, int ndim) {
+  if (!w || !name || (!data && ndim > 0) || (!shape && ndim > 0)) return fail(LNB_EINVAL, "NULL argument");
+  if (ndim < 0 || ndim > 8) return fail(LNB_EINVAL, "bad rank %d", ndim);
+  std::string err;
+  std::vector<int64_t> sh(shape, shape + ndim);
+  if (!w->w.add(name, dtype, data, sh, err)) return fail(LNB_EINVAL, "%s", err.c_str());
+  return 0;
+}
+extern "C" int lnb_pth_writer_finish(lnb_pth_writer* w) {
+  if (!w) return fail(LNB_EINVAL, "NULL argument");
+  std::string err;
+  const bool ok = w->w.finish(err);
+  delete w;
+  return ok ? 0 : fail(LNB_EINVAL, "%s", err.c_str());
+}
+
 // ---- synthetic checkpoint ------------------------------------------------------------------
 static uint64_t fnv1a64(const char* s) {
   uint64_t h = 0xcbf29ce484222325ULL;
@@ -421,6 +557,53 @@ extern "C" int lnb_model_init_synthetic(lnb_model* m, uint64_t seed) {
       if ((rc = fill(name, k, l))) return rc;
     }
   CU(cudaDeviceSynchronize());
+  return 0;
+}
+
+// The synthetic checkpoint as a file the UNMODIFIED reference loader can read (SURVEY 8d "Synthetic weights":
+// "same bytes feed oracle, GPU path and (if ever available) the Go binary via a .pth writer").  Tensor order
+// follows Meta's consolidated.00.pth (tok_embeddings, layers.*, norm, output); host-only, no CUDA call.
+extern "C" int lnb_pth_write_synthetic(const char* path, const lnb_model_args* args, uint64_t seed) {
+  if (!path || !args) return fail(LNB_EINVAL, "NULL argument");
+  const lnb_model_args& a = *args;
+  if (a.dim <= 0 || a.n_layers <= 0 || a.n_heads <= 0 || a.n_kv_heads <= 0 || a.head_dim <= 0 || a.ffn_dim <= 0 || a.vocab_size <= 0)
+    return fail(LNB_EINVAL, "non-positive model dimension");
+  lnb_model tmp;
+  tmp.a = a;
+  tmp.q_dim = a.n_heads * a.head_dim;
+  tmp.kv_dim = a.n_kv_heads * a.head_dim;
+  lnb::PthWriter w;
+  std::string err;
+  if (!w.open(path, err)) return fail(LNB_EINVAL, "%s", err.c_str());
+  std::vector<uint16_t> buf;
+  auto emit = [&](const char* name, int kind) -> int {
+    int64_t rows, cols;
+    full_shape(&tmp, kind, &rows, &cols);
+    float scale, offset;
+    synth_spec_kind(a, kind, &scale, &offset);
+    buf.resize((size_t)(rows * cols));
+    int rc = lnb_synth_fill_host(seed, name, scale, offset, rows * cols, buf.data());
+    if (rc) return rc;
+    std::vector<int64_t> shape;
+    shape.push_back(rows);
+    if (cols != 1) shape.push_back(cols);
+    if (!w.add(name, lnb::PTH_BF16, buf.data(), shape, err)) return fail(LNB_EINVAL, "%s", err.c_str());
+    return 0;
+  };
+  static const char* lnames[9] = {"attention_norm.weight", "attention.wq.weight", "attention.wk.weight",
+                                  "attention.wv.weight",   "attention.wo.weight", "ffn_norm.weight",
+                                  "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight"};
+  int rc;
+  if ((rc = emit("tok_embeddings.weight", T_EMBD))) return rc;
+  char name[128];
+  for (int l = 0; l < a.n_layers; l++)
+    for (int k = 0; k < 9; k++) {
+      snprintf(name, sizeof(name), "layers.%d.%s", l, lnames[k]);
+      if ((rc = emit(name, k))) return rc;
+    }
+  if ((rc = emit("norm.weight", T_NORM))) return rc;
+  if ((rc = emit("output.weight", T_OUTPUT))) return rc;
+  if (!w.finish(err)) return fail(LNB_EINVAL, "%s", err.c_str());
   return 0;
 }
 

@@ -81,6 +81,13 @@ class LlamaTransformer:
     def init_synthetic(self, seed: int = synth.SEED):
         check(lib.lnb_model_init_synthetic(self.h, seed))
 
+    def load_pth(self, path: str) -> int:
+        """every tensor the architecture names, from the checkpoint mapping straight to HBM (lnb_model_load_pth);
+        returns how many were uploaded"""
+        n = C.c_int(0)
+        check(lib.lnb_model_load_pth(self.h, path.encode(), C.byref(n)))
+        return n.value
+
     def finalize(self):
         check(lib.lnb_model_finalize(self.h))
         self.finalized = True
@@ -257,4 +264,36 @@ def LoadModelFromTensors(args_dict: dict, tensors: dict[str, np.ndarray], device
     for name, arr in tensors.items():
         m.Transformer.upload_tensor(name, arr)
     m.Transformer.finalize()
+    return m
+
+
+def load_model_args(modelDir: str, max_seq_len: int = 2048) -> dict:
+    """loadModelArgs (src/model/loader.go:72-82): params.json -> model args incl. the derived widths"""
+    import os
+    c = _capi.ModelArgsC()
+    check(lib.lnb_model_args_from_params_json(os.path.join(modelDir, "params.json").encode(), max_seq_len, C.byref(c)))
+    return {f: getattr(c, f) for f, _ in _capi.ModelArgsC._fields_}
+
+
+def LoadModel(modelDir: str, device: int = 0, tp_rank: int = 0, tp_size: int = 1, nccl_id=None, max_seq_len: int = 2048) -> Model:
+    """model.LoadModel (src/model/loader.go:18-70): <modelDir>/consolidated.00.pth + params.json.
+    The tokenizer is out of scope, so VocabSize (which the reference takes from tokenizer.model when
+    params.json has none, loader.go:103-111) falls back to the rows of tok_embeddings.weight."""
+    import os
+    from .torch_reader import TorchModelReader
+    path = os.path.join(modelDir, "consolidated.00.pth")
+    d = load_model_args(modelDir, max_seq_len)
+    if d["vocab_size"] < 1:
+        with TorchModelReader(path) as r:
+            t = r.Load().get("tok_embeddings.weight")
+        if t is None:
+            raise _capi.LnbError(-1, 'tensor "tok_embeddings.weight" not found')
+        d["vocab_size"] = t.Size[0]
+    m = Model(ModelArgs.from_c_dict(d), device, tp_rank, tp_size, nccl_id)
+    try:
+        m.Transformer.load_pth(path)
+        m.Transformer.finalize()
+    except Exception:
+        m.Free()
+        raise
     return m

@@ -299,3 +299,52 @@ def test_batched_decode_equals_independent_contexts(L, tiny, mode):
         ctx.close()
         for o in osess:
             o.close()
+
+
+def test_load_model_from_checkpoint_directory(L, tiny, tmp_path):
+    """model.LoadModel(modelDir) -- params.json + consolidated.00.pth go from the file mapping straight
+    to HBM (lnb_model_load_pth) and the model is bit-identical to the one built from host tensors / the oracle"""
+    import json
+    from lnb_b200.torch_reader import TorchModelWriter, write_synthetic_checkpoint
+    args, tensors, om, gm = tiny
+    write_synthetic_checkpoint(str(tmp_path / "consolidated.00.pth"), L.synth.args_c(args), SEED)
+    # a params.json that derives TINY's widths the reference's way: head_dim = dim / n_heads,
+    # ffn = multiple_of * ceil(int(mult * int(2 * 4 dim / 3)) / multiple_of) = 256 * ceil(511 / 256) = 512
+    (tmp_path / "params.json").write_text(json.dumps({
+        "dim": args["dim"], "n_layers": args["n_layers"], "n_heads": args["n_heads"], "n_kv_heads": args["n_kv_heads"],
+        "ffn_dim_multiplier": 0.75, "multiple_of": 256, "norm_eps": 1e-05, "rope_theta": 500000.0, "use_scaled_rope": True}))
+    d = L.model.load_model_args(str(tmp_path), max_seq_len=args["max_seq_len"])
+    assert d["ffn_dim"] == args["ffn_dim"] and d["head_dim"] == args["head_dim"] and d["vocab_size"] == -1
+    m = L.model.LoadModel(str(tmp_path), max_seq_len=args["max_seq_len"])     # vocab from tok_embeddings rows
+    try:
+        assert m.ModelArgs.VocabSize == args["vocab_size"]
+        toks = np.array([3, 77, 1000, 5, 9], np.int32)
+        ctx = L.model.InferenceContext(m.Transformer, L.model.InferenceArgs(16), acc_mode=L._capi.LNB_ACC_STRICT)
+        so = om.new_session(16)
+        got = m.Transformer.Forward(ctx, L.ml.Tensor(toks, L.ml.DT_INT32), 0).RawData
+        assert np.array_equal(got, so.forward(toks, 0))
+        nxt, lg = m.Transformer.forward_argmax(ctx, np.array([int(np.argmax(got[-1]))], np.int32), 5, want_logits="last")
+        assert np.array_equal(lg, so.forward(np.array([int(np.argmax(got[-1]))], np.int32), 5))
+        ctx.close(); so.close()
+    finally:
+        m.Free()
+    # a checkpoint with a missing tensor / a wrong shape / a non-bf16 tensor is refused the reference's way
+    def variant(mutate):
+        w = TorchModelWriter(str(tmp_path / "consolidated.00.pth"))
+        for name, arr in tensors.items():
+            r = mutate(name, arr)
+            if r is not None:
+                w.Add(name, *r)
+        w.Finish()
+    variant(lambda n, a: None if n == "layers.1.ffn_norm.weight" else (a,))
+    with pytest.raises(L._capi.LnbError) as e:
+        L.model.LoadModel(str(tmp_path), max_seq_len=args["max_seq_len"])
+    assert "missing" in str(e.value)
+    variant(lambda n, a: (a[:-1],) if n == "norm.weight" else (a,))
+    with pytest.raises(L._capi.LnbError) as e:
+        L.model.LoadModel(str(tmp_path), max_seq_len=args["max_seq_len"])
+    assert "norm.weight" in str(e.value) and "shape" in str(e.value)
+    variant(lambda n, a: (a.astype(np.float32),) if n == "norm.weight" else (a,))
+    with pytest.raises(L._capi.LnbError) as e:
+        L.model.LoadModel(str(tmp_path), max_seq_len=args["max_seq_len"])
+    assert "float32" in str(e.value)
