@@ -1,7 +1,9 @@
 // lnb_generate -- the cmd/main.go of this repository for the synthetic checkpoint: loads (random-inits)
 // Llama-3.1-8B on device 0 through the C++ host mirror, runs the reference generate loop on the fixed
 // 8-token prompt and prints the generated token ids and the decode rate.
-// Build: make -C host      Run: host/lnb_generate [seq_len=136] [strict|fast] [tiny]
+// Build: make -C host      Run: host/lnb_generate [seq_len=136] [strict|fast] [tiny | <modelDir>]
+// <modelDir> holds params.json + consolidated.00.pth (model.LoadModel, src/model/loader.go:18-70);
+// `lnb_generate --write-synthetic <modelDir> [tiny]` writes such a directory for the synthetic weights (host-only).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -11,7 +13,36 @@
 
 using namespace lnb_host;
 
+static int write_synthetic_dir(const char* dir, bool tiny) {
+  model::ModelArgs args = model::ModelArgs::Llama31_8B();
+  const char* params = "{\"dim\": 4096, \"n_layers\": 32, \"n_heads\": 32, \"n_kv_heads\": 8, \"vocab_size\": 128256, "
+                       "\"ffn_dim_multiplier\": 1.3, \"multiple_of\": 1024, \"norm_eps\": 1e-05, \"rope_theta\": 500000.0, "
+                       "\"use_scaled_rope\": true}\n";
+  if (tiny) {
+    args.dim = 256; args.n_layers = 2; args.n_heads = 8; args.n_kv_heads = 2; args.head_dim = 32; args.ffn_dim = 512;
+    args.vocab_size = 1024; args.max_seq_len = 64;
+    params = "{\"dim\": 256, \"n_layers\": 2, \"n_heads\": 8, \"n_kv_heads\": 2, \"vocab_size\": 1024, \"ffn_dim_multiplier\": 0.75, "
+             "\"multiple_of\": 256, \"norm_eps\": 1e-05, \"rope_theta\": 500000.0, \"use_scaled_rope\": true}\n";
+  }
+  const std::string d(dir);
+  FILE* f = fopen((d + "/params.json").c_str(), "w");
+  if (!f) { fprintf(stderr, "error: cannot write %s/params.json\n", dir); return 1; }
+  fputs(params, f);
+  fclose(f);
+  check(lnb_pth_write_synthetic((d + "/consolidated.00.pth").c_str(), &args, tiny ? 7 : 0x4C4E42));
+  printf("wrote %s/params.json and %s/consolidated.00.pth\n", dir, dir);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 2 && !strcmp(argv[1], "--write-synthetic")) {
+    try {
+      return write_synthetic_dir(argv[2], argc > 3 && !strcmp(argv[3], "tiny"));
+    } catch (const std::exception& e) {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+  }
   const int seq_len = argc > 1 ? atoi(argv[1]) : 136;
   const int acc = (argc > 2 && !strcmp(argv[2], "fast")) ? LNB_ACC_FAST : LNB_ACC_STRICT;
   const bool tiny = argc > 3 && !strcmp(argv[3], "tiny");
@@ -23,11 +54,19 @@ int main(int argc, char** argv) {
       args.vocab_size = 1024; args.max_seq_len = 64;
       prompt = {1, 50, 999, 7, 300, 12, 64, 2};
     }
-    model::LlamaTransformer transformer(args, 0);
-    transformer.InitSynthetic(tiny ? 7 : 0x4C4E42);
-    transformer.Finalize();
+    const bool from_dir = argc > 3 && !tiny;
+    std::unique_ptr<model::LlamaTransformer> loaded;
+    if (from_dir) {
+      loaded = model::LoadModel(argv[3], 0, 2048);
+      if (loaded->args.vocab_size < 128256) prompt = {1, 50, 999, 7, 300, 12, 64, 2};
+    } else {
+      loaded = std::make_unique<model::LlamaTransformer>(args, 0);
+      loaded->InitSynthetic(tiny ? 7 : 0x4C4E42);
+      loaded->Finalize();
+    }
+    model::LlamaTransformer& transformer = *loaded;
     model::Vocabulary vocab;
-    if (tiny) vocab.StopTokenIds = {1000000000};
+    if (tiny || transformer.args.vocab_size < 128256) vocab.StopTokenIds = {1000000000};
     std::vector<int32_t> out;
     auto t0 = std::chrono::steady_clock::now();
     std::chrono::steady_clock::time_point t_first;

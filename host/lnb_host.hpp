@@ -10,6 +10,7 @@
 #include <cstring>
 #include <functional>
 #include <stdexcept>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -107,12 +108,77 @@ class LlamaTransformer {  // llamatransformer.go:16-113
     check(lnb_model_upload_tensor(h_, name.c_str(), data, shape.data(), (int)shape.size()));
   }
   void InitSynthetic(uint64_t seed) { check(lnb_model_init_synthetic(h_, seed)); }
+  // torch.TorchModelReader.Load + the by-name binding of NewLlamaTransformer: checkpoint mapping -> HBM
+  int LoadPth(const std::string& path) {
+    int n = 0;
+    check(lnb_model_load_pth(h_, path.c_str(), &n));
+    return n;
+  }
   void Finalize() { check(lnb_model_finalize(h_)); }
   lnb_model* handle() { return h_; }
 
  private:
   lnb_model* h_ = nullptr;
 };
+
+// src/torch: TorchModelReader over the native reader of liblnb.so (RawData aliases the read-only file mapping)
+class TorchModelReader {  // torchmodelreader.go:13-66
+ public:
+  struct Entry {
+    std::string Name;
+    int DType = 0;                 // LNB_PTH_*
+    std::vector<int64_t> Size;
+    const void* RawData = nullptr;
+    int64_t ByteCount = 0;
+    bool Contiguous = true;
+  };
+  explicit TorchModelReader(const std::string& modelFilePath) { check(lnb_pth_open(modelFilePath.c_str(), &h_)); }
+  ~TorchModelReader() { lnb_pth_close(h_); }
+  TorchModelReader(const TorchModelReader&) = delete;
+  std::vector<Entry> Load() const {
+    std::vector<Entry> out;
+    const int n = lnb_pth_tensor_count(h_);
+    for (int i = 0; i < n; i++) {
+      Entry e;
+      const char* name = nullptr;
+      int nd = 0;
+      int64_t shape[8], off = 0;
+      const int rc = lnb_pth_tensor_info(h_, i, &name, &e.DType, &nd, shape, &off, &e.ByteCount);
+      check(rc < 0 ? rc : 0);
+      e.Contiguous = (rc == 0);
+      e.Name = name;
+      e.Size.assign(shape, shape + nd);
+      e.RawData = lnb_pth_tensor_data(h_, i);
+      out.push_back(std::move(e));
+    }
+    return out;
+  }
+
+ private:
+  lnb_pth* h_ = nullptr;
+};
+
+// loadModelArgsFromFile (modelargs.go:52-64) + derived widths; vocab_size < 1 -> rows of tok_embeddings.weight
+// (the reference takes it from tokenizer.model, loader.go:103-111; the tokenizer is out of scope here)
+inline ModelArgs LoadModelArgs(const std::string& modelDir, int maxSeqLen = 2048) {
+  ModelArgs a{};
+  check(lnb_model_args_from_params_json((modelDir + "/params.json").c_str(), maxSeqLen, &a));
+  if (a.vocab_size < 1) {
+    TorchModelReader r(modelDir + "/consolidated.00.pth");
+    for (const auto& e : r.Load())
+      if (e.Name == "tok_embeddings.weight" && !e.Size.empty()) a.vocab_size = (int32_t)e.Size[0];
+    if (a.vocab_size < 1) throw Error("tensor \"tok_embeddings.weight\" not found");
+  }
+  return a;
+}
+
+// model.LoadModel (loader.go:18-70): <modelDir>/params.json + consolidated.00.pth -> a finalized transformer
+inline std::unique_ptr<LlamaTransformer> LoadModel(const std::string& modelDir, int device = 0, int maxSeqLen = 2048) {
+  auto t = std::make_unique<LlamaTransformer>(LoadModelArgs(modelDir, maxSeqLen), device);
+  t->LoadPth(modelDir + "/consolidated.00.pth");
+  t->Finalize();
+  return t;
+}
 
 class InferenceContext {  // inferencecontext.go:8-46 (KV cache in HBM)
  public:

@@ -90,7 +90,7 @@ int lnb_model_upload_tensor(lnb_model* m, const char* name, const uint16_t* host
 /* ---- checkpoint files --------------------------------------------------------
  * Native reader / writer for PyTorch ".pth" archives (zip + pickle), host-only.
  * Replaces: torch.NewTorchModelReader / Load / persistentLoad (src/torch/torchmodelreader.go:21-145),
- * rebuild_tensor_v2 + TorchStorage.Load (src/torch/types.go:23-56), the unpickler (src/pickle/*.go)
+ * rebuild_tensor_v2 + TorchStorage.Load (src/torch/types.go:23-56), the unpickler (src/pickle/picklereader.go, pickledispatch.go)
  * and the read-only mmap (src/common/memorymapper_unix.go:21-45). */
 typedef struct lnb_pth lnb_pth;
 enum { LNB_PTH_BF16 = 0, LNB_PTH_F16 = 1, LNB_PTH_F32 = 2, LNB_PTH_F64 = 3, LNB_PTH_I8 = 4, LNB_PTH_U8 = 5,

@@ -251,6 +251,15 @@ def test_cpp_host_mirror_generates_the_oracle_tokens(L):
     exp = list(om.generate([1, 50, 999, 7, 300, 12, 64, 2], 24, stop_ids=(10**9,)))
     om.close()
     assert got == exp
+    # the same through model.LoadModel: `--write-synthetic` writes params.json + consolidated.00.pth (host-only),
+    # the second run maps that file and uploads it
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.check_call([exe, "--write-synthetic", d, "tiny"])
+        out = subprocess.run([exe, "24", "strict", d], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        line = [l for l in out.stdout.splitlines() if l.startswith("tokens:")][0]
+        assert [int(t) for t in line.split()[1:]] == exp
 
 
 @pytest.mark.parametrize("mode", ["strict", "fast"])

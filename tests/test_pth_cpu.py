@@ -251,3 +251,20 @@ def test_sanitized_mutation_fuzz_of_the_native_reader(tmp_path):
     out = subprocess.run([exe, good, str(tmp_path / "scratch.pth"), "8000", "5"], capture_output=True, text=True)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert "parsed" in out.stdout and "rejected" in out.stdout
+
+
+def test_cpp_host_cli_writes_a_model_directory_without_a_gpu(tmp_path):
+    """host/lnb_generate --write-synthetic: params.json + consolidated.00.pth through the C++ host mirror (host-only);
+    the files satisfy PyTorch and derive TINY's widths the reference's way"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "host"), "-s"])
+    subprocess.check_call([os.path.join(root, "host", "lnb_generate"), "--write-synthetic", str(tmp_path), "tiny"])
+    d = L.model.load_model_args(str(tmp_path), max_seq_len=64)
+    tiny = dict(L.synth.TINY)
+    assert {k: d[k] for k in ("dim", "n_layers", "n_heads", "n_kv_heads", "head_dim", "ffn_dim", "vocab_size")} == \
+        {k: tiny[k] for k in ("dim", "n_layers", "n_heads", "n_kv_heads", "head_dim", "ffn_dim", "vocab_size")}
+    sd = torch.load(str(tmp_path / "consolidated.00.pth"), weights_only=True)
+    expect = host_tensors(tiny, 7)
+    assert set(sd) == set(expect)
+    for k in ("tok_embeddings.weight", "layers.1.feed_forward.w2.weight", "norm.weight"):
+        assert np.array_equal(bits(sd[k]), expect[k])
