@@ -1,7 +1,8 @@
 // lnb_generate -- the cmd/main.go of this repository for the synthetic checkpoint: loads (random-inits)
 // Llama-3.1-8B on device 0 through the C++ host mirror, runs the reference generate loop on the fixed
 // 8-token prompt and prints the generated token ids and the decode rate.
-// Build: make -C host      Run: host/lnb_generate [seq_len=136] [strict|fast] [tiny | <modelDir>]
+// Build: make -C host      Run: host/lnb_generate [seq_len=136] [strict|fast] [tiny | <modelDir>] [batch=N]
+// batch=N: N prompts (prompt b = ids[1:] + 977 b) generated together, one pass over the weights per step.
 // <modelDir> holds params.json + consolidated.00.pth (model.LoadModel, src/model/loader.go:18-70);
 // `lnb_generate --write-synthetic <modelDir> [tiny]` writes such a directory for the synthetic weights (host-only).
 #include <chrono>
@@ -46,6 +47,7 @@ int main(int argc, char** argv) {
   const int seq_len = argc > 1 ? atoi(argv[1]) : 136;
   const int acc = (argc > 2 && !strcmp(argv[2], "fast")) ? LNB_ACC_FAST : LNB_ACC_STRICT;
   const bool tiny = argc > 3 && !strcmp(argv[3], "tiny");
+  const bool has_dir = argc > 3 && !tiny && strncmp(argv[3], "batch=", 6) != 0;
   try {
     model::ModelArgs args = model::ModelArgs::Llama31_8B();
     std::vector<int32_t> prompt{128000, 9906, 11, 856, 836, 374, 220, 16};
@@ -54,7 +56,7 @@ int main(int argc, char** argv) {
       args.vocab_size = 1024; args.max_seq_len = 64;
       prompt = {1, 50, 999, 7, 300, 12, 64, 2};
     }
-    const bool from_dir = argc > 3 && !tiny;
+    const bool from_dir = has_dir;
     std::unique_ptr<model::LlamaTransformer> loaded;
     if (from_dir) {
       loaded = model::LoadModel(argv[3], 0, 2048);
@@ -67,6 +69,29 @@ int main(int argc, char** argv) {
     model::LlamaTransformer& transformer = *loaded;
     model::Vocabulary vocab;
     if (tiny || transformer.args.vocab_size < 128256) vocab.StopTokenIds = {1000000000};
+    int batch = 0;
+    for (int i = 1; i < argc; i++)
+      if (!strncmp(argv[i], "batch=", 6)) batch = atoi(argv[i] + 6);
+    if (batch > 0) {
+      const int mod = transformer.args.vocab_size < 128256 ? 1000 : 128000;
+      std::vector<std::vector<int32_t>> prompts(batch, prompt);
+      for (int b = 0; b < batch; b++)
+        for (size_t j = 1; j < prompt.size(); j++) prompts[b][j] = (prompt[j] + 977 * b) % mod;
+      std::vector<std::vector<int32_t>> outs(batch);
+      auto b0 = std::chrono::steady_clock::now();
+      inference::GenerateTokensBatch(transformer, vocab, seq_len, acc, prompts,
+                                     [&](int seq, inference::GenerationState, int32_t tok) { outs[seq].push_back(tok); });
+      const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - b0).count();
+      size_t total = 0;
+      for (int b = 0; b < batch; b++) {
+        printf("tokens[%d]:", b);
+        for (int32_t t : outs[b]) printf(" %d", t);
+        printf("\n");
+        total += outs[b].size();
+      }
+      printf("generated %zu tokens for %d prompts in %.1f ms = %.1f tokens/s aggregate (prefill included)\n", total, batch, sec * 1e3, total / sec);
+      return 0;
+    }
     std::vector<int32_t> out;
     auto t0 = std::chrono::steady_clock::now();
     std::chrono::steady_clock::time_point t_first;

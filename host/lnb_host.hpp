@@ -10,6 +10,7 @@
 #include <cstring>
 #include <functional>
 #include <stdexcept>
+#include <algorithm>
 #include <memory>
 #include <string>
 #include <vector>
@@ -187,7 +188,25 @@ class InferenceContext {  // inferencecontext.go:8-46 (KV cache in HBM)
       : SequenceLength(sequenceLength > 0 ? sequenceLength : t.args.max_seq_len), vocab_(t.args.vocab_size) {
     check(lnb_session_create(t.handle(), SequenceLength, maxRows, accMode, &h_));
   }
+  // n reference InferenceContexts that share the weights (batched decode): own KV cache and position each
+  InferenceContext(LlamaTransformer& t, int sequenceLength, int accMode, int maxRows, int nSeq)
+      : SequenceLength(sequenceLength > 0 ? sequenceLength : t.args.max_seq_len), vocab_(t.args.vocab_size) {
+    check(lnb_session_create_batch(t.handle(), SequenceLength, nSeq, maxRows, accMode, &h_));
+  }
   ~InferenceContext() { lnb_session_destroy(h_); }
+  void SetActiveSequence(int seq) { check(lnb_session_set_active_sequence(h_, seq)); }
+  // Forward + last-row ml.Argmax in one call (inference.go:202-216), 4-byte read-back
+  int32_t ForwardArgmax(const std::vector<int32_t>& tokens, int startPos) {
+    int32_t next = -1;
+    check(lnb_forward(h_, tokens.data(), (int)tokens.size(), startPos, nullptr, 0, &next));
+    return next;
+  }
+  // one decode step of every sequence: tokens[i] at positions[i] -> greedy next token of sequence i
+  std::vector<int32_t> ForwardBatch(const std::vector<int32_t>& tokens, const std::vector<int32_t>& positions) {
+    std::vector<int32_t> next(tokens.size(), -1);
+    check(lnb_forward_batch(h_, tokens.data(), positions.data(), (int)tokens.size(), nullptr, next.data()));
+    return next;
+  }
   InferenceContext(const InferenceContext&) = delete;
   // LlamaTransformer.Forward (llamatransformer.go:145-180): tokens [S] -> f32 logits [S, vocab]
   ml::Tensor Forward(const ml::Tensor& inputTokens, int startPos) {
@@ -236,6 +255,43 @@ inline void GenerateTokens(model::LlamaTransformer& transformer, const model::Vo
     if (eos) { emit(GSFinishedByReachingEOS, nextTokenId); break; }                 // :233-240
     if (curPos + 1 == infContext.SequenceLength) { emit(GSFinishedByReachingSeqLen, nextTokenId); break; }
     emit(GSInProgress, nextTokenId);
+  }
+}
+
+// The consumer InferenceEngine.TokenizeBatch (src/inference/tokenize.go:97-107) never got in the reference
+// (SURVEY 8f-4): every prompt runs the loop above -- own KV cache, positions and stop condition -- but all
+// sequences advance together, one pass over the weights per step.  emit(sequence, state, token).
+inline void GenerateTokensBatch(model::LlamaTransformer& transformer, const model::Vocabulary& vocab, int sequenceLength, int accMode,
+                                const std::vector<std::vector<int32_t>>& prompts,
+                                const std::function<void(int, GenerationState, int32_t)>& emit) {
+  const int n = (int)prompts.size();
+  if (n < 1) throw Error("empty prompt batch");
+  model::InferenceContext infContext(transformer, sequenceLength, accMode, std::max(8, n), n);
+  const int seqLen = infContext.SequenceLength;
+  for (const auto& p : prompts)
+    if ((int)p.size() >= seqLen)
+      throw Error("context SequenceLength " + std::to_string(seqLen) + " must be higher than prompt tokens length " + std::to_string(p.size()));
+  std::vector<int32_t> cur(n), pos(n);
+  std::vector<char> done(n, 0);
+  int n_done = 0;
+  auto record = [&](int i, int32_t tok, int curPos) {   // :218-248
+    cur[i] = tok;
+    pos[i] = curPos;
+    bool eos = false;
+    for (int32_t s : vocab.StopTokenIds) eos |= (s == tok);
+    GenerationState st = eos ? GSFinishedByReachingEOS : (curPos + 1 == seqLen ? GSFinishedByReachingSeqLen : GSInProgress);
+    if (st != GSInProgress) { done[i] = 1; n_done++; }
+    emit(i, st, tok);
+  };
+  for (int i = 0; i < n; i++) {                           // prefill on sequence i's cache
+    infContext.SetActiveSequence(i);
+    record(i, infContext.ForwardArgmax(prompts[i], 0), (int)prompts[i].size());
+  }
+  while (n_done < n) {
+    // finished sequences are stepped again at their last position (a no-op for their state)
+    const std::vector<int32_t> next = infContext.ForwardBatch(cur, pos);
+    for (int i = 0; i < n; i++)
+      if (!done[i]) record(i, next[i], pos[i] + 1);
   }
 }
 }  // namespace inference

@@ -75,3 +75,63 @@ class InferenceEngine:
                 yield GSInProgress, nextTokenId
         finally:
             infContext.close()
+
+    def GenerateTokensBatch(self, prompts, step_times: list | None = None):
+        """The consumer `InferenceEngine.TokenizeBatch` (src/inference/tokenize.go:97-107) never got in the
+        reference: every prompt runs the loop of generateTokensInternal (:173-254) -- own
+        InferenceContext / KV cache, own positions, own stop condition -- but all sequences advance together,
+        one pass over the weights per step (lnb_forward_batch).  Yields (sequence index, state, token id);
+        per sequence the stream is exactly what GenerateTokens(prompts[i]) yields."""
+        n = len(prompts)
+        if n < 1:
+            raise ml.MlError("empty prompt batch")
+        if n == 1:
+            for state, tok in self.GenerateTokens(prompts[0]):
+                yield 0, state, tok
+            return
+        infContext = model_mod.InferenceContext(self.model.Transformer, self.inferenceArgs, self.logFn,
+                                                max_rows=max(self.max_rows, n), acc_mode=self.acc_mode, n_seq=n)
+        if self.context_hook is not None:
+            self.context_hook(infContext)
+        try:
+            seqLen = infContext.SequenceLength
+            stop = self.model.Vocabulary.StopTokenIds
+            for p in prompts:
+                if len(p) >= seqLen:  # :176-179
+                    raise ml.MlError(f"context SequenceLength {seqLen} must be higher than prompt tokens length {len(p)}")
+                if len(p) < 1 or len(p) > infContext.max_rows:
+                    raise ml.MlError(f"prompt length {len(p)} must be in [1, {infContext.max_rows}]")
+            cur = [0] * n                                  # token fed next / position it is fed at
+            pos = [0] * n
+            done = [False] * n
+
+            def emit(i, tok, curPos):
+                """bookkeeping of one generated token at curPos (:218-248); returns the state to yield"""
+                cur[i], pos[i] = tok, curPos
+                if tok in stop:
+                    done[i] = True
+                    return GSFinishedByReachingEOS
+                if curPos + 1 == seqLen:
+                    done[i] = True
+                    return GSFinishedByReachingSeqLen
+                return GSInProgress
+
+            t0 = time.perf_counter()
+            for i, p in enumerate(prompts):                # prefill: the ordinary Forward on sequence i's cache
+                infContext.set_active_sequence(i)
+                nxt, _ = self.model.Transformer.forward_argmax(infContext, np.asarray(p, np.int32), 0)
+                yield i, emit(i, int(nxt), len(p)), int(nxt)
+            if step_times is not None:
+                step_times.append(time.perf_counter() - t0)
+            while not all(done):
+                t0 = time.perf_counter()
+                # finished sequences are stepped again at their last position (same token, same cache row: a no-op
+                # for their state); the weights are read once per step regardless
+                nxt, _ = infContext.forward_batch(cur, pos)
+                if step_times is not None:
+                    step_times.append(time.perf_counter() - t0)
+                for i in range(n):
+                    if not done[i]:
+                        yield i, emit(i, int(nxt[i]), pos[i] + 1), int(nxt[i])
+        finally:
+            infContext.close()

@@ -260,6 +260,16 @@ def test_cpp_host_mirror_generates_the_oracle_tokens(L):
         assert out.returncode == 0, out.stderr
         line = [l for l in out.stdout.splitlines() if l.startswith("tokens:")][0]
         assert [int(t) for t in line.split()[1:]] == exp
+    # inference::GenerateTokensBatch: 3 prompts generated together, each gets its single-prompt stream
+    out = subprocess.run([exe, "24", "strict", "tiny", "batch=3"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    base = [1, 50, 999, 7, 300, 12, 64, 2]
+    om = oracle_model(args, host_tensors(args, 7))
+    for b in range(3):
+        prompt = [base[0]] + [(t + 977 * b) % 1000 for t in base[1:]]
+        line = [l for l in out.stdout.splitlines() if l.startswith(f"tokens[{b}]:")][0]
+        assert [int(t) for t in line.split()[1:]] == list(om.generate(prompt, 24, stop_ids=(10**9,))), b
+    om.close()
 
 
 @pytest.mark.parametrize("mode", ["strict", "fast"])
@@ -357,3 +367,38 @@ def test_load_model_from_checkpoint_directory(L, tiny, tmp_path):
     with pytest.raises(L._capi.LnbError) as e:
         L.model.LoadModel(str(tmp_path), max_seq_len=args["max_seq_len"])
     assert "float32" in str(e.value)
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_generate_tokens_batch_equals_per_prompt_generation(L, tiny, mode):
+    """the batched generate loop -- every prompt gets exactly the stream the single-prompt loop of
+    generateTokensInternal gives it (oracle: orc_generate), with different prompt lengths and one sequence that
+    stops early on an EOS id while the others run to SequenceLength"""
+    args, _, om, gm = tiny
+    prompts = [[1, 50, 999, 7, 300, 12, 64, 2], [5, 6, 7], [1000], [3, 3, 3, 3, 3]]
+    seq = 24
+    free = [list(om.generate(p, seq, stop_ids=(10**9,))) for p in prompts]
+    stop = int(free[1][4])                                   # sequence 1 will hit it at its 5th token at the latest
+    exp = [list(om.generate(p, seq, stop_ids=(stop,))) for p in prompts]
+    assert len(exp[1]) <= 5 and any(len(e) == seq - len(p) for e, p in zip(exp, prompts))
+    saved = gm.Vocabulary.StopTokenIds
+    gm.Vocabulary.StopTokenIds = (stop,)
+    try:
+        acc = L._capi.LNB_ACC_STRICT if mode == "strict" else L._capi.LNB_ACC_FAST
+        eng = L.inference.InferenceEngine(gm, L.model.InferenceArgs(seq), acc_mode=acc)
+        got, last_state = [[] for _ in prompts], {}
+        for i, state, tok in eng.GenerateTokensBatch(prompts):
+            assert last_state.get(i, L.inference.GSInProgress) == L.inference.GSInProgress      # nothing after the end
+            got[i].append(tok); last_state[i] = state
+        if mode == "strict":
+            assert got == exp
+            for i, e in enumerate(exp):
+                assert last_state[i] == (L.inference.GSFinishedByReachingEOS if e[-1] == stop else L.inference.GSFinishedByReachingSeqLen)
+        else:   # FAST may flip a near-tie; the streams must at least be complete and well-formed
+            assert all(len(g) >= 1 and s != L.inference.GSInProgress for g, s in zip(got, last_state.values()))
+        one = [tok for _, _, tok in eng.GenerateTokensBatch([prompts[2]])]                       # n = 1 delegates
+        assert mode != "strict" or one == exp[2]
+        with pytest.raises(L.ml.MlError):
+            list(eng.GenerateTokensBatch([list(range(seq))]))
+    finally:
+        gm.Vocabulary.StopTokenIds = saved
