@@ -3,8 +3,11 @@
 // 8-token prompt and prints the generated token ids and the decode rate.
 // Build: make -C host      Run: host/lnb_generate [seq_len=136] [strict|fast] [tiny | <modelDir>] [batch=N]
 // batch=N: N prompts (prompt b = ids[1:] + 977 b) generated together, one pass over the weights per step.
+// prompt=TEXT (with <modelDir>/tokenizer.model): TEXT goes through the chat template and the BPE tokenizer, the
+// generated ids come back as text (cmd/main.go's flow without the console UI).
 // <modelDir> holds params.json + consolidated.00.pth (model.LoadModel, src/model/loader.go:18-70);
 // `lnb_generate --write-synthetic <modelDir> [tiny]` writes such a directory for the synthetic weights (host-only).
+// `lnb_generate --tokenize <tokenizer.model> <text>` prints the chat-template token ids of <text> (host-only).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -44,6 +47,19 @@ int main(int argc, char** argv) {
       return 1;
     }
   }
+  if (argc > 3 && !strcmp(argv[1], "--tokenize")) {   // host-only: chat template + BPE + round trip
+    try {
+      model::Tokenizer tok(argv[2]);
+      const std::vector<int32_t> ids = tok.Tokenize({{"user", argv[3]}});
+      printf("ids:");
+      for (int32_t t : ids) printf(" %d", t);
+      printf("\ntext: %s\n", tok.TokenBatchToString(ids).c_str());
+      return 0;
+    } catch (const std::exception& e) {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+  }
   const int seq_len = argc > 1 ? atoi(argv[1]) : 136;
   const int acc = (argc > 2 && !strcmp(argv[2], "fast")) ? LNB_ACC_FAST : LNB_ACC_STRICT;
   const bool tiny = argc > 3 && !strcmp(argv[3], "tiny");
@@ -70,8 +86,21 @@ int main(int argc, char** argv) {
     model::Vocabulary vocab;
     if (tiny || transformer.args.vocab_size < 128256) vocab.StopTokenIds = {1000000000};
     int batch = 0;
-    for (int i = 1; i < argc; i++)
+    const char* prompt_text = nullptr;
+    for (int i = 1; i < argc; i++) {
       if (!strncmp(argv[i], "batch=", 6)) batch = atoi(argv[i] + 6);
+      if (!strncmp(argv[i], "prompt=", 7)) prompt_text = argv[i] + 7;
+    }
+    std::unique_ptr<model::Tokenizer> tokenizer;
+    if (prompt_text) {
+      if (!from_dir) throw Error("prompt= needs a model directory with tokenizer.model");
+      tokenizer = std::make_unique<model::Tokenizer>(std::string(argv[3]) + "/tokenizer.model");
+      if (tokenizer->Size() != transformer.args.vocab_size)   // checkModelArgs (loader.go:98-120)
+        throw Error("VocabSize=" + std::to_string(transformer.args.vocab_size) + " and vocabulary model length=" +
+                    std::to_string(tokenizer->Size()) + " aren't equal");
+      vocab = tokenizer->GetVocabulary();
+      prompt = tokenizer->Tokenize({{"user", prompt_text}});
+    }
     if (batch > 0) {
       const int mod = transformer.args.vocab_size < 128256 ? 1000 : 128000;
       std::vector<std::vector<int32_t>> prompts(batch, prompt);
@@ -100,6 +129,7 @@ int main(int argc, char** argv) {
       out.push_back(tok);
     });
     auto t1 = std::chrono::steady_clock::now();
+    if (tokenizer) printf("text: %s\n", tokenizer->TokenBatchToString(out).c_str());
     printf("tokens:");
     for (int32_t t : out) printf(" %d", t);
     const double dec_s = std::chrono::duration<double>(t1 - t_first).count();

@@ -98,6 +98,61 @@ struct Vocabulary {  // vocabulary.go (ids only)
   std::vector<int32_t> StopTokenIds{128008, 128009};  // src/tiktoken/tiktokenreader.go:81
 };
 
+// src/tiktoken + model.Vocabulary's tables + the tokenizer half of src/inference/tokenize.go over lnb_vocab
+struct PromptPart {  // inference.PromptPart (tokenize.go:21-25)
+  std::string Header, Content;
+};
+class Tokenizer {
+ public:
+  explicit Tokenizer(const std::string& vocabFilePath) { check(lnb_vocab_load(vocabFilePath.c_str(), &h_)); }   // tiktoken.Load
+  ~Tokenizer() { lnb_vocab_destroy(h_); }
+  Tokenizer(const Tokenizer&) = delete;
+  int Size() const { return lnb_vocab_size(h_); }
+  Vocabulary GetVocabulary() const {   // PadId / StopTokenIds of NewVocabulary (vocabulary.go:23-50)
+    Vocabulary v;
+    int32_t stop[2];
+    check(lnb_vocab_special_ids(h_, nullptr, nullptr, &v.PadId, stop));
+    v.StopTokenIds = {stop[0], stop[1]};
+    return v;
+  }
+  std::vector<int32_t> TokenizeString(const std::string& text) const {   // tokenize.go:175-193
+    std::vector<int32_t> out(text.size() + 8);
+    int n = 0;
+    check(lnb_tokenize_string(h_, text.data(), (int64_t)text.size(), out.data(), (int)out.size(), &n));
+    out.resize((size_t)n);
+    return out;
+  }
+  std::vector<int32_t> Tokenize(const std::vector<PromptPart>& parts) const {   // tokenize.go:27-95
+    std::vector<const char*> hs, cs;
+    size_t cap = 32;
+    for (const auto& p : parts) {
+      hs.push_back(p.Header.c_str());
+      cs.push_back(p.Content.c_str());
+      cap += p.Header.size() + p.Content.size() + 16;
+    }
+    std::vector<int32_t> out(cap);
+    int n = 0;
+    check(lnb_tokenize_prompt(h_, hs.data(), cs.data(), (int)parts.size(), out.data(), (int)out.size(), &n));
+    out.resize((size_t)n);
+    return out;
+  }
+  std::string TokenBatchToString(const std::vector<int32_t>& ids) const {   // tokenize.go:239-258 (bytes; no emoji annotation)
+    std::string out(64 + 128 * ids.size(), '\0');
+    int64_t n = 0;
+    int rc = lnb_detokenize(h_, ids.data(), (int)ids.size(), &out[0], (int64_t)out.size(), &n);
+    if (rc != 0 && n > (int64_t)out.size()) {
+      out.assign((size_t)n, '\0');
+      rc = lnb_detokenize(h_, ids.data(), (int)ids.size(), &out[0], (int64_t)out.size(), &n);
+    }
+    check(rc);
+    out.resize((size_t)n);
+    return out;
+  }
+
+ private:
+  lnb_vocab* h_ = nullptr;
+};
+
 class LlamaTransformer {  // llamatransformer.go:16-113
  public:
   ModelArgs args;
@@ -231,7 +286,8 @@ enum GenerationState { GSInProgress = 0, GSFinishedByReachingEOS = 1, GSFinished
 // generateTokensInternal (inference.go:173-254); `emit` plays generatedTokensCh
 inline void GenerateTokens(model::LlamaTransformer& transformer, const model::Vocabulary& vocab, int sequenceLength, int accMode,
                            const std::vector<int32_t>& promptTokens, const std::function<void(GenerationState, int32_t)>& emit) {
-  model::InferenceContext infContext(transformer, sequenceLength, accMode);
+  // the prefill call carries the whole prompt: size the session's row buffers for it
+  model::InferenceContext infContext(transformer, sequenceLength, accMode, std::max<int>(8, (int)promptTokens.size()));
   const int promptLength = (int)promptTokens.size();
   if (promptLength >= infContext.SequenceLength)
     throw Error("context SequenceLength " + std::to_string(infContext.SequenceLength) + " must be higher than prompt tokens length " +

@@ -126,6 +126,36 @@ int lnb_pth_writer_finish(lnb_pth_writer* w);
 /* the synthetic checkpoint of lnb_model_init_synthetic as a consolidated.00.pth (same bits, host-only) */
 int lnb_pth_write_synthetic(const char* path, const lnb_model_args* args, uint64_t seed);
 
+/* ---- tokenizer ------------------------------------------------------------------
+ * tiktoken vocabulary + Llama-3 BPE, host-only.  Replaces tiktoken.Load (src/tiktoken/tiktokenreader.go:12-85),
+ * model.NewVocabulary incl. its split regexp (src/model/vocabulary.go:23-50), InferenceEngine.TokenizeString /
+ * bytePairMerge / Tokenize (src/inference/tokenize.go:27-193) and the byte concatenation under
+ * TokenBatchToString (:239-258).  The console's emoji alias annotation (src/inference/emoji.go) is not built. */
+typedef struct lnb_vocab lnb_vocab;
+/* tokenizer.model: "<base64 token> <rank>" lines; the 256 special tokens are appended after the ranks */
+int lnb_vocab_load(const char* tokenizer_model_path, lnb_vocab** out);
+int lnb_vocab_destroy(lnb_vocab* v);
+/* len(Vocabulary.IdToToken) (vocabulary.go:27) */
+int lnb_vocab_size(const lnb_vocab* v);
+/* Vocabulary.TokenToId[token]; *id = -1 when absent.  `token` is raw bytes (pieces need not be valid UTF-8) */
+int lnb_vocab_token_id(const lnb_vocab* v, const void* token, int token_len, int32_t* id);
+/* Vocabulary.IdToToken[id]: pointer into the vocabulary, valid until lnb_vocab_destroy */
+int lnb_vocab_token_bytes(const lnb_vocab* v, int32_t id, const void** bytes, int* len);
+/* BeginOfSentenceId, EndOfSentenceId, PadId (-1) and the two StopTokenIds <|eom_id|>, <|eot_id|> (tiktokenreader.go:74-82) */
+int lnb_vocab_special_ids(const lnb_vocab* v, int32_t* bos, int32_t* eos, int32_t* pad, int32_t* stop2);
+/* Vocabulary.SplitRegexp.FindAllString (src/model/vocabulary.go:36, used at tokenize.go:180): byte offsets one past
+ * each piece of `text`, by a hand-written matcher with Go/RE2 semantics (leftmost-first, ASCII \s, \p{L} / \p{N} of
+ * Unicode 15.0, simple case folding in the contraction alternative) */
+int lnb_split_pieces(const char* text, int64_t text_len, int64_t* ends, int cap, int* n_out);
+/* InferenceEngine.TokenizeString (tokenize.go:175-193).  *n_out = tokens produced (also when cap is too small) */
+int lnb_tokenize_string(const lnb_vocab* v, const char* text, int64_t text_len, int32_t* out, int cap, int* n_out);
+/* InferenceEngine.Tokenize (tokenize.go:27-95): <|begin_of_text|>, every non-empty part wrapped in header tokens and
+ * closed with <|eot_id|>, then the open assistant header */
+int lnb_tokenize_prompt(const lnb_vocab* v, const char* const* headers, const char* const* contents, int n_parts,
+                        int32_t* out, int cap, int* n_out);
+/* bytes of the tokens up to the first PadId (TokenBatchToString :239-258 without the emoji annotation) */
+int lnb_detokenize(const lnb_vocab* v, const int32_t* ids, int n, char* out, int64_t cap, int64_t* n_out);
+
 /* Random-init every tensor directly in HBM with the synthetic generator of DESIGN.md
  * (no checkpoint exists in the build environment).  Same bits as oracle's
  * orc_synth_fill for the same seed. */

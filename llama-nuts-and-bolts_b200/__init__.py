@@ -14,6 +14,6 @@ cgo shims (INTEGRATION.md shows the Go side).  There is NO CPU fallback: importi
 package fails loudly if liblnb.so is missing, and every op raises if CUDA is unavailable.
 """
 from . import _capi  # noqa: F401  (loads liblnb.so or raises)
-from . import ml, model, inference, synth, torch_reader  # noqa: F401
+from . import ml, model, inference, synth, torch_reader, vocabulary  # noqa: F401
 
 __all__ = ["ml", "model", "inference", "synth", "_capi"]

@@ -75,6 +75,16 @@ SIGNATURES = {
     "lnb_pth_writer_add": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
     "lnb_pth_writer_finish": (C.c_int, [C.c_void_p]),
     "lnb_pth_write_synthetic": (C.c_int, [C.c_char_p, C.POINTER(ModelArgsC), C.c_uint64]),
+    "lnb_vocab_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "lnb_vocab_destroy": (C.c_int, [C.c_void_p]),
+    "lnb_vocab_size": (C.c_int, [C.c_void_p]),
+    "lnb_vocab_token_id": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, i32p]),
+    "lnb_vocab_token_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "lnb_vocab_special_ids": (C.c_int, [C.c_void_p, i32p, i32p, i32p, i32p]),
+    "lnb_split_pieces": (C.c_int, [C.c_char_p, C.c_int64, i64p, C.c_int, C.POINTER(C.c_int)]),
+    "lnb_tokenize_string": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, i32p, C.c_int, C.POINTER(C.c_int)]),
+    "lnb_tokenize_prompt": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, i32p, C.c_int, C.POINTER(C.c_int)]),
+    "lnb_detokenize": (C.c_int, [C.c_void_p, i32p, C.c_int, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
     "lnb_op_linear_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_matmul_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "lnb_op_rmsnorm_bf16": (C.c_int, [u16p, u16p, u16p, C.c_int, C.c_int, C.c_float, C.c_int]),

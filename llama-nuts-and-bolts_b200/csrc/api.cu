@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "seqsum.cuh"
 #include "pth.hpp"
+#include "tokenizer.hpp"
 
 namespace lnb {
 void build_rope_table(int dim, int end, double theta, bool use_scaled, std::vector<float>& out);
@@ -477,6 +478,96 @@ extern "C" int lnb_pth_writer_finish(lnb_pth_writer* w) {
   const bool ok = w->w.finish(err);
   delete w;
   return ok ? 0 : fail(LNB_EINVAL, "%s", err.c_str());
+}
+
+// ---- tokenizer: tiktoken vocabulary + BPE, host-only ----------------------------------
+struct lnb_vocab {
+  lnb::Vocab v;
+};
+extern "C" int lnb_vocab_load(const char* tokenizer_model_path, lnb_vocab** out) {
+  if (!tokenizer_model_path || !out) return fail(LNB_EINVAL, "NULL argument");
+  lnb_vocab* h = new lnb_vocab();
+  std::string err;
+  if (!h->v.load(tokenizer_model_path, err)) {
+    delete h;
+    return fail(LNB_EINVAL, "%s", err.c_str());
+  }
+  *out = h;
+  return 0;
+}
+extern "C" int lnb_vocab_destroy(lnb_vocab* v) {
+  delete v;
+  return 0;
+}
+extern "C" int lnb_vocab_size(const lnb_vocab* v) {
+  if (!v) return fail(LNB_EINVAL, "NULL argument");
+  return v->v.size();
+}
+extern "C" int lnb_vocab_token_id(const lnb_vocab* v, const void* token, int token_len, int32_t* id) {
+  if (!v || !token || token_len < 0 || !id) return fail(LNB_EINVAL, "bad argument");
+  *id = v->v.id_of(std::string((const char*)token, (size_t)token_len));
+  return 0;
+}
+extern "C" int lnb_vocab_token_bytes(const lnb_vocab* v, int32_t id, const void** bytes, int* len) {
+  if (!v || !bytes || !len) return fail(LNB_EINVAL, "NULL argument");
+  if (id < 0 || id >= v->v.size()) return fail(LNB_EINVAL, "token id %d out of range", id);
+  *bytes = v->v.id_to_token[(size_t)id].data();
+  *len = (int)v->v.id_to_token[(size_t)id].size();
+  return 0;
+}
+extern "C" int lnb_vocab_special_ids(const lnb_vocab* v, int32_t* bos, int32_t* eos, int32_t* pad, int32_t* stop2) {
+  if (!v) return fail(LNB_EINVAL, "NULL argument");
+  if (bos) *bos = v->v.bos_id;
+  if (eos) *eos = v->v.eos_id;
+  if (pad) *pad = v->v.pad_id;
+  if (stop2) { stop2[0] = v->v.stop_ids[0]; stop2[1] = v->v.stop_ids[1]; }
+  return 0;
+}
+static int copy_ids(const std::vector<int32_t>& ids, int32_t* out, int cap, int* n_out) {
+  if (n_out) *n_out = (int)ids.size();
+  if ((int)ids.size() > cap) return fail(LNB_EINVAL, "token buffer too small: need %zu, have %d", ids.size(), cap);
+  if (!ids.empty()) memcpy(out, ids.data(), ids.size() * 4);
+  return 0;
+}
+extern "C" int lnb_tokenize_string(const lnb_vocab* v, const char* text, int64_t text_len, int32_t* out, int cap, int* n_out) {
+  if (!v || (!text && text_len > 0) || text_len < 0 || (!out && cap > 0)) return fail(LNB_EINVAL, "bad argument");
+  std::vector<int32_t> ids;
+  v->v.tokenize_string(std::string(text ? text : "", (size_t)text_len), ids);
+  return copy_ids(ids, out, cap, n_out);
+}
+extern "C" int lnb_split_pieces(const char* text, int64_t text_len, int64_t* ends, int cap, int* n_out) {
+  if ((!text && text_len > 0) || text_len < 0 || (!ends && cap > 0)) return fail(LNB_EINVAL, "bad argument");
+  const std::string t(text ? text : "", (size_t)text_len);
+  int n = 0;
+  for (size_t p = 0; p < t.size();) {
+    p = lnb::Vocab::next_piece(t, p);
+    if (n < cap) ends[n] = (int64_t)p;
+    n++;
+  }
+  if (n_out) *n_out = n;
+  return n > cap ? fail(LNB_EINVAL, "piece buffer too small: need %d, have %d", n, cap) : 0;
+}
+extern "C" int lnb_tokenize_prompt(const lnb_vocab* v, const char* const* headers, const char* const* contents, int n_parts,
+                                   int32_t* out, int cap, int* n_out) {
+  if (!v || n_parts < 0 || (n_parts > 0 && (!headers || !contents)) || (!out && cap > 0)) return fail(LNB_EINVAL, "bad argument");
+  std::vector<lnb::PromptPart> parts;
+  for (int i = 0; i < n_parts; i++) {
+    if (!headers[i] || !contents[i]) return fail(LNB_EINVAL, "NULL prompt part");
+    parts.push_back(lnb::PromptPart{headers[i], contents[i]});
+  }
+  std::vector<int32_t> ids;
+  std::string err;
+  if (!v->v.tokenize_prompt(parts, ids, err)) return fail(LNB_EINVAL, "%s", err.c_str());
+  return copy_ids(ids, out, cap, n_out);
+}
+extern "C" int lnb_detokenize(const lnb_vocab* v, const int32_t* ids, int n, char* out, int64_t cap, int64_t* n_out) {
+  if (!v || (!ids && n > 0) || n < 0 || (!out && cap > 0)) return fail(LNB_EINVAL, "bad argument");
+  std::string s;
+  if (!v->v.detokenize(ids, n, s)) return fail(LNB_EINVAL, "token id out of range");
+  if (n_out) *n_out = (int64_t)s.size();
+  if ((int64_t)s.size() > cap) return fail(LNB_EINVAL, "text buffer too small: need %zu", s.size());
+  if (!s.empty()) memcpy(out, s.data(), s.size());
+  return 0;
 }
 
 // ---- synthetic checkpoint ------------------------------------------------------------------

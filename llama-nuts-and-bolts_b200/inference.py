@@ -31,6 +31,28 @@ class InferenceEngine:
             self.context_hook(ctx)
         return ctx
 
+    # --- tokenizer half of the engine (src/inference/tokenize.go), served by model.Vocabulary when it is a loaded one
+    def _vocab(self):
+        v = self.model.Vocabulary
+        if not hasattr(v, "TokenizeString"):
+            raise ml.MlError("the model was loaded without tokenizer.model (ids only)")
+        return v
+
+    def Tokenize(self, promptParts):                 # tokenize.go:27-95
+        return self._vocab().Tokenize(promptParts)
+
+    def TokenizeBatch(self, prompts):                # :97-107
+        return self._vocab().TokenizeBatch(prompts)
+
+    def TokenizeString(self, text, addBeginOfSentence: bool = False):   # :175-193 (the flag is unused there too)
+        return self._vocab().TokenizeString(text)
+
+    def TokenToString(self, tokenId, decodingContext):                  # :195-237
+        return self._vocab().TokenToString(tokenId, decodingContext)
+
+    def TokenBatchToString(self, tokenIdBatch):      # :239-258
+        return self._vocab().TokenBatchToString(tokenIdBatch)
+
     def GenerateTokens(self, promptTokens, use_reference_api: bool = False, step_times: list | None = None):
         """Generator over (state, token id) exactly like generatedTokensCh.
 

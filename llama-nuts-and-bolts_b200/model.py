@@ -277,12 +277,22 @@ def load_model_args(modelDir: str, max_seq_len: int = 2048) -> dict:
 
 def LoadModel(modelDir: str, device: int = 0, tp_rank: int = 0, tp_size: int = 1, nccl_id=None, max_seq_len: int = 2048) -> Model:
     """model.LoadModel (src/model/loader.go:18-70): <modelDir>/consolidated.00.pth + params.json.
-    The tokenizer is out of scope, so VocabSize (which the reference takes from tokenizer.model when
-    params.json has none, loader.go:103-111) falls back to the rows of tok_embeddings.weight."""
+    tokenizer.model is optional here: when present it becomes model.Vocabulary and supplies / checks VocabSize like
+    the reference (loader.go:84-120); when absent VocabSize falls back to the rows of tok_embeddings.weight."""
     import os
     from .torch_reader import TorchModelReader
     path = os.path.join(modelDir, "consolidated.00.pth")
     d = load_model_args(modelDir, max_seq_len)
+    vocab = None
+    vocab_path = os.path.join(modelDir, "tokenizer.model")
+    if os.path.exists(vocab_path):                      # loadVocab + checkModelArgs (loader.go:84-120)
+        from . import vocabulary
+        vocab = vocabulary.Load(vocab_path)
+        if d["vocab_size"] < 1:
+            d["vocab_size"] = len(vocab)
+        elif d["vocab_size"] != len(vocab):
+            raise _capi.LnbError(-1, f"error while checking config and model: [VocabSize={d['vocab_size']} and vocabulary model "
+                                     f"length={len(vocab)} aren't equal]")
     if d["vocab_size"] < 1:
         with TorchModelReader(path) as r:
             t = r.Load().get("tok_embeddings.weight")
@@ -290,6 +300,8 @@ def LoadModel(modelDir: str, device: int = 0, tp_rank: int = 0, tp_size: int = 1
             raise _capi.LnbError(-1, 'tensor "tok_embeddings.weight" not found')
         d["vocab_size"] = t.Size[0]
     m = Model(ModelArgs.from_c_dict(d), device, tp_rank, tp_size, nccl_id)
+    if vocab is not None:
+        m.Vocabulary = vocab
     try:
         m.Transformer.load_pth(path)
         m.Transformer.finalize()
