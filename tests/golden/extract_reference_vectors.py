@@ -1,0 +1,113 @@
+"""Extracts the reference's weight-free golden vectors for the hot path from its OWN test sources and docs and
+writes tests/golden/reference_vectors.json.
+
+The reference is Go (no toolchain in the image), so it cannot be imported or run to generate fixtures; its tests
+however hold literal known answers for this path.  This script parses those literals where they lie
+under /root/reference (read-only) and records file:line for each, so the committed fixture is provably the
+reference's data and not a transcription.  Run here:  python tests/golden/extract_reference_vectors.py
+(/root/reference does not exist on the GPU box; tests only read the committed JSON.)"""
+import json
+import os
+import re
+import sys
+
+REF = os.environ.get("LNB_REFERENCE_DIR", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json")
+NUM = r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?"
+
+
+def read(rel):
+    with open(os.path.join(REF, rel)) as f:
+        return f.read()
+
+
+def func_body(src, name):
+    """(first line number, text) of `func name(` ... up to the next top-level func"""
+    m = re.search(r"^func %s\(" % re.escape(name), src, re.M)
+    assert m, name
+    nxt = re.search(r"^func ", src[m.end():], re.M)
+    end = m.end() + nxt.start() if nxt else len(src)
+    return src.count("\n", 0, m.start()) + 1, src[m.start():end]
+
+
+def literal(body, var):
+    """nested list of floats of `var := [][]T{ ... }`, BFloat16fromFloat32(x) wrappers removed"""
+    m = re.search(r"\b%s\s*:=\s*((?:\[\])+)[\w.]+\{" % re.escape(var), body)
+    assert m, var
+    depth_decl = m.group(1).count("[]")
+    i = m.end() - 1
+    depth, j = 0, i
+    while True:
+        if body[j] == "{":
+            depth += 1
+        elif body[j] == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        j += 1
+    text = body[i:j + 1]
+    text = re.sub(r"dtype\.BFloat16fromFloat32\((%s)\)" % NUM, r"\1", text)
+    text = re.sub(r"float32\((%s)\)" % NUM, r"\1", text)
+    text = text.replace("{", "[").replace("}", "]")
+    text = re.sub(r",\s*\]", "]", text)
+    text = re.sub(r"(?<![\d.])\.(\d)", r"0.\1", text)          # .5 -> 0.5
+    text = re.sub(r"(\d)\.(?!\d)", r"\1.0", text)               # 1. -> 1.0
+    val = json.loads(text)
+    d, v = 0, val
+    while isinstance(v, list):
+        d += 1
+        v = v[0]
+    assert d == depth_decl, (var, d, depth_decl)
+    return val
+
+
+def main():
+    out = {"_generated_by": "tests/golden/extract_reference_vectors.py", "_reference": "adalkiran/llama-nuts-and-bolts"}
+
+    ops = read("src/ml/operations_test.go")
+    for key, fn, vars_ in (("linear_f32", "TestLinearTransformationF32", ("expected", "weightVals", "inputVals")),
+                           ("linear_bf16", "TestLinearTransformationBF16", ("expected", "weightVals", "inputVals")),
+                           ("matmul_bf16", "TestMatMulBF16", ("expected", "inputVals", "otherVals"))):
+        line, body = func_body(ops, fn)
+        entry = {"source": "src/ml/operations_test.go:%d (%s)" % (line, fn), "threshold": "common.THRESHOLD_F32 = 1e-3"}
+        for v in vars_:
+            entry[v] = literal(body, v)
+        out[key] = entry
+    thr = read("src/common/utils.go")
+    m = re.search(r"THRESHOLD_F32\s*=\s*(%s)" % NUM, thr)
+    out["threshold_f32"] = {"source": "src/common/utils.go:%d" % (thr.count("\n", 0, m.start()) + 1), "value": float(m.group(1))}
+
+    bft = read("src/dtype/bfloat16_test.go")
+    cases = []
+    for fn in ("TestNotTruncatedDecimalPart", "TestTruncatedDecimalPart"):
+        line, body = func_body(bft, fn)
+        exp = re.findall(r"expected\s*:?=\s*float32\((%s)\)" % NUM, body)
+        inp = re.findall(r"BFloat16fromFloat32\((%s)\)" % NUM, body)
+        assert len(exp) == len(inp) and exp, fn
+        cases += [{"input": float(i), "expected": float(e), "source": "src/dtype/bfloat16_test.go:%d (%s)" % (line, fn)} for i, e in zip(inp, exp)]
+    out["bf16_from_f32"] = cases
+    line, body = func_body(bft, "TestReadBFloat16LittleEndian")
+    le = []
+    for m in re.finditer(r'"input":\s*\[\]byte\{0x([0-9A-Fa-f]+),\s*0x([0-9A-Fa-f]+)\}.*?"expectedUInt16Bits":\s*uint16\(0x([0-9A-Fa-f]+)\).*?'
+                         r'"expectedF32":\s*float32\((%s)\)' % NUM, body, re.S):
+        le.append({"bytes": [int(m.group(1), 16), int(m.group(2), 16)], "bits": int(m.group(3), 16), "f32": float(m.group(4))})
+    assert len(le) == 3
+    out["bf16_little_endian"] = {"source": "src/dtype/bfloat16_test.go:%d (TestReadBFloat16LittleEndian)" % line, "cases": le}
+
+    doc = read("docs/10-ROPE-ROTARY-POSITIONAL-EMBEDDINGS.md")
+    m = re.search(r"after running Apply_AsFloat32 and then applyScaling, freqs will be:\s*\nfreqs:\s*\{[^\n]*\n(.*?)\n\}", doc, re.S)
+    assert m
+    freqs = [float(x) for x in re.findall(NUM, m.group(1))]
+    assert len(freqs) == 64, len(freqs)
+    out["rope_scaled_inv_freqs"] = {"source": "docs/10-ROPE-ROTARY-POSITIONAL-EMBEDDINGS.md:%d" % (doc.count("\n", 0, m.start(1)) + 1),
+                                    "note": "all 64 bf16 inverse frequencies after Llama-3.1 scaling, printed with 5 significant digits",
+                                    "values": freqs}
+
+    with open(OUT, "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+        f.write("\n")
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.helpers import bf, bf16_ulp_diff, emulate_fast_linear, emulate_fast_rms_scale, f32, rand_bf16
+from tests.helpers import bf, bf16_ulp_diff, emulate_fast_linear, emulate_fast_rms_scale, f32, rand_bf16, reference_vectors
 
 pytestmark = pytest.mark.gpu
 
@@ -26,9 +26,8 @@ def test_device_present(L):
 
 def test_linear_bf16_reference_golden(L):
     ml = L.ml
-    w = ml.Tensor.from_f32([[0.01, 0.02, 0.03], [0.04, 0.05, 0.06], [0.07, 0.08, 0.09], [0.10, 0.11, 0.12]])
-    x = ml.Tensor.from_f32([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]])
-    exp = np.array([[0.0138, 0.0317, 0.0495, 0.0673], [0.0317, 0.0761, 0.1210, 0.1660]], np.float32)
+    g = reference_vectors()["linear_bf16"]          # tests/golden: TestLinearTransformationBF16's literals
+    w, x, exp = ml.Tensor.from_f32(g["weightVals"]), ml.Tensor.from_f32(g["inputVals"]), np.array(g["expected"], np.float32)
     got = ml.LinearTransformation(x, w)
     assert got.Size == [2, 4]
     assert np.abs(got.to_f32_array() - exp).max() <= 1e-3      # common.THRESHOLD_F32
@@ -37,10 +36,8 @@ def test_linear_bf16_reference_golden(L):
 
 def test_matmul_bf16_reference_golden(L):
     ml = L.ml
-    a = ml.Tensor.from_f32([[[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]]] * 2)
-    b = ml.Tensor.from_f32([[[0.01, 0.02, 0.03, 0.04], [0.05, 0.06, 0.07, 0.08], [0.09, 0.10, 0.11, 0.12]]] * 2)
-    exp = np.array([[[3.7598e-02, 4.3457e-02, 4.9561e-02, 5.5420e-02], [8.2520e-02, 9.7168e-02, 1.1230e-01, 1.2695e-01]]] * 2,
-                   np.float32)
+    g = reference_vectors()["matmul_bf16"]          # tests/golden: TestMatMulBF16's literals
+    a, b, exp = ml.Tensor.from_f32(g["inputVals"]), ml.Tensor.from_f32(g["otherVals"]), np.array(g["expected"], np.float32)
     got = ml.MatMul(a, b)
     assert got.Size == [2, 2, 4]
     assert np.abs(got.to_f32_array() - exp).max() <= 1e-3

@@ -10,8 +10,10 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
+from tests.helpers import reference_vectors
 
-THRESHOLD_F32 = 1e-3
+GOLD = reference_vectors()                     # tests/golden/reference_vectors.json (the reference's own literals)
+THRESHOLD_F32 = GOLD["threshold_f32"]["value"]
 
 
 def bf(x):
@@ -24,7 +26,7 @@ def f(b):
 
 # ---- src/dtype/bfloat16_test.go:8-66 -------------------------------------------------
 
-@pytest.mark.parametrize("inp,exp", [(6.25, 6.25), (1.53, 1.5234375), (6.53, 6.5), (11.34, 11.3125), (586.25, 584.0)])
+@pytest.mark.parametrize("inp,exp", [(c["input"], c["expected"]) for c in GOLD["bf16_from_f32"]])
 def test_bf16_truncation(inp, exp):
     b = O.lib().orc_f32_to_bf16(inp)
     assert O.lib().orc_bf16_to_f32(b) == np.float32(exp)
@@ -32,8 +34,7 @@ def test_bf16_truncation(inp, exp):
 
 
 # src/dtype/bfloat16_test.go:68-106 (little-endian storage)
-@pytest.mark.parametrize("raw,bits,val", [
-    (b"\xA5\x35", 0x35A5, 0.0000012293458), (b"\xF4\xB5", 0xB5F4, -0.00000181794167), (b"\x92\xB6", 0xB692, -0.000004351139)])
+@pytest.mark.parametrize("raw,bits,val", [(bytes(c["bytes"]), c["bits"], c["f32"]) for c in GOLD["bf16_little_endian"]["cases"]])
 def test_bf16_little_endian(raw, bits, val):
     b = np.frombuffer(raw, dtype="<u2")
     assert int(b[0]) == bits
@@ -43,18 +44,17 @@ def test_bf16_little_endian(raw, bits, val):
 # ---- src/ml/operations_test.go:782-829 ------------------------------------------------
 
 def test_linear_f32_golden():
-    w = np.array([[0.01, 0.02, 0.03], [0.04, 0.05, 0.06], [0.07, 0.08, 0.09], [0.10, 0.11, 0.12]], np.float32)
-    x = np.array([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]], np.float32)
-    exp = np.array([[0.014, 0.032, 0.05, 0.068], [0.032, 0.077, 0.122, 0.167]], np.float32)
+    g = GOLD["linear_f32"]
+    w, x, exp = (np.array(g[k], np.float32) for k in ("weightVals", "inputVals", "expected"))
+    assert w.shape == (4, 3) and x.shape == (2, 3) and exp.shape == (2, 4)
     assert np.abs(O.linear_f32(x, w) - exp).max() <= THRESHOLD_F32
 
 
 # ---- src/ml/operations_test.go:831-878 ------------------------------------------------
 
 def test_linear_bf16_golden():
-    w = bf([[0.01, 0.02, 0.03], [0.04, 0.05, 0.06], [0.07, 0.08, 0.09], [0.10, 0.11, 0.12]])
-    x = bf([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]])
-    exp = np.array([[0.0138, 0.0317, 0.0495, 0.0673], [0.0317, 0.0761, 0.1210, 0.1660]], np.float32)
+    g = GOLD["linear_bf16"]
+    w, x, exp = bf(g["weightVals"]), bf(g["inputVals"]), np.array(g["expected"], np.float32)
     got = f(O.linear_bf16(x, w))
     assert np.abs(got - exp).max() <= THRESHOLD_F32
     # (the literals are 4-decimal PyTorch prints, so 1e-3 is as tight as the reference pins this)
@@ -64,10 +64,8 @@ def test_linear_bf16_golden():
 # ---- src/ml/operations_test.go:880-946 ------------------------------------------------
 
 def test_matmul_bf16_golden():
-    a = bf([[[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]]] * 2)
-    b = bf([[[0.01, 0.02, 0.03, 0.04], [0.05, 0.06, 0.07, 0.08], [0.09, 0.10, 0.11, 0.12]]] * 2)
-    exp = np.array([[[3.7598e-02, 4.3457e-02, 4.9561e-02, 5.5420e-02], [8.2520e-02, 9.7168e-02, 1.1230e-01, 1.2695e-01]]] * 2,
-                   np.float32)
+    g = GOLD["matmul_bf16"]
+    a, b, exp = bf(g["inputVals"]), bf(g["otherVals"]), np.array(g["expected"], np.float32)
     got = f(O.matmul_bf16(a, b))
     assert got.shape == (2, 2, 4)
     assert np.abs(got - exp).max() <= THRESHOLD_F32
@@ -94,14 +92,8 @@ def test_mean_golden():
 
 # ---- docs/10-ROPE-ROTARY-POSITIONAL-EMBEDDINGS.md:276-288 (all 64 scaled inverse freqs) --
 
-DOC_FREQS = [
-    1.0000e+00, 8.1250e-01, 6.6016e-01, 5.3906e-01, 4.3945e-01, 3.5742e-01, 2.9102e-01, 2.3730e-01, 1.9336e-01, 1.5723e-01,
-    1.2793e-01, 1.0449e-01, 8.4961e-02, 6.9336e-02, 5.6641e-02, 4.6143e-02, 3.7598e-02, 3.0518e-02, 2.4902e-02, 2.0264e-02,
-    1.6479e-02, 1.3489e-02, 1.0986e-02, 8.9111e-03, 7.2632e-03, 5.9204e-03, 4.8218e-03, 3.9368e-03, 3.2043e-03, 2.1515e-03,
-    1.3504e-03, 8.5068e-04, 5.1880e-04, 3.1090e-04, 1.7834e-04, 9.5367e-05, 7.7724e-05, 6.2943e-05, 5.1498e-05, 4.1962e-05,
-    3.4094e-05, 2.7895e-05, 2.2650e-05, 1.8477e-05, 1.5080e-05, 1.2279e-05, 1.0014e-05, 8.1062e-06, 6.6459e-06, 5.3942e-06,
-    4.4107e-06, 3.5912e-06, 2.9206e-06, 2.3842e-06, 1.9372e-06, 1.5795e-06, 1.2890e-06, 1.0431e-06, 8.5309e-07, 6.9663e-07,
-    5.6624e-07, 4.6194e-07, 3.7625e-07, 3.0547e-07]
+DOC_FREQS = GOLD["rope_scaled_inv_freqs"]["values"]
+assert len(DOC_FREQS) == 64
 
 
 def test_rope_freqs_match_reference_doc():
@@ -202,3 +194,20 @@ def test_linear_paths_agree_s1_vs_sN():
         for k in range(96):
             acc = np.float32(acc + np.float32(xs[s, k] * ws[n, k]))
         assert full[s, n] == bf([acc])[0]
+
+
+def test_committed_fixture_is_what_the_reference_sources_say(tmp_path):
+    """re-run the extractor against /root/reference when it is there (this container; not the GPU box)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/src/ml"):
+        pytest.skip("/root/reference is not present")
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = open(os.path.join(here, "golden", "extract_reference_vectors.py")).read().replace(
+        'OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json")', "OUT = %r" % str(tmp_path / "v.json"))
+    script = tmp_path / "extract.py"
+    script.write_text(src)
+    subprocess.check_call([sys.executable, str(script)])
+    assert json.load(open(tmp_path / "v.json")) == GOLD
