@@ -73,6 +73,10 @@ def main():
         for v in vars_:
             entry[v] = literal(body, v)
         out[key] = entry
+    line, body = func_body(ops, "TestPow")          # ARange(3, 8, 1, DT_BF16) squared
+    out["pow2_arange_3_8"] = {"source": "src/ml/operations_test.go:%d (TestPow, case 1)" % line, "expected": literal(body, "expected")}
+    line, body = func_body(ops, "TestMean3dKeepDimTrue")   # createTestInputTensor([5,4,3]) = 1, 2, 3, ... ; mean over the last dim
+    out["mean_5x4x3_keepdim"] = {"source": "src/ml/operations_test.go:%d (TestMean3dKeepDimTrue)" % line, "expected": literal(body, "expected")}
     thr = read("src/common/utils.go")
     m = re.search(r"THRESHOLD_F32\s*=\s*(%s)" % NUM, thr)
     out["threshold_f32"] = {"source": "src/common/utils.go:%d" % (thr.count("\n", 0, m.start()) + 1), "value": float(m.group(1))}

@@ -76,7 +76,7 @@ def test_matmul_bf16_golden():
 
 def test_pow2_golden():
     x = bf(np.arange(3, 8, dtype=np.float32))
-    assert np.array_equal(O.pow2_bf16(x), np.array([9, 16, 25, 36, 49], np.float32))
+    assert np.array_equal(O.pow2_bf16(x), np.array(GOLD["pow2_arange_3_8"]["expected"], np.float32))
 
 
 # ---- src/ml/operations_test.go:654-780 (Mean over createTestInputTensor 1,2,3,...) -----
@@ -84,7 +84,7 @@ def test_pow2_golden():
 def test_mean_golden():
     t = np.arange(1, 61, dtype=np.float32).reshape(5, 4, 3)
     got = O.mean_f32(t)
-    exp = t.mean(-1, keepdims=True)  # 2, 5, 8, ... exactly representable
+    exp = np.array(GOLD["mean_5x4x3_keepdim"]["expected"], np.float32)  # 2, 5, 8, ... exactly representable
     assert got.shape == (5, 4, 1)
     assert np.array_equal(got, exp)
     assert got[0, 0, 0] == 2.0 and got[4, 3, 0] == 59.0
