@@ -34,7 +34,8 @@ static int write_synthetic_dir(const char* dir, bool tiny) {
   fputs(params, f);
   fclose(f);
   check(lnb_pth_write_synthetic((d + "/consolidated.00.pth").c_str(), &args, tiny ? 7 : 0x4C4E42));
-  printf("wrote %s/params.json and %s/consolidated.00.pth\n", dir, dir);
+  check(lnb_vocab_write_synthetic((d + "/tokenizer.model").c_str(), args.vocab_size - 256));   // + 256 special tokens
+  printf("wrote %s/params.json, %s/consolidated.00.pth and %s/tokenizer.model\n", dir, dir, dir);
   return 0;
 }
 

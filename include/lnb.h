@@ -135,6 +135,10 @@ typedef struct lnb_vocab lnb_vocab;
 /* tokenizer.model: "<base64 token> <rank>" lines; the 256 special tokens are appended after the ranks */
 int lnb_vocab_load(const char* tokenizer_model_path, lnb_vocab** out);
 int lnb_vocab_destroy(lnb_vocab* v);
+/* writes a stand-in tokenizer.model with n_mergeable ranks (256 bytes + unique 3-byte fillers that never merge) so that a
+ * synthetic model directory passes checkModelArgs' VocabSize == vocabulary length (src/model/loader.go:98-120) */
+int lnb_vocab_write_synthetic(const char* path, int n_mergeable);
+
 /* len(Vocabulary.IdToToken) (vocabulary.go:27) */
 int lnb_vocab_size(const lnb_vocab* v);
 /* Vocabulary.TokenToId[token]; *id = -1 when absent.  `token` is raw bytes (pieces need not be valid UTF-8) */

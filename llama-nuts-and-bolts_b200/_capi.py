@@ -76,6 +76,7 @@ SIGNATURES = {
     "lnb_pth_writer_finish": (C.c_int, [C.c_void_p]),
     "lnb_pth_write_synthetic": (C.c_int, [C.c_char_p, C.POINTER(ModelArgsC), C.c_uint64]),
     "lnb_vocab_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "lnb_vocab_write_synthetic": (C.c_int, [C.c_char_p, C.c_int]),
     "lnb_vocab_destroy": (C.c_int, [C.c_void_p]),
     "lnb_vocab_size": (C.c_int, [C.c_void_p]),
     "lnb_vocab_token_id": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, i32p]),

@@ -495,6 +495,12 @@ extern "C" int lnb_vocab_load(const char* tokenizer_model_path, lnb_vocab** out)
   *out = h;
   return 0;
 }
+extern "C" int lnb_vocab_write_synthetic(const char* path, int n_mergeable) {
+  if (!path) return fail(LNB_EINVAL, "NULL argument");
+  std::string err;
+  if (!lnb::write_synthetic_vocab(path, n_mergeable, err)) return fail(LNB_EINVAL, "%s", err.c_str());
+  return 0;
+}
 extern "C" int lnb_vocab_destroy(lnb_vocab* v) {
   delete v;
   return 0;

@@ -305,4 +305,41 @@ bool Vocab::detokenize(const int32_t* ids, int n, std::string& out) const {
   return true;
 }
 
+static void b64encode(const unsigned char* p, size_t n, std::string* out) {
+  static const char* T = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+  for (size_t i = 0; i < n; i += 3) {
+    const uint32_t b0 = p[i], b1 = i + 1 < n ? p[i + 1] : 0, b2 = i + 2 < n ? p[i + 2] : 0;
+    const uint32_t w = (b0 << 16) | (b1 << 8) | b2;
+    out->push_back(T[w >> 18]);
+    out->push_back(T[(w >> 12) & 63]);
+    out->push_back(i + 1 < n ? T[(w >> 6) & 63] : '=');
+    out->push_back(i + 2 < n ? T[w & 63] : '=');
+  }
+}
+
+bool write_synthetic_vocab(const std::string& path, int n_mergeable, std::string& err) {
+  if (n_mergeable < 256 || n_mergeable > 256 + (1 << 23)) { err = "synthetic vocabulary needs 256 <= n_mergeable <= 256 + 2^23"; return false; }
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) { err = "create " + path + ": " + strerror(errno); return false; }
+  std::string line;
+  for (int r = 0; r < n_mergeable; r++) {
+    unsigned char tok[3];
+    size_t len = 1;
+    if (r < 256) tok[0] = (unsigned char)r;
+    else {
+      const uint32_t j = (uint32_t)(r - 256);
+      tok[0] = (unsigned char)(j & 0xff);
+      tok[1] = (unsigned char)((j >> 8) & 0xff);
+      tok[2] = (unsigned char)(0x80 | ((j >> 16) & 0x7f));
+      len = 3;
+    }
+    line.clear();
+    b64encode(tok, len, &line);
+    line += " " + std::to_string(r) + "\n";
+    if (fwrite(line.data(), 1, line.size(), f) != line.size()) { fclose(f); err = "write failed"; return false; }
+  }
+  if (fclose(f) != 0) { err = "close failed"; return false; }
+  return true;
+}
+
 }  // namespace lnb

@@ -47,4 +47,10 @@ class Vocab {
   void byte_pair_merge(const std::string& piece, std::vector<int32_t>& out) const;   // tokenize.go:109-173
 };
 
+// A stand-in tokenizer.model with exactly n_mergeable ranks: the 256 single bytes followed by unique 3-byte filler
+// strings.  No 2-byte token exists, so the byte-pair merge never fires: text tokenizes byte by byte (a whole 3-byte
+// piece may coincide with a filler and become that one id; it detokenizes to the same bytes).  Lets a synthetic model directory satisfy checkModelArgs (VocabSize == vocabulary length,
+// src/model/loader.go:98-120) so that the unmodified reference -- or lnb_generate prompt=... -- runs end to end.
+bool write_synthetic_vocab(const std::string& path, int n_mergeable, std::string& err);
+
 }  // namespace lnb

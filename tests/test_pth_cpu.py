@@ -263,6 +263,13 @@ def test_cpp_host_cli_writes_a_model_directory_without_a_gpu(tmp_path):
     tiny = dict(L.synth.TINY)
     assert {k: d[k] for k in ("dim", "n_layers", "n_heads", "n_kv_heads", "head_dim", "ffn_dim", "vocab_size")} == \
         {k: tiny[k] for k in ("dim", "n_layers", "n_heads", "n_kv_heads", "head_dim", "ffn_dim", "vocab_size")}
+    # the stand-in tokenizer.model makes the directory pass checkModelArgs: vocabulary length == VocabSize
+    from lnb_b200 import vocabulary
+    v = vocabulary.Load(str(tmp_path / "tokenizer.model"))
+    assert len(v) == tiny["vocab_size"] and v.BeginOfSentenceId == tiny["vocab_size"] - 256
+    ids = v.TokenizeString("Hi é!\n")
+    assert ids == list("Hi é!\n".encode()) and v.TokenBatchToString(ids) == "Hi é!\n"
+    v.close()
     sd = torch.load(str(tmp_path / "consolidated.00.pth"), weights_only=True)
     expect = host_tensors(tiny, 7)
     assert set(sd) == set(expect)
