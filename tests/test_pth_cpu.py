@@ -275,3 +275,30 @@ def test_cpp_host_cli_writes_a_model_directory_without_a_gpu(tmp_path):
     assert set(sd) == set(expect)
     for k in ("tok_embeddings.weight", "layers.1.feed_forward.w2.weight", "norm.weight"):
         assert np.array_equal(bits(sd[k]), expect[k])
+
+
+@pytest.mark.skipif(os.environ.get("LNB_SLOW_TESTS") != "1", reason="writes a 5 GiB file; set LNB_SLOW_TESTS=1")
+def test_archive_beyond_4gib_uses_real_zip64_offsets(tmp_path):
+    """five 1 GiB tensors: local-header offsets pass 4 GiB, so the central directory carries zip64 extras and the
+    zip64 end records are mandatory -- the shape of the 16 GB consolidated.00.pth.  torch.load(mmap=True) and the
+    native reader must both return the data (last verified by hand: 5.0 GiB, identical)."""
+    p = str(tmp_path / "big.pth")
+    base = np.random.default_rng(0).integers(0, 65536, size=(1 << 27), dtype=np.uint16)
+
+    def block(i):
+        return np.concatenate([np.roll(base, i * 4 + j) for j in range(4)]).reshape(16384, 32768)
+    w = TorchModelWriter(p)
+    for i in range(5):
+        w.Add(f"layers.{i}.big.weight", block(i))
+    w.Add("tail.weight", np.arange(10, dtype=np.uint16))
+    w.Finish()
+    assert os.path.getsize(p) > 5 * 2**30
+    sd = torch.load(p, weights_only=True, mmap=True)
+    with TorchModelReader(p) as r:
+        ts = r.Load()
+        assert ts["tail.weight"].file_offset > 5 * 2**30
+        for i in range(5):
+            exp = block(i)
+            assert np.array_equal(sd[f"layers.{i}.big.weight"].view(torch.uint16).numpy(), exp)
+            assert np.array_equal(ts[f"layers.{i}.big.weight"].RawData, exp)
+        assert np.array_equal(ts["tail.weight"].RawData, np.arange(10, dtype=np.uint16))
