@@ -77,6 +77,25 @@ def main():
     out["pow2_arange_3_8"] = {"source": "src/ml/operations_test.go:%d (TestPow, case 1)" % line, "expected": literal(body, "expected")}
     line, body = func_body(ops, "TestMean3dKeepDimTrue")   # createTestInputTensor([5,4,3]) = 1, 2, 3, ... ; mean over the last dim
     out["mean_5x4x3_keepdim"] = {"source": "src/ml/operations_test.go:%d (TestMean3dKeepDimTrue)" % line, "expected": literal(body, "expected")}
+    # weight-dependent goldens (usable only with the real Meta-Llama-3.1-8B-Instruct checkpoint)
+    sim = read("src/model/llamatransformer_simulated_test.go")
+    line, body = func_body(sim, "testSimulatedInternal")
+    body_nc = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    m = re.search(r"promptTokens := \[\]TokenId\{([^}]*)\}", body_nc)
+    prompt = [int(x) for x in re.findall(r"\d+", m.group(1))]
+    m = re.search(r"expectedOutputTokenIds := \[\]TokenId\{([^}]*)\}", body_nc)
+    toks = [int(x) for x in re.findall(r"\d+", m.group(1))]
+    m = re.search(r"expectedLogitsOnlyFirstLayer := \[\]\[\]float32\{(.*?)\n\t\t\t\}", body_nc, re.S)
+    rows = [[float(x) for x in re.findall(NUM, r)] for r in re.findall(r"\{([^{}]*)\}", m.group(1))]
+    assert len(prompt) == 15 and len(toks) == 5 and len(rows) == 6 and all(len(r) == 6 for r in rows)
+    m = re.search(r"inferenceArgs\.SequenceLength = (\d+)", body_nc)
+    out["simulated_only_first_layer"] = {
+        "source": "src/model/llamatransformer_simulated_test.go:%d (testSimulatedInternal, onlyFirstLayer=true)" % line,
+        "needs": "models-original/Meta-Llama-3.1-8B-Instruct (not available offline)",
+        "prompt_text": "<|begin_of_text|><|start_header_id|>user<|end_header_id|>\n\nWhat is your name?<|eot_id|><|start_header_id|>assistant<|end_header_id|>\n\n",
+        "prompt_tokens": prompt, "sequence_length": int(m.group(1)), "expected_output_tokens": toks,
+        "logits_rows": [0, 1, 2, 12, 13, 14], "logits_first3_last3": rows,
+        "logits_tolerance": "30 * common.THRESHOLD_BF16 = 0.3 (PyTorch round-to-nearest vs Go truncation)"}
     thr = read("src/common/utils.go")
     m = re.search(r"THRESHOLD_F32\s*=\s*(%s)" % NUM, thr)
     out["threshold_f32"] = {"source": "src/common/utils.go:%d" % (thr.count("\n", 0, m.start()) + 1), "value": float(m.group(1))}
