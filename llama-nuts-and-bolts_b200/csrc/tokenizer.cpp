@@ -5,6 +5,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstring>
+#include <queue>
 
 #include "unicode_tables.hpp"
 
@@ -236,29 +237,45 @@ int32_t Vocab::id_of(const std::string& token) const {
 // ---------------------------------------------------------------------------------------------
 // byte pair merge: repeatedly fuse the adjacent pair of parts whose concatenation has the lowest rank
 // (leftmost on ties) until no adjacent pair is a token.  Works on BYTES like tiktoken and the reference.
+// Same result as the reference's quadratic scan (tokenize.go:109-173), found with a heap in O(n log n) so that a
+// pathological piece (a 100 KB "word") cannot stall the caller.
 void Vocab::byte_pair_merge(const std::string& piece, std::vector<int32_t>& out) const {
   const int n = (int)piece.size();
   auto rank_of = [&](int a, int b) -> int {   // rank of bytes [a, b) or INT_MAX
     auto it = token_to_id.find(piece.substr((size_t)a, (size_t)(b - a)));
     return it == token_to_id.end() ? INT_MAX : it->second;
   };
-  std::vector<int> start(n + 1);              // part i = [start[i], start[i+1])
-  for (int i = 0; i <= n; i++) start[i] = i;
-  std::vector<int> pair_rank;                 // rank of part i fused with part i+1
-  for (int i = 0; i + 2 <= n; i++) pair_rank.push_back(rank_of(i, i + 2));
-  for (;;) {
-    int best = INT_MAX, at = -1;
-    for (int i = 0; i < (int)pair_rank.size(); i++)
-      if (pair_rank[i] < best) { best = pair_rank[i]; at = i; }
-    if (at < 0) break;
-    start.erase(start.begin() + at + 1);      // parts at and at+1 become one
-    pair_rank.erase(pair_rank.begin() + at);
-    const int parts = (int)start.size() - 1;
-    if (at < parts - 1) pair_rank[at] = rank_of(start[at], start[at + 2]);
-    if (at > 0) pair_rank[at - 1] = rank_of(start[at - 1], start[at + 1]);
+  // parts as a linked list over their start offsets: part i = [i, end[i]); nxt/prv = neighbouring starts (-1 = none)
+  std::vector<int> end(n), nxt(n), prv(n);
+  std::vector<char> alive(n, 1);
+  for (int i = 0; i < n; i++) { end[i] = i + 1; nxt[i] = i + 1 < n ? i + 1 : -1; prv[i] = i - 1; }
+  struct Cand {
+    int rank, start, span;                     // span = end of the right part at push time: stale entries are skipped
+    bool operator>(const Cand& o) const { return rank != o.rank ? rank > o.rank : start > o.start; }
+  };
+  std::priority_queue<Cand, std::vector<Cand>, std::greater<Cand>> heap;
+  auto push = [&](int i) {
+    if (i < 0 || nxt[i] < 0) return;
+    const int r = rank_of(i, end[nxt[i]]);
+    if (r != INT_MAX) heap.push(Cand{r, i, end[nxt[i]]});
+  };
+  for (int i = 0; i + 1 < n; i++) push(i);
+  while (!heap.empty()) {
+    const Cand c = heap.top();
+    heap.pop();
+    const int i = c.start;
+    if (!alive[i] || nxt[i] < 0 || end[nxt[i]] != c.span || end[i] >= c.span) continue;   // one side changed since the push
+    const int j = nxt[i];
+    if (rank_of(i, end[j]) != c.rank) continue;
+    alive[j] = 0;                                // fuse part j into part i
+    end[i] = end[j];
+    nxt[i] = nxt[j];
+    if (nxt[i] >= 0) prv[nxt[i]] = i;
+    push(prv[i]);
+    push(i);
   }
-  for (size_t i = 0; i + 1 < start.size(); i++) {
-    auto it = token_to_id.find(piece.substr((size_t)start[i], (size_t)(start[i + 1] - start[i])));
+  for (int i = 0; i >= 0 && i < n; i = nxt[i]) {
+    auto it = token_to_id.find(piece.substr((size_t)i, (size_t)(end[i] - i)));
     out.push_back(it == token_to_id.end() ? 0 : it->second);   // Go's map zero value (tokenize.go:169)
   }
 }
