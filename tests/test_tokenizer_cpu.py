@@ -210,3 +210,24 @@ def test_cpp_host_tokenizer_equals_the_python_mirror(vocab, tmp_path):
     ids = [int(t) for t in out.stdout.splitlines()[0].split()[1:]]
     assert ids == v.Tokenize([PromptPart("user", text)])
     assert out.stdout.split("text: ", 1)[1].removesuffix("\n") == v.TokenBatchToString(ids)
+
+
+def test_bpe_with_adversarial_rank_order_equals_tiktoken(tmp_path):
+    """overlapping merges over a 3-letter alphabet in random rank order: the heap-based merge must pick the same pairs
+    as tiktoken's scan (lowest rank, leftmost on ties), also on a 200 KB single piece"""
+    rnd = random.Random(1)
+    ranks = {bytes([b]): b for b in range(256)}
+    while len(ranks) < 256 + 400:
+        t = bytes(rnd.choice(b"abc") for _ in range(rnd.randrange(2, 7)))
+        ranks.setdefault(t, len(ranks))
+    path = str(tmp_path / "abc.model")
+    write_model(path, ranks)
+    v = Load(path)
+    enc = tiktoken.Encoding("abc", pat_str=r"[abc]+|[^abc]+", mergeable_ranks=ranks, special_tokens={})
+    for _ in range(300):
+        t = "".join(rnd.choice("abc") for _ in range(rnd.randrange(1, 80)))
+        assert v.TokenizeString(t) == enc.encode_ordinary(t), t
+    big = "".join(rnd.choice("abc") for _ in range(200_000))
+    ids = v.TokenizeString(big)
+    assert v.TokenBatchToBytes(ids) == big.encode() and ids == enc.encode_ordinary(big)
+    v.close()
