@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lnb.h"
@@ -603,10 +604,8 @@ extern "C" int lnb_synth_spec(const lnb_model_args* args, const char* name, floa
   synth_spec_kind(*args, kind, scale, offset);
   return 0;
 }
-extern "C" int lnb_synth_fill_host(uint64_t seed, const char* name, float scale, float offset, int64_t n, uint16_t* out) {
-  if (!name || !out) return fail(LNB_EINVAL, "NULL argument");
-  const uint64_t s = seed ^ fnv1a64(name);
-  for (int64_t i = 0; i < n; i++) {
+static void synth_fill_range(uint64_t s, float scale, float offset, int64_t i0, int64_t i1, uint16_t* out) {
+  for (int64_t i = i0; i < i1; i++) {
     uint64_t z = s + ((uint64_t)i + 1) * 0x9E3779B97F4A7C15ULL;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
@@ -620,9 +619,26 @@ extern "C" int lnb_synth_fill_host(uint64_t seed, const char* name, float scale,
     memcpy(&b, &vv, 4);
     out[i] = (uint16_t)(b >> 16);
   }
+}
+extern "C" int lnb_synth_fill_host(uint64_t seed, const char* name, float scale, float offset, int64_t n, uint16_t* out) {
+  if (!name || !out) return fail(LNB_EINVAL, "NULL argument");
+  const uint64_t s = seed ^ fnv1a64(name);
+  // counter-based generator: ranges are independent, so large tensors are filled by a few threads
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nt = (n < (1 << 20)) ? 1 : (int)std::min<unsigned>(16u, hw ? hw : 1u);
+  if (nt <= 1) {
+    synth_fill_range(s, scale, offset, 0, n, out);
+    return 0;
+  }
+  std::vector<std::thread> th;
+  const int64_t step = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; t++) {
+    const int64_t a = (int64_t)t * step, b = std::min<int64_t>(n, a + step);
+    if (a < b) th.emplace_back(synth_fill_range, s, scale, offset, a, b, out);
+  }
+  for (auto& x : th) x.join();
   return 0;
 }
-
 extern "C" int lnb_model_init_synthetic(lnb_model* m, uint64_t seed) {
   if (!m) return fail(LNB_EINVAL, "model is NULL");
   if (m->finalized) return fail(LNB_ESTATE, "model is finalized");
