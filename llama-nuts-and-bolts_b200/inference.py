@@ -53,6 +53,40 @@ class InferenceEngine:
     def TokenBatchToString(self, tokenIdBatch):      # :239-258
         return self._vocab().TokenBatchToString(tokenIdBatch)
 
+    # --- text streaming (generateStringInternal, inference.go:91-170) ------------------------------------------
+    def GenerateString(self, promptTokens, **kw):
+        """GenerateString (inference.go:56-58): GeneratedPart stream for the tokens the model generates"""
+        return self.GenerateStringGeneric(self.GenerateTokens(promptTokens, **kw))
+
+    def GenerateStringFromOutputTokens(self, outputTokens):
+        """GenerateStringFromOutputTokens (inference.go:60-69): replays given ids through the detokenizer (the
+        reference's own tests drive the streaming decoder this way)"""
+        return self.GenerateStringGeneric((GSInProgress, int(t)) for t in outputTokens)
+
+    def GenerateStringGeneric(self, tokenStream):
+        """yields dict(DecodedString, TokenId, AddedToWaiting, IsResendOfWaiting, GenerationState) per token.  Tokens
+        that end inside a UTF-8 sequence are reported with AddedToWaiting and, if the stream ends before they
+        complete, re-sent at the end with their raw bytes (IsResendOfWaiting), the last one carrying the final
+        state -- inference.go:104-170.  WaitingRunesExtraStr (emoji alias annotation) is not produced."""
+        from .vocabulary import GenerationDecodingContext
+        vocab = self._vocab()
+        ctx = GenerationDecodingContext()
+        waiting, last_state = [], GSInProgress
+        for state, tok in tokenStream:
+            text, added = vocab.TokenToString(tok, ctx)
+            part = dict(DecodedString=text, TokenId=tok, AddedToWaiting=added, IsResendOfWaiting=False, GenerationState=GSInProgress)
+            if state != GSInProgress and not waiting:
+                part["GenerationState"] = state
+            last_state = state
+            if added:
+                waiting.append(part)
+            elif waiting:
+                waiting = []
+            yield part
+        for i, w in enumerate(waiting):
+            yield dict(DecodedString=vocab.IdToToken(w["TokenId"]).decode("utf-8", "replace"), TokenId=w["TokenId"], AddedToWaiting=False,
+                       IsResendOfWaiting=True, GenerationState=last_state if i + 1 == len(waiting) else GSInProgress)
+
     def GenerateTokens(self, promptTokens, use_reference_api: bool = False, step_times: list | None = None):
         """Generator over (state, token id) exactly like generatedTokensCh.
 

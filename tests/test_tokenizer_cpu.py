@@ -231,3 +231,37 @@ def test_bpe_with_adversarial_rank_order_equals_tiktoken(tmp_path):
     ids = v.TokenizeString(big)
     assert v.TokenBatchToBytes(ids) == big.encode() and ids == enc.encode_ordinary(big)
     v.close()
+
+
+def test_generate_string_streams_text_like_generate_string_internal(tmp_path):
+    """InferenceEngine.GenerateStringFromOutputTokens (the reference's tests drive the streaming decoder with it,
+    cmd/main_test.go:70-93): parts in order, waiting flags for split UTF-8, resend of an unfinished tail"""
+    ranks = {bytes([b]): b for b in range(256)}
+    ranks[b"ab"] = 256
+    path = str(tmp_path / "bytes.model")
+    write_model(path, ranks)
+    v = Load(path)
+
+    class FakeModel:            # the engine only needs model.Vocabulary here
+        Vocabulary = v
+        Transformer = None
+    eng = L.inference.InferenceEngine(FakeModel, L.model.InferenceArgs(16))
+    flag = "🇹".encode()        # F0 9F 87 B9 arrives as four byte tokens
+    ids = [256] + list(flag) + [ord("!")]
+    parts = list(eng.GenerateStringFromOutputTokens(ids))
+    assert [p["DecodedString"] for p in parts] == ["ab", "", "", "", "🇹", "!"]
+    assert [p["AddedToWaiting"] for p in parts] == [False, True, True, True, False, False]
+    assert all(p["GenerationState"] == L.inference.GSInProgress and not p["IsResendOfWaiting"] for p in parts)
+    # the stream ends inside a character: the held-back tokens are re-sent, the last one carries the final state
+    stream = [(L.inference.GSInProgress, ord("x")), (L.inference.GSInProgress, flag[0]), (L.inference.GSFinishedByReachingSeqLen, flag[1])]
+    parts = list(eng.GenerateStringGeneric(stream))
+    assert [(p["AddedToWaiting"], p["IsResendOfWaiting"]) for p in parts] == [(False, False), (True, False), (True, False), (False, True), (False, True)]
+    assert [p["GenerationState"] for p in parts] == [L.inference.GSInProgress] * 4 + [L.inference.GSFinishedByReachingSeqLen]
+    assert [p["TokenId"] for p in parts[3:]] == [flag[0], flag[1]]
+    # a finished state on a complete token is reported immediately
+    parts = list(eng.GenerateStringGeneric([(L.inference.GSFinishedByReachingEOS, ord("z"))]))
+    assert parts == [dict(DecodedString="z", TokenId=ord("z"), AddedToWaiting=False, IsResendOfWaiting=False,
+                          GenerationState=L.inference.GSFinishedByReachingEOS)]
+    with pytest.raises(L.ml.MlError):
+        L.inference.InferenceEngine(type("M", (), {"Vocabulary": L.model.Vocabulary(), "Transformer": None}), L.model.InferenceArgs(16)).Tokenize([])
+    v.close()
