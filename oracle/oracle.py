@@ -351,3 +351,48 @@ class OracleSession:
         v = np.ctypeslib.as_array(lib().orc_session_cache_v(self.h, layer), shape=(n,))
         shp = (self.seq_len, a.n_kv_heads, a.head_dim)
         return k.reshape(shp), v.reshape(shp)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Building blocks of the RoPE table and the causal mask (init-time ops of src/ml), restated in NumPy.  The C
+# oracle computes precomputeFreqsCis in one piece (orc_rope_table); these blocks are pinned to the reference's own
+# literals (TestARange*, TestOuter, TestPolar, TestTriangularUpper*) and then composed the way
+# precomputeFreqsCis composes them (src/model/llamatransformer.go:694-751) to cross-check the C table bit for bit.
+
+def arange_bf16(start: int, end: int, step: int) -> np.ndarray:
+    """ml.ARange(start, end, step, DT_BF16) (src/ml/operations_impl.go:11-24): float32(val) truncated to bf16"""
+    if start >= end:
+        raise ValueError(f"start value {start} must be less than end value {end} in ARange")
+    return bf16_bits(np.arange(start, end, step, dtype=np.int64).astype(np.float32))
+
+
+def outer_bf16(vec1: np.ndarray, vec2: np.ndarray) -> np.ndarray:
+    """ml.Outer for BF16 vectors (operations_impl.go:26-52): float32 product, truncated to bf16"""
+    a, b = bf16_to_f32(vec1), bf16_to_f32(vec2)
+    return bf16_bits((a[:, None] * b[None, :]).astype(np.float32))
+
+
+def polar(abs_f32: np.ndarray, angle_f32: np.ndarray) -> np.ndarray:
+    """ml.Polar (operations_impl.go:100-140): complex64(complex(abs * cos(angle), abs * sin(angle))) in float64"""
+    a, t = np.asarray(abs_f32, np.float64), np.asarray(angle_f32, np.float64)
+    return ((a * np.cos(t)) + 1j * (a * np.sin(t))).astype(np.complex64)
+
+
+def full_f32(size, value) -> np.ndarray:
+    """ml.Full(size, DT_F32, value) (operations_impl.go:55-64)"""
+    return np.full(size, np.float32(value), np.float32)
+
+
+def triangular_upper(x: np.ndarray, diagonal: int) -> np.ndarray:
+    """ml.TriangularUpper (operations_impl.go:175-195): keeps x[i, j] where j - i >= diagonal, zero elsewhere"""
+    i, j = np.indices(x.shape)
+    return np.where(j - i >= diagonal, x, np.zeros_like(x))
+
+
+def rope_table_from_blocks(dim: int, end: int, theta: float, inv_freqs_bf16: np.ndarray) -> np.ndarray:
+    """the tail of precomputeFreqsCis (llamatransformer.go:728-750): t = ARange(0, end) in bf16, Outer(t, freqs) in
+    bf16, Polar(ones, .) -> [end, dim/2] complex64, returned as [end, dim/2, 2] float32 (cos, sin)"""
+    t = arange_bf16(0, end, 1)
+    ang = outer_bf16(t, inv_freqs_bf16)
+    c = polar(np.ones(ang.shape, np.float32), bf16_to_f32(ang))
+    return np.stack([c.real, c.imag], -1).astype(np.float32)

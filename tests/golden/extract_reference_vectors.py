@@ -77,6 +77,41 @@ def main():
     out["pow2_arange_3_8"] = {"source": "src/ml/operations_test.go:%d (TestPow, case 1)" % line, "expected": literal(body, "expected")}
     line, body = func_body(ops, "TestMean3dKeepDimTrue")   # createTestInputTensor([5,4,3]) = 1, 2, 3, ... ; mean over the last dim
     out["mean_5x4x3_keepdim"] = {"source": "src/ml/operations_test.go:%d (TestMean3dKeepDimTrue)" % line, "expected": literal(body, "expected")}
+    # building blocks of the RoPE table and the causal mask (operations_test.go:56-587)
+    cases = []
+    for fn in ("TestARangeStep1BF16", "TestARangeMultipleCasesBF16"):
+        line, body = func_body(ops, fn)
+        exps = re.findall(r"expected\s*:?=\s*\[\]float32\{([^}]*)\}", body)
+        calls = re.findall(r"ARange\((-?\d+),\s*(-?\d+),\s*(-?\d+),\s*DT_BF16\)", body)
+        assert len(exps) == len(calls) and exps, fn
+        for e, c in zip(exps, calls):
+            cases.append({"args": [int(x) for x in c], "expected": [float(x) for x in re.findall(NUM, e)],
+                          "source": "src/ml/operations_test.go:%d (%s)" % (line, fn)})
+    out["arange_bf16"] = cases
+    line, body = func_body(ops, "TestOuter")
+    calls = re.findall(r"ARange\((-?\d+),\s*(-?\d+),\s*(-?\d+),\s*DT_BF16\)", body)
+    out["outer_bf16"] = {"source": "src/ml/operations_test.go:%d (TestOuter)" % line, "vec1_arange": [int(x) for x in calls[0]],
+                         "vec2_arange": [int(x) for x in calls[1]], "expected": literal(body, "expected")}
+    line, body = func_body(ops, "TestPolar")
+    exp = [[float(a), float(b)] for a, b in re.findall(r"complex64\(complex\((%s),\s*(%s)\)\)" % (NUM, NUM), body)]
+    absv = [float(x) for x in re.findall(r"abs\.SetItem\(\[\]int\{0, \d\}, float32\((%s)\)\)" % NUM, body)]
+    ang = re.findall(r"angle\.SetItem\(\[\]int\{0, \d\}, float32\(([^)]*)\)\)", body)
+    assert len(exp) == 5 and len(absv) == 5 and len(ang) == 5
+    out["polar"] = {"source": "src/ml/operations_test.go:%d (TestPolar)" % line, "abs": absv, "angle_expr": ang, "expected_re_im": exp}
+    triu = []
+    for fn in ("TestTriangularUpperOnSquare", "TestTriangularUpperOnLandscapeRectangle", "TestTriangularUpperOnPortraitRectangle"):
+        line, body = func_body(ops, fn)
+        m = re.search(r"Full\(\[\]int\{(\d+), (\d+)\}, DT_F32, float32\((%s)\)\)" % NUM, body)
+        size, fill = [int(m.group(1)), int(m.group(2))], float(m.group(3))
+        exps = [m2.group(1) for m2 in re.finditer(r"expected\s*:?=\s*\[\]\[\]float32(\{(?:[^{}]|\{[^{}]*\})*\})", body)]
+        diags = [int(x) for x in re.findall(r"TriangularUpper\(originalInput,\s*(-?\d+)\)", body)]
+        assert len(exps) == len(diags) and exps, fn
+        for e, dg in zip(exps, diags):
+            rows = [[float(x) for x in re.findall(NUM, r)] for r in re.findall(r"\{([^{}]*)\}", e)]
+            assert len(rows) == size[0] and all(len(r) == size[1] for r in rows), (fn, dg)
+            triu.append({"size": size, "fill": fill, "diagonal": dg, "expected": rows, "source": "src/ml/operations_test.go:%d (%s)" % (line, fn)})
+    out["triangular_upper"] = triu
+
     # weight-dependent goldens (usable only with the real Meta-Llama-3.1-8B-Instruct checkpoint)
     sim = read("src/model/llamatransformer_simulated_test.go")
     line, body = func_body(sim, "testSimulatedInternal")

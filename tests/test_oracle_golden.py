@@ -211,3 +211,48 @@ def test_committed_fixture_is_what_the_reference_sources_say(tmp_path):
     script.write_text(src)
     subprocess.check_call([sys.executable, str(script)])
     assert json.load(open(tmp_path / "v.json")) == GOLD
+
+
+# ---- building blocks of the RoPE table and the mask: the reference's own literals (operations_test.go:56-587) ----
+
+@pytest.mark.parametrize("case", GOLD["arange_bf16"], ids=lambda c: "arange" + str(c["args"]))
+def test_arange_bf16_golden(case):
+    got = f(O.arange_bf16(*case["args"]))
+    assert got.shape == (len(case["expected"]),) and np.array_equal(got, np.array(case["expected"], np.float32))
+    with pytest.raises(ValueError):
+        O.arange_bf16(3, 3, 1)                                       # "start value must be less than end value"
+
+
+def test_outer_bf16_golden():
+    g = GOLD["outer_bf16"]
+    got = f(O.outer_bf16(O.arange_bf16(*g["vec1_arange"]), O.arange_bf16(*g["vec2_arange"])))
+    assert np.array_equal(got, np.array(g["expected"], np.float32))
+
+
+def test_polar_golden():
+    g = GOLD["polar"]
+    angle = np.array([eval(e.replace("math.Pi", "math.pi"), {"math": math}) for e in g["angle_expr"]], np.float32)   # float32(math.Pi/2), ...
+    got = O.polar(np.array([g["abs"]], np.float32), angle[None, :])
+    exp = np.array([[complex(a, b) for a, b in g["expected_re_im"]]], np.complex64)
+    assert got.shape == (1, 5) and got.dtype == np.complex64
+    assert np.abs(got - exp).max() <= THRESHOLD_F32
+
+
+@pytest.mark.parametrize("case", GOLD["triangular_upper"], ids=lambda c: "triu%sx%s_d%s" % (c["size"][0], c["size"][1], c["diagonal"]))
+def test_triangular_upper_golden(case):
+    got = O.triangular_upper(O.full_f32(case["size"], case["fill"]), case["diagonal"])
+    assert np.array_equal(got, np.array(case["expected"], np.float32))
+
+
+def test_c_rope_table_equals_the_composition_of_the_pinned_blocks():
+    """precomputeFreqsCis (llamatransformer.go:694-751) = ARange -> pow -> scaling -> Outer -> Polar.  The C oracle
+    computes it in one function; composing the NumPy blocks above (each pinned to the reference's literals) from the
+    C oracle's inverse frequencies must give the same table bit for bit, for every position and frequency."""
+    for dim, end, theta, scaled in ((128, 4096, 500000.0, True), (128, 300, 500000.0, False), (32, 128, 10000.0, True)):
+        freqs, cis = O.rope_table(dim, end, theta, scaled)
+        assert np.array_equal(cis, O.rope_table_from_blocks(dim, end, theta, freqs))
+    # and the unscaled inverse frequencies themselves: ARange(0, dim, 2) -> float32(1 / theta^(val / dim)) -> bf16
+    freqs, _ = O.rope_table(128, 8, 500000.0, False)
+    val = f(O.arange_bf16(0, 128, 2))
+    exp = bf((1.0 / np.power(500000.0, (val / np.float32(128)).astype(np.float64))).astype(np.float32))
+    assert np.array_equal(freqs, exp)
