@@ -238,3 +238,66 @@ def Fwd_Get_Rows(embedding: Tensor, tokens: Tensor) -> Tensor:  # operations_imp
 
 def Full(size, dtype: DataType, fill_value) -> Tensor:  # operations_impl.go:55-64
     return Tensor(np.full(size, fill_value, dtype.np_dtype), dtype)
+
+
+# ---- init-time builders (host-side in the reference as well: they only run inside precomputeFreqsCis / prepare,
+# src/model/llamatransformer.go:115-143,694-751) ---------------------------------------------------------------
+
+def _fill_value(dtype: DataType, v: float):
+    if dtype is DT_BF16:
+        return int(f32_to_bf16_bits(np.float32(v)).reshape(-1)[0])
+    if dtype is DT_F32:
+        return np.float32(v)
+    raise MlError(f"unsupported tensor datatype {dtype}")
+
+
+def Zeros(size, dtype: DataType) -> Tensor:  # operations_impl.go:66-77
+    return Full(size, dtype, _fill_value(dtype, 0.0))
+
+
+def Ones(size, dtype: DataType) -> Tensor:  # operations_impl.go:79-90
+    return Full(size, dtype, _fill_value(dtype, 1.0))
+
+
+def ZerosLike(input: Tensor) -> Tensor:  # :92-94
+    return Zeros(input.Size, input.DataType)
+
+
+def OnesLike(input: Tensor) -> Tensor:  # :96-98
+    return Ones(input.Size, input.DataType)
+
+
+def ARange(start: int, end: int, step: int, dtype: DataType) -> Tensor:  # operations_impl.go:11-24
+    if start >= end:
+        raise MlError(f"start value {start} must be less than end value {end} in ARange")
+    vals = np.arange(start, end, step, dtype=np.int64).astype(np.float32)   # SetItem_FromFloat32(float32(val))
+    if dtype is DT_BF16:
+        return Tensor(f32_to_bf16_bits(vals), DT_BF16)
+    if dtype is DT_F32:
+        return Tensor(vals, DT_F32)
+    raise MlError(f"unsupported tensor datatype {dtype}")
+
+
+def Outer(vec1: Tensor, vec2: Tensor) -> Tensor:  # operations_impl.go:26-52
+    if vec1.RawData.ndim != 1 or vec2.RawData.ndim != 1:
+        raise MlError("tensor must be a vector")                     # checkIsVector
+    _same_dtype(vec1, vec2)
+    prod = (vec1.to_f32_array()[:, None] * vec2.to_f32_array()[None, :]).astype(np.float32)   # valF32 := row * col
+    return Tensor.from_f32(prod, vec1.DataType)
+
+
+def Polar(abs: Tensor, angle: Tensor) -> Tensor:  # operations_impl.go:100-140
+    if abs.Size != angle.Size:
+        raise MlError(f"tensors are not in same shape: {abs.Size} and {angle.Size}")
+    _same_dtype(abs, angle)
+    if abs.RawData.ndim != 2:
+        raise MlError("tensor must be a matrix")                     # "Currently only 2D matrices are supported"
+    a, t = abs.to_f32_array().astype(np.float64), angle.to_f32_array().astype(np.float64)
+    return Tensor(((a * np.cos(t)) + 1j * (a * np.sin(t))).astype(np.complex64), DT_COMPLEX)
+
+
+def TriangularUpper(input: Tensor, diagonal: int) -> Tensor:  # operations_impl.go:175-195
+    if input.RawData.ndim != 2:
+        raise MlError("tensor must be a matrix")
+    i, j = np.indices(input.RawData.shape)
+    return Tensor(np.where(j - i >= diagonal, input.RawData, np.zeros_like(input.RawData)), input.DataType)

@@ -309,3 +309,37 @@ def LoadModel(modelDir: str, device: int = 0, tp_rank: int = 0, tp_size: int = 1
         m.Free()
         raise
     return m
+
+
+def applyScaling(freqs: ml.Tensor) -> ml.Tensor:
+    """applyScaling (src/model/llamatransformer.go:662-692): the Llama-3.1 inverse-frequency remap, evaluated in
+    float32 per element on a bf16 vector"""
+    scaleFactor, lowFreqFactor, highFreqFactor, oldContextLen = np.float32(8), np.float32(1), np.float32(4), np.float32(8192)
+    lowFreqWavelen, highFreqWavelen = oldContextLen / lowFreqFactor, oldContextLen / highFreqFactor
+    twoPi = np.float32(2.0 * np.pi)
+    out = []
+    for freq in freqs.to_f32_array():
+        freq = np.float32(freq)
+        wavelen = twoPi / freq
+        if wavelen < highFreqWavelen:
+            new = freq
+        elif wavelen > lowFreqWavelen:
+            new = freq / scaleFactor
+        else:
+            smooth = (oldContextLen / wavelen - lowFreqFactor) / (highFreqFactor - lowFreqFactor)
+            new = np.float32((np.float32(1) - smooth) * freq) / scaleFactor + np.float32(smooth * freq)
+        out.append(np.float32(new))
+    return ml.Tensor.from_f32(np.array(out, np.float32), ml.DT_BF16)
+
+
+def precomputeFreqsCis(dim: int, end: int, theta: float, useScaled: bool) -> ml.Tensor:
+    """precomputeFreqsCis (llamatransformer.go:694-751) from the ml builders, exactly as the Go host does it; the
+    result ([end, dim/2] complex64) can be handed to lnb_model_set_rope_table, which otherwise builds the same bits"""
+    freqs = ml.ARange(0, dim, 2, ml.DT_BF16)
+    val = freqs.to_f32_array()
+    freqs = ml.Tensor.from_f32((1.0 / np.power(theta, (val / np.float32(dim)).astype(np.float64))).astype(np.float32), ml.DT_BF16)
+    t = ml.ARange(0, end, 1, ml.DT_BF16)
+    if useScaled:
+        freqs = applyScaling(freqs)
+    freqs = ml.Outer(t, freqs)
+    return ml.Polar(ml.OnesLike(freqs), freqs)

@@ -158,3 +158,33 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu():
         pytest.skip("a GPU is present")
     out = subprocess.run([exe, "16", "strict", "tiny"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "lnb:" in out.stderr          # no CPU fallback
+
+
+def test_ml_builders_match_the_reference_literals_and_build_the_rope_table():
+    """ml.ARange / Outer / Polar / Ones / TriangularUpper of the host mirror against tests/golden (the reference's own
+    test literals), and model.precomputeFreqsCis composed from them against the oracle's table, bit for bit"""
+    import math
+    from tests.helpers import reference_vectors
+    g = reference_vectors()
+    ml = L.ml
+    for c in g["arange_bf16"]:
+        t = ml.ARange(*c["args"], ml.DT_BF16)
+        assert t.Size == [len(c["expected"])] and np.array_equal(t.to_f32_array(), np.array(c["expected"], np.float32))
+    with pytest.raises(ml.MlError, match="must be less than end value"):
+        ml.ARange(5, 5, 1, ml.DT_BF16)
+    o = g["outer_bf16"]
+    got = ml.Outer(ml.ARange(*o["vec1_arange"], ml.DT_BF16), ml.ARange(*o["vec2_arange"], ml.DT_BF16))
+    assert got.Size == [4, 3] and np.array_equal(got.to_f32_array(), np.array(o["expected"], np.float32))
+    p = g["polar"]
+    angle = np.array([[eval(e.replace("math.Pi", "math.pi"), {"math": math}) for e in p["angle_expr"]]], np.float32)
+    got = ml.Polar(ml.Tensor(np.array([p["abs"]], np.float32), ml.DT_F32), ml.Tensor(angle, ml.DT_F32))
+    assert got.DataType is ml.DT_COMPLEX and np.abs(got.RawData - np.array([[complex(a, b) for a, b in p["expected_re_im"]]])).max() <= 1e-3
+    for c in g["triangular_upper"]:
+        got = ml.TriangularUpper(ml.Full(c["size"], ml.DT_F32, np.float32(c["fill"])), c["diagonal"])
+        assert np.array_equal(got.RawData, np.array(c["expected"], np.float32))
+    assert ml.OnesLike(ml.Zeros([2, 3], ml.DT_BF16)).to_f32_array().tolist() == [[1.0] * 3] * 2
+    for dim, end, theta, scaled in ((128, 512, 500000.0, True), (32, 128, 500000.0, True), (64, 64, 10000.0, False)):
+        cis = L.model.precomputeFreqsCis(dim, end, theta, scaled)
+        _, exp = O.rope_table(dim, end, theta, scaled)
+        assert cis.Size == [end, dim // 2]
+        assert np.array_equal(np.stack([cis.RawData.real, cis.RawData.imag], -1), exp)
