@@ -106,6 +106,35 @@ class Tensor:
                 idx.append(slice(a, b))
         return Tensor(np.ascontiguousarray(self.RawData[tuple(idx)]), self.DataType, self.Name)
 
+    def SetSlice(self, loc_start, loc_end, val: "Tensor") -> None:
+        """tensor.go:345-384: writes `val` over the region Slice(loc_start, loc_end) would return (same leading-index
+        rule); sizes and data types must agree"""
+        if val.DataType is not self.DataType:
+            raise MlError("tensors are not in same data type")
+        if len(loc_start) != len(loc_end) or len(loc_start) == 0 or len(loc_start) > self.RawData.ndim:
+            raise MlError("incompatible locStart, locEnd values and tensor")
+        idx, leading = [], True
+        for d, (a, b) in enumerate(zip(loc_start, loc_end)):
+            n = self.RawData.shape[d]
+            if a < 0 or a > n or b < 0 or b > n or b - a < 0:
+                raise MlError("incompatible locStart, locEnd values and tensor")
+            if leading and a == b and d < self.RawData.ndim - 1:
+                idx.append(a)
+            else:
+                leading = False
+                idx.append(slice(a, b))
+        region = self.RawData[tuple(idx)]
+        if list(region.shape) != val.Size:
+            raise MlError(f"incompatible sizes: region {list(region.shape)} and value {val.Size}")
+        region[...] = val.RawData
+
+    def Transpose(self, dim1: int, dim2: int) -> "Tensor":
+        """tensor.go:542-598: swaps two dimensions and returns a contiguous copy"""
+        nd = self.RawData.ndim
+        if not (0 <= dim1 < nd and 0 <= dim2 < nd):
+            raise MlError(f"dimensions {dim1}, {dim2} out of range for a {nd}-D tensor")
+        return Tensor(np.ascontiguousarray(np.swapaxes(self.RawData, dim1, dim2)), self.DataType, self.Name)
+
     def ToFloat32(self) -> "Tensor":  # tensor.go:430-454
         if self.DataType is DT_F32:
             return self

@@ -112,6 +112,21 @@ def main():
             triu.append({"size": size, "fill": fill, "diagonal": dg, "expected": rows, "source": "src/ml/operations_test.go:%d (%s)" % (line, fn)})
     out["triangular_upper"] = triu
 
+    # Tensor.Transpose / SetSlice (KV-cache append and the attention layout changes; src/ml/tensor_test.go)
+    tt = read("src/ml/tensor_test.go")
+    tr = []
+    for fn in ("TestTranspose_Simple", "TestTranspose_Simple_Dim1_Dim3", "TestTranspose_Large"):
+        line, body = func_body(tt, fn)
+        m = re.search(r"\.Transpose\((\d+),\s*(\d+)\)", body)
+        tr.append({"source": "src/ml/tensor_test.go:%d (%s)" % (line, fn), "dims": [int(m.group(1)), int(m.group(2))],
+                   "input": literal(body, "inputVals"), "expected": literal(body, "expected")})
+    out["transpose"] = tr
+    line, body = func_body(tt, "TestSetSlice")
+    out["set_slice"] = {"source": "src/ml/tensor_test.go:%d (TestSetSlice)" % line, "input_size": [4, 5],
+                        "note": "createTestInputTensor([4,5]) = 1..20 in bf16, written with SetSlice([1],[5]) into [10,5] and "
+                                "SetSlice([19,1],[19,5]) into [20,10,5], read back with the same Slice",
+                        "expected": literal(body, "expected")}
+
     # weight-dependent goldens (usable only with the real Meta-Llama-3.1-8B-Instruct checkpoint)
     sim = read("src/model/llamatransformer_simulated_test.go")
     line, body = func_body(sim, "testSimulatedInternal")

@@ -188,3 +188,27 @@ def test_ml_builders_match_the_reference_literals_and_build_the_rope_table():
         _, exp = O.rope_table(dim, end, theta, scaled)
         assert cis.Size == [end, dim // 2]
         assert np.array_equal(np.stack([cis.RawData.real, cis.RawData.imag], -1), exp)
+
+
+def test_tensor_transpose_and_set_slice_match_the_reference_literals():
+    """Tensor.Transpose / SetSlice / Slice of the host mirror on the reference's own cases (src/ml/tensor_test.go:171-479):
+    the layout changes of attention and the KV-cache append are exactly these on the host side of the Go path"""
+    from tests.helpers import reference_vectors
+    g = reference_vectors()
+    ml = L.ml
+    for c in g["transpose"]:
+        t = ml.Tensor(np.array(c["input"], np.float32), ml.DT_F32).Transpose(*c["dims"])
+        exp = np.array(c["expected"], np.float32)
+        assert t.Size == list(exp.shape) and np.array_equal(t.RawData, exp) and t.RawData.flags["C_CONTIGUOUS"]
+    exp = np.array(g["set_slice"]["expected"], np.float32)
+    inp = ml.Tensor.from_f32(np.arange(1, 21, dtype=np.float32).reshape(4, 5))          # createTestInputTensor([4, 5])
+    a = ml.Zeros([10, 5], ml.DT_BF16)
+    a.SetSlice([1], [5], inp)
+    assert np.array_equal(a.Slice([1], [5]).to_f32_array(), exp) and not a.RawData[0].any() and not a.RawData[5:].any()
+    b = ml.Zeros([20, 10, 5], ml.DT_BF16)
+    b.SetSlice([19, 1], [19, 5], inp)
+    assert np.array_equal(b.Slice([19, 1], [19, 5]).to_f32_array(), exp) and not b.RawData[:19].any()
+    with pytest.raises(ml.MlError):
+        a.SetSlice([1], [4], inp)
+    with pytest.raises(ml.MlError):
+        a.SetSlice([1], [5], ml.Tensor(np.zeros((4, 5), np.float32), ml.DT_F32))
