@@ -61,6 +61,20 @@ int main(int argc, char** argv) {
       return 1;
     }
   }
+  if (argc > 3 && !strcmp(argv[1], "--detok-stream")) {   // host-only: streaming TokenToString over the given ids
+    try {
+      model::Tokenizer tok(argv[2]);
+      std::string waiting, text;
+      for (int i = 3; i < argc; i++) {
+        const bool added = tok.TokenToString(atoi(argv[i]), waiting, text);
+        printf("%d %s [%s]\n", atoi(argv[i]), added ? "waiting" : "text", text.c_str());
+      }
+      return 0;
+    } catch (const std::exception& e) {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+  }
   const int seq_len = argc > 1 ? atoi(argv[1]) : 136;
   const int acc = (argc > 2 && !strcmp(argv[2], "fast")) ? LNB_ACC_FAST : LNB_ACC_STRICT;
   const bool tiny = argc > 3 && !strcmp(argv[3], "tiny");

@@ -136,6 +136,47 @@ class Tokenizer {
     out.resize((size_t)n);
     return out;
   }
+  // Vocabulary.IdToToken[id] (raw bytes; a piece need not be valid UTF-8)
+  std::string IdToToken(int32_t id) const {
+    const void* p = nullptr;
+    int n = 0;
+    check(lnb_vocab_token_bytes(h_, id, &p, &n));
+    return std::string((const char*)p, (size_t)n);
+  }
+  // TokenToString (tokenize.go:195-237) without the emoji annotation: a piece that is not valid UTF-8 on its own is
+  // collected in waitingBytes and released one rune per call once the bytes decode; returns addedToWaiting
+  bool TokenToString(int32_t id, std::string& waitingBytes, std::string& text) const {
+    const std::string piece = IdToToken(id);
+    text.clear();
+    if (Utf8Valid(piece)) { text = piece; return false; }
+    waitingBytes += piece;
+    if (!Utf8Valid(waitingBytes)) return true;
+    const size_t n = Utf8RuneLen((unsigned char)waitingBytes[0]);
+    text = waitingBytes.substr(0, n);
+    waitingBytes.erase(0, n);
+    return false;
+  }
+  static size_t Utf8RuneLen(unsigned char c) { return c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : 4; }
+  static bool Utf8Valid(const std::string& s) {   // utf8.Valid
+    for (size_t i = 0; i < s.size();) {
+      const unsigned char c = (unsigned char)s[i];
+      size_t n;
+      uint32_t cp, min;
+      if (c < 0x80) { i++; continue; }
+      if ((c & 0xe0) == 0xc0) { n = 2; cp = c & 0x1f; min = 0x80; }
+      else if ((c & 0xf0) == 0xe0) { n = 3; cp = c & 0x0f; min = 0x800; }
+      else if ((c & 0xf8) == 0xf0) { n = 4; cp = c & 0x07; min = 0x10000; }
+      else return false;
+      if (i + n > s.size()) return false;
+      for (size_t k = 1; k < n; k++) {
+        if (((unsigned char)s[i + k] & 0xc0) != 0x80) return false;
+        cp = (cp << 6) | ((unsigned char)s[i + k] & 0x3f);
+      }
+      if (cp < min || cp > 0x10ffff || (cp >= 0xd800 && cp <= 0xdfff)) return false;
+      i += n;
+    }
+    return true;
+  }
   std::string TokenBatchToString(const std::vector<int32_t>& ids) const {   // tokenize.go:239-258 (bytes; no emoji annotation)
     std::string out(64 + 128 * ids.size(), '\0');
     int64_t n = 0;

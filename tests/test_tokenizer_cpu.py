@@ -265,3 +265,26 @@ def test_generate_string_streams_text_like_generate_string_internal(tmp_path):
     with pytest.raises(L.ml.MlError):
         L.inference.InferenceEngine(type("M", (), {"Vocabulary": L.model.Vocabulary(), "Transformer": None}), L.model.InferenceArgs(16)).Tokenize([])
     v.close()
+
+
+def test_cpp_streaming_detokenizer_equals_the_python_mirror(tmp_path):
+    """model::Tokenizer::TokenToString (C++) through `lnb_generate --detok-stream`: same waiting flags and text as
+    Vocabulary.TokenToString (Python) on a character split across byte tokens"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "host"), "-s"])
+    path = str(tmp_path / "bytes.model")
+    write_model(path, {bytes([b]): b for b in range(256)})
+    v = Load(path)
+    ids = list("a🇹é!".encode())
+    out = subprocess.run([os.path.join(root, "host", "lnb_generate"), "--detok-stream", path] + [str(i) for i in ids],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    ctx = GenerationDecodingContext()
+    exp = []
+    for i in ids:
+        text, waiting = v.TokenToString(i, ctx)
+        exp.append(f"{i} {'waiting' if waiting else 'text'} [{text}]")
+    assert out.stdout.splitlines() == exp
+    v.close()
