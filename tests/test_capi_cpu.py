@@ -84,6 +84,11 @@ def test_host_generator_twin_equals_oracle_generator():
         a = L.synth.fill_host(args, name, 99)
         b = O.synth_fill(99, name, sc, off, int(np.prod(shape))).reshape(shape)
         assert np.array_equal(a, b), name
+    # tensors of a million elements and more are filled by several threads (counter-based generator): same bits
+    for n in (1_048_576, 5_000_001):
+        out = np.empty(n, np.uint16)
+        L._capi.check(L._capi.lib.lnb_synth_fill_host(77, b"layers.3.feed_forward.w1.weight", 0.027, 0.0, n, L._capi.ptr(out, L._capi.u16p)))
+        assert np.array_equal(out, O.synth_fill(77, "layers.3.feed_forward.w1.weight", 0.027, 0.0, n))
     # published scales keep activations O(1): sqrt(3)/sqrt(fan_in), norms 1 +- 0.1
     sc, off = L.synth.spec(dict(L.synth.LLAMA31_8B), "layers.0.attention.wq.weight")
     assert abs(sc - 3 ** 0.5 / 64) < 1e-7 and off == 0.0
