@@ -256,3 +256,18 @@ def test_c_rope_table_equals_the_composition_of_the_pinned_blocks():
     val = f(O.arange_bf16(0, 128, 2))
     exp = bf((1.0 / np.power(500000.0, (val / np.float32(128)).astype(np.float64))).astype(np.float32))
     assert np.array_equal(freqs, exp)
+
+
+def test_oracle_outputs_did_not_drift():
+    """the oracle checks every GPU kernel; its own outputs for fixed seeded inputs are anchored by committed digests
+    (tests/golden/oracle_regression.json, written by tests/golden/make_oracle_regression.py)"""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_regression", os.path.join(here, "golden", "make_oracle_regression.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "golden", "oracle_regression.json")) as fh:
+        committed = json.load(fh)
+    assert mod.compute() == committed
