@@ -22,7 +22,8 @@ from tests.test_tokenizer_cpu import CORPUS, GO_PAT, train_bpe, write_model
 # code points assigned in Unicode 15.0 (the tables of csrc/unicode_tables.hpp); newer assignments may be classified differently
 # by the regex module's newer database
 text15 = st.text(alphabet=st.characters(blacklist_categories=("Cs", "Cn")), max_size=200)
-COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+COMMON = dict(deadline=None, derandomize=True, database=None,          # same examples on every run: no flaky round-end surprises
+              suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 
 
 @pytest.fixture(scope="module")
