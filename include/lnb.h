@@ -39,7 +39,8 @@ enum {
   LNB_ECUDA = -2,    /* CUDA runtime failure (sticky on the handle) */
   LNB_ENCCL = -3,    /* NCCL failure */
   LNB_ESTATE = -4,   /* call order (e.g. forward before finalize) */
-  LNB_ENOMEM = -5
+  LNB_ENOMEM = -5,
+  LNB_ETIMEOUT = -6  /* a tensor-parallel peer did not deliver its all-reduce words in time (late / dead rank) */
 };
 
 enum { LNB_ACC_STRICT = 0, LNB_ACC_FAST = 1 };
@@ -209,6 +210,17 @@ int lnb_session_set_active_sequence(lnb_session* s, int seq);
 int lnb_forward_batch(lnb_session* s, const int32_t* tokens, const int32_t* positions, int n,
                       float* logits /* NULL or [n, vocab] */, int32_t* argmax_out /* [n] */);
 
+/* LlamaTransformer.Forward whose result stays in HBM: the host mirror returns an ml.Tensor that carries a handle
+ * (session, generation) instead of S x vocab floats, Tensor.Slice keeps the handle, and ml.Argmax on it runs on the
+ * device -- the reference's call sequence Forward -> Slice(last row) -> Argmax (src/inference/inference.go:202-216)
+ * moves 4 bytes per token over PCIe.  Touching the tensor's data calls lnb_session_logits_read.
+ * rows_kept: 1 (last row) or S.  A handle is valid until the session's next forward (LNB_ESTATE afterwards).
+ * Tensor-parallel: logits_read / logits_argmax are collectives (every rank makes the same call). */
+int lnb_forward_device(lnb_session* s, const int32_t* tokens, int S, int start_pos, int rows_kept,
+                       int32_t* argmax_last /* may be NULL */, int64_t* generation_out);
+int lnb_session_logits_read(lnb_session* s, int64_t generation, int row0, int rows, float* host /* [rows, vocab] */);
+int lnb_session_logits_argmax(lnb_session* s, int64_t generation, int row0, int rows, int32_t* out /* [rows] */);
+
 /* Device-resident greedy decode: runs n_steps consecutive S=1 forwards starting with
  * `first_token` at position start_pos, feeding each argmax back on the device (no host
  * sync inside), optionally as CUDA-graph replays.  tokens_out[n_steps]; ms_out = device
@@ -225,6 +237,10 @@ int lnb_decode_run(lnb_session* s, int32_t first_token, int start_pos, int n_ste
  * session uses NCCL (exactly one all-reduce after Wo and one after w2, as north_star prescribes). */
 int lnb_session_p2p_export(lnb_session* s, void* handle64);
 int lnb_session_p2p_import(lnb_session* s, const void* handles /* tp_size x 64 bytes */, int n);
+/* Every in-kernel wait for a peer is bounded (LNB_P2P_TIMEOUT_MS, default 1500): a late or dead rank turns the
+ * running call into LNB_ETIMEOUT on its peers instead of hanging their GPUs.  After that error the session's peer
+ * path is poisoned; lnb_session_p2p_disable switches the session back to ncclAllReduce (all ranks must do the same). */
+int lnb_session_p2p_disable(lnb_session* s);
 
 /* debugging / parity probes */
 enum { LNB_BUF_RESIDUAL = 0, LNB_BUF_CACHE_K = 1, LNB_BUF_CACHE_V = 2, LNB_BUF_LOGITS = 3 };

@@ -52,12 +52,16 @@ SIGNATURES = {
     "lnb_session_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "lnb_session_destroy": (C.c_int, [vp]),
     "lnb_forward": (C.c_int, [vp, i32p, C.c_int, C.c_int, f32p, C.c_int, i32p]),
+    "lnb_forward_device": (C.c_int, [vp, i32p, C.c_int, C.c_int, C.c_int, i32p, i64p]),
+    "lnb_session_logits_read": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, f32p]),
+    "lnb_session_logits_argmax": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, i32p]),
     "lnb_decode_run": (C.c_int, [vp, C.c_int32, C.c_int, C.c_int, C.c_int, i32p, f32p]),
     "lnb_session_create_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "lnb_session_set_active_sequence": (C.c_int, [vp, C.c_int]),
     "lnb_forward_batch": (C.c_int, [vp, i32p, i32p, C.c_int, f32p, i32p]),
     "lnb_session_p2p_export": (C.c_int, [vp, vp]),
     "lnb_session_p2p_import": (C.c_int, [vp, vp, C.c_int]),
+    "lnb_session_p2p_disable": (C.c_int, [vp]),
     "lnb_session_read": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64]),
     "lnb_session_set_layer_limit": (C.c_int, [vp, C.c_int]),
     "lnb_session_launch_count": (C.c_int64, [vp]),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -812,12 +813,16 @@ template <class Cfg, int PRO, int EPI>
 static int launch_gemv_cfg(const Launcher& L, const GemvParams& p) {
   auto kern = gemv_kernel<Cfg, PRO, EPI>;
   const size_t smem = Cfg::smem_bytes(p.K);
-  static bool attr_set = false;  // per instantiation
-  static size_t attr_smem = 0;
-  if (!attr_set || smem > attr_smem) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    attr_set = true;
-    attr_smem = kMaxSmem;
+  // the opt-in is per function AND per device (context): track it per instantiation per device
+  static std::atomic<uint64_t> attr_mask{0};
+  {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(attr_mask.load(std::memory_order_relaxed) & bit)) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      attr_mask.fetch_or(bit, std::memory_order_relaxed);
+    }
   }
   cudaLaunchConfig_t cfg{};
   const int n_panels = p.N / 8;
@@ -947,10 +952,15 @@ template <int EPI>
 static int launch_gemm_tc(const Launcher& L, const GemmTcParams& p) {
   if (p.N % TC_BN || p.K % TC_KT) return fail(LNB_EINVAL, "gemm_tc: N %d and K %d must be multiples of 128", p.N, p.K);
   auto kern = gemm_tc_kernel<EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    attr_set = true;
+  static std::atomic<uint64_t> attr_mask{0};   // per device, see launch_gemv_cfg
+  {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(attr_mask.load(std::memory_order_relaxed) & bit)) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+      attr_mask.fetch_or(bit, std::memory_order_relaxed);
+    }
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((p.M + TC_BM - 1) / TC_BM, p.N / TC_BN);
@@ -981,7 +991,7 @@ __global__ void set_state_kernel(LnbDevState* st, int pos, int n_rows, int next_
 }
 __global__ void set_p2p_epoch_kernel(LnbDevState* st, uint32_t e) {
   st->ar_epoch = e;
-  st->ar_done = 0;
+  st->ar_error = 0;
   st->ar_done2 = 0;
 }
 // tensor-parallel tail of the LM head: decode the reduced key, advance the decode state
@@ -1024,6 +1034,14 @@ struct lnb_session {
   LnbDevState* st = nullptr;
   int32_t* d_tok_out = nullptr;
   int32_t* h_pin = nullptr;
+  uint32_t* h_err = nullptr;     // pinned mirror of st->ar_error (peer all-reduce timeout flag)
+  // logits of the last forward stay in HBM (lnb_forward_device); the host reads rows / argmaxes on demand
+  int kept_rows = 0;             // rows of s->logits that belong to the last forward (0: none)
+  int32_t kept_last_token = -1;  // greedy token of the last kept row (fused argmax of the LM-head kernel)
+  int64_t generation = 0;        // forward calls so far (a logits handle is valid for one generation)
+  float* h_logits_pin = nullptr; // pinned staging for logits read-backs
+  size_t h_logits_bytes = 0;
+  unsigned long long* d_keys = nullptr;  // [max_rows] per-row argmax keys (tensor-parallel on-demand argmax)
   int layer_limit = 0;
   // batched decode (BASELINE config 5): n_seq independent sequences share the weights; caches are
   // [n_seq][seq_len][kv]; single-sequence calls address the cache of `active_seq`
@@ -1108,6 +1126,8 @@ static int session_create_impl(lnb_model* m, int seq_len, int max_rows, int acc_
   }
   if (e == cudaSuccess) e = cudaMemsetAsync(s->st, 0, sizeof(LnbDevState), s->stream);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_pin, (size_t)(max_rows + seq_len + 16) * 4);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->h_err, 64);
+  if (e == cudaSuccess) *s->h_err = 0;
   if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
@@ -1133,6 +1153,9 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
   if (s->h_pin) cudaFreeHost(s->h_pin);
+  if (s->h_err) cudaFreeHost(s->h_err);
+  if (s->h_logits_pin) cudaFreeHost(s->h_logits_pin);
+  cudaFree(s->d_keys);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -1186,6 +1209,11 @@ extern "C" int lnb_session_p2p_import(lnb_session* s, const void* handles, int n
   s->p2p.rank = m->tp_rank;
   s->p2p.n = n;
   s->p2p.slot_elems = s->max_rows * m->a.dim;
+  {  // budget of one in-kernel wait for a peer (a late or dead rank yields LNB_ETIMEOUT instead of a hung GPU)
+    const char* e = getenv("LNB_P2P_TIMEOUT_MS");
+    const long ms = e ? atol(e) : 1500;
+    s->p2p.timeout_ns = ms > 0 ? (unsigned long long)ms * 1000000ull : 0ull;
+  }
   // epochs start at 1 (the region is zero-initialised, so no word carries a live epoch)
   set_p2p_epoch_kernel<<<1, 1, 0, s->stream>>>(s->st, 1u);
   CU(cudaStreamSynchronize(s->stream));
@@ -1195,8 +1223,20 @@ extern "C" int lnb_session_p2p_import(lnb_session* s, const void* handles, int n
   return 0;
 }
 
+// the captured decode graph bakes in the active sequence's cache pointers and the layer count
+static void drop_graph(lnb_session* s) {
+  if (s->graph) {
+    cudaSetDevice(s->m->device);
+    cudaStreamSynchronize(s->stream);
+    cudaGraphExecDestroy(s->graph);
+    s->graph = nullptr;
+  }
+  s->graph_tried = false;
+}
 extern "C" int lnb_session_set_layer_limit(lnb_session* s, int n) {
   if (!s) return fail(LNB_EINVAL, "session is NULL");
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (n != s->layer_limit) drop_graph(s);
   s->layer_limit = n;
   return 0;
 }
@@ -1205,6 +1245,30 @@ extern "C" int lnb_session_sync(lnb_session* s) {
   if (!s) return fail(LNB_EINVAL, "session is NULL");
   CU(cudaSetDevice(s->m->device));
   CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// peer all-reduce health: the flag travels with the call's own read-backs (enqueue before the stream sync, test after it)
+static int p2p_err_enqueue(lnb_session* s) {
+  if (s->p2p_ready) CU(cudaMemcpyAsync(s->h_err, &s->st->ar_error, 4, cudaMemcpyDeviceToHost, s->stream));
+  return 0;
+}
+static int p2p_err_check(lnb_session* s) {
+  if (!s->p2p_ready || *s->h_err == 0u) return 0;
+  const uint32_t e = *s->h_err;
+  return fail(LNB_ETIMEOUT, "peer all-reduce timed out after %llu ms: rank %d never received the words of rank %u for all-reduce #%u "
+              "(a peer is late, dead or drives its session differently); the session's peer path is poisoned -- "
+              "re-import the handles (lnb_session_p2p_import) or fall back with lnb_session_p2p_disable",
+              (unsigned long long)(s->p2p.timeout_ns / 1000000ull), s->m->tp_rank, e & 15u, (e >> 4) & 0xffffffu);
+}
+extern "C" int lnb_session_p2p_disable(lnb_session* s) {
+  if (!s) return fail(LNB_EINVAL, "session is NULL");
+  std::lock_guard<std::mutex> lk(s->mu);
+  CU(cudaSetDevice(s->m->device));
+  CU(cudaStreamSynchronize(s->stream));
+  drop_graph(s);
+  s->p2p_ready = false;   // the region stays mapped (peers may still write); every later call uses ncclAllReduce
+  *s->h_err = 0;
   return 0;
 }
 
@@ -1223,7 +1287,8 @@ static int ensure_logits(lnb_session* s, size_t rows) {
 // Enqueue one LlamaTransformer.Forward (llamatransformer.go:145-180) for S rows on the
 // session stream.  from_state_token: row 0's token is st->next_token (device-driven decode).
 // logits_rows: 0 = none stored, 1 = last row, S = all rows.  advance: decode-loop bookkeeping.
-static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int logits_rows, bool advance, bool pdl, bool batch = false) {
+static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int logits_rows, bool advance, bool pdl, bool batch = false,
+                           bool gather_logits = true) {
   lnb_model* m = s->m;
   const lnb_model_args& a = m->a;
   Launcher L{s->stream, pdl, &s->launches};
@@ -1363,7 +1428,7 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
         NC(g_nccl.AllReduce(&s->st->amax_key, &s->st->amax_key, 1, ncclUint64_, ncclMax_, m->comm, s->stream));
         if ((rc = launch_simple(L, publish_kernel, dim3(1), dim3(1), 0, s->st, advance ? 1 : 0, s->d_tok_out))) return rc;
       }
-      if (logits_rows > 0)
+      if (logits_rows > 0 && gather_logits)
         for (int r = 0; r < rows; r++)
           NC(g_nccl.AllGather(s->logits + (size_t)r * m->vocab_l, s->logits_full + (size_t)r * a.vocab_size, m->vocab_l,
                               ncclFloat32_, m->comm, s->stream));
@@ -1382,7 +1447,7 @@ static bool forward_tc_ok(const lnb_session* s, int S) {
   return s->mode == LNB_ACC_FAST && s->xn8 && S >= 32 && (m->q_l + 2 * m->kv_l) % TC_BN == 0 && a.dim % TC_BN == 0 &&
          (2 * m->ffn_l) % TC_BN == 0 && a.dim % TC_KT == 0 && m->q_l % TC_KT == 0 && m->ffn_l % TC_KT == 0;
 }
-static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows) {
+static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows, bool gather_logits = true) {
   lnb_model* m = s->m;
   const lnb_model_args& a = m->a;
   Launcher L{s->stream, true, &s->launches};
@@ -1494,7 +1559,7 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows) {
     if (m->tp_size > 1) {
       NC(g_nccl.AllReduce(&s->st->amax_key, &s->st->amax_key, 1, ncclUint64_, ncclMax_, m->comm, s->stream));
       if ((rc = launch_simple(L, publish_kernel, dim3(1), dim3(1), 0, s->st, 0, s->d_tok_out))) return rc;
-      if (logits_rows > 0) {
+      if (logits_rows > 0 && gather_logits) {
         const int rows = logits_rows > 1 ? S : 1;
         for (int r = 0; r < rows; r++)
           NC(g_nccl.AllGather(s->logits + (size_t)r * m->vocab_l, s->logits_full + (size_t)r * a.vocab_size, m->vocab_l, ncclFloat32_,
@@ -1537,9 +1602,148 @@ extern "C" int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int sta
   }
   int32_t* tokpin = s->h_pin + s->max_rows;
   if (argmax_last) CU(cudaMemcpyAsync(tokpin, &s->st->next_token, 4, cudaMemcpyDeviceToHost, s->stream));
+  if ((rc = p2p_err_enqueue(s))) return rc;
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
+  if ((rc = p2p_err_check(s))) return rc;
   if (argmax_last) *argmax_last = *tokpin;
+  return 0;
+}
+
+// Forward whose logits stay on the device: the host mirror of LlamaTransformer.Forward hands the caller a tensor
+// that carries a handle to them (ml.Tensor with a device view) and only lnb_session_logits_read copies rows out.
+// inference.generateTokensInternal slices the last row and argmaxes it (inference.go:207-216): with the handle
+// that is lnb_session_logits_argmax -- 4 bytes cross PCIe per token instead of S x 513 KB down and 513 KB up again.
+// rows_kept: 1 = last row, S = all rows.  generation_out identifies the call (handles of older calls are stale).
+extern "C" int lnb_forward_device(lnb_session* s, const int32_t* tokens, int S, int start_pos, int rows_kept,
+                                  int32_t* argmax_last, int64_t* generation_out) {
+  if (!s || !tokens) return fail(LNB_EINVAL, "NULL argument");
+  if (S <= 0) return fail(LNB_EINVAL, "empty token array");
+  if (rows_kept != 1 && rows_kept != S) return fail(LNB_EINVAL, "rows_kept must be 1 or S");
+  // same checks and the same enqueue as lnb_forward; only the D2H of the logits is left out
+  if (S > s->max_rows) return fail(LNB_EINVAL, "S %d exceeds the session's max_rows %d", S, s->max_rows);
+  if (start_pos < 0 || start_pos + S > s->seq_len)
+    return fail(LNB_EINVAL, "positions [%d, %d) exceed SequenceLength %d", start_pos, start_pos + S, s->seq_len);
+  if (S > 1 && start_pos != 0)
+    return fail(LNB_EINVAL, "S>1 requires startPos 0 (the reference's [S,S] mask does not broadcast to [S,T])");
+  for (int i = 0; i < S; i++)
+    if (tokens[i] < 0 || tokens[i] >= s->m->a.vocab_size) return fail(LNB_EINVAL, "token id %d out of range", tokens[i]);
+  std::lock_guard<std::mutex> lk(s->mu);
+  lnb_model* m = s->m;
+  CU(cudaSetDevice(m->device));
+  int rc = ensure_logits(s, (size_t)(rows_kept > 1 ? s->max_rows : 1));
+  if (rc) return rc;
+  memcpy(s->h_pin, tokens, (size_t)S * 4);
+  CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)S * 4, cudaMemcpyHostToDevice, s->stream));
+  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, S, -1, 0);
+  s->launches++;
+  s->kept_rows = 0;
+  rc = forward_tc_ok(s, S) ? enqueue_forward_tc(s, S, rows_kept, false) : enqueue_forward(s, S, false, rows_kept, false, true, false, false);
+  if (rc) return rc;
+  int32_t* tokpin = s->h_pin + s->max_rows;
+  CU(cudaMemcpyAsync(tokpin, &s->st->next_token, 4, cudaMemcpyDeviceToHost, s->stream));
+  if ((rc = p2p_err_enqueue(s))) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  if ((rc = p2p_err_check(s))) return rc;
+  if (argmax_last) *argmax_last = *tokpin;
+  s->kept_last_token = *tokpin;
+  s->kept_rows = rows_kept;
+  s->generation++;
+  if (generation_out) *generation_out = s->generation;
+  return 0;
+}
+static int logits_handle_check(lnb_session* s, int64_t generation, int row0, int rows) {
+  if (generation != s->generation || s->kept_rows == 0)
+    return fail(LNB_ESTATE, "logits handle of forward #%lld is stale (the session is at #%lld)", (long long)generation, (long long)s->generation);
+  if (row0 < 0 || rows <= 0 || row0 + rows > s->kept_rows) return fail(LNB_EINVAL, "rows [%d, %d) outside the %d kept rows", row0, row0 + rows, s->kept_rows);
+  return 0;
+}
+// rows [row0, row0+rows) of the kept logits -> host [rows, vocab] f32 (pinned staging; tensor-parallel: all-gather first,
+// a collective -- every rank must make the same call)
+extern "C" int lnb_session_logits_read(lnb_session* s, int64_t generation, int row0, int rows, float* host) {
+  if (!s || !host) return fail(LNB_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> lk(s->mu);
+  int rc = logits_handle_check(s, generation, row0, rows);
+  if (rc) return rc;
+  lnb_model* m = s->m;
+  CU(cudaSetDevice(m->device));
+  const size_t V = (size_t)m->a.vocab_size, bytes = (size_t)rows * V * 4;
+  const float* src = s->logits + (size_t)row0 * m->vocab_l;
+  if (m->tp_size > 1) {
+    for (int r = 0; r < rows; r++)
+      NC(g_nccl.AllGather(s->logits + (size_t)(row0 + r) * m->vocab_l, s->logits_full + (size_t)(row0 + r) * V, m->vocab_l, ncclFloat32_,
+                          m->comm, s->stream));
+    src = s->logits_full + (size_t)row0 * V;
+  }
+  if (bytes <= ((size_t)16 << 20)) {
+    if (s->h_logits_bytes < bytes) {
+      if (s->h_logits_pin) cudaFreeHost(s->h_logits_pin);
+      s->h_logits_pin = nullptr; s->h_logits_bytes = 0;
+      CU(cudaMallocHost((void**)&s->h_logits_pin, bytes));
+      s->h_logits_bytes = bytes;
+    }
+    CU(cudaMemcpyAsync(s->h_logits_pin, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(host, s->h_logits_pin, bytes);
+  } else {
+    CU(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  return 0;
+}
+// ml.Argmax (operations_impl.go:513-548) of kept rows, on the device: first maximum wins, NaN never.  The last row's
+// greedy token was already produced by the LM-head kernel of the forward (fused argmax) and is returned as is; other
+// rows run argmax_f32_kernel on the kept logits (tensor-parallel: keys are max-reduced over the ranks, a collective).
+__global__ void __launch_bounds__(256) argmax_key_rows_kernel(const float* __restrict__ x, int cols, int ld, int n_offset,
+                                                              unsigned long long* __restrict__ keys) {
+  __shared__ unsigned long long best[8];
+  const float* xr = x + (size_t)blockIdx.x * ld;
+  unsigned long long key = LNB_ARGMAX_EMPTY;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float v = xr[c];
+    if (v > -3.402823466e+38f) {
+      const unsigned long long k2 = argmax_key(v, (uint32_t)(c + n_offset));
+      key = k2 > key ? k2 : key;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) key = best[i] > key ? best[i] : key;
+    keys[blockIdx.x] = key;
+  }
+}
+extern "C" int lnb_session_logits_argmax(lnb_session* s, int64_t generation, int row0, int rows, int32_t* out) {
+  if (!s || !out) return fail(LNB_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> lk(s->mu);
+  int rc = logits_handle_check(s, generation, row0, rows);
+  if (rc) return rc;
+  lnb_model* m = s->m;
+  CU(cudaSetDevice(m->device));
+  if (rows == 1 && row0 + 1 == s->kept_rows) {   // the row the generate loop asks for: argmaxed by the forward itself
+    out[0] = s->kept_last_token;
+    return 0;
+  }
+  if (!s->d_keys) CU(cudaMalloc((void**)&s->d_keys, (size_t)s->max_rows * 8));
+  unsigned long long* hk = reinterpret_cast<unsigned long long*>(s->h_err + 2);  // pinned, 8-byte aligned, 7 words free
+  for (int r0 = 0; r0 < rows; r0 += 7) {
+    const int n = rows - r0 < 7 ? rows - r0 : 7;
+    argmax_key_rows_kernel<<<n, 256, 0, s->stream>>>(s->logits + (size_t)(row0 + r0) * m->vocab_l, m->vocab_l, m->vocab_l,
+                                                      m->tp_rank * m->vocab_l, s->d_keys);
+    s->launches++;
+    if (m->tp_size > 1) NC(g_nccl.AllReduce(s->d_keys, s->d_keys, (size_t)n, ncclUint64_, ncclMax_, m->comm, s->stream));
+    CU(cudaMemcpyAsync(hk, s->d_keys, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    for (int i = 0; i < n; i++)
+      out[r0 + i] = (hk[i] == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(hk[i] & 0xffffffffull));
+  }
   return 0;
 }
 
@@ -1548,6 +1752,7 @@ extern "C" int lnb_session_set_active_sequence(lnb_session* s, int seq) {
   if (!s) return fail(LNB_EINVAL, "session is NULL");
   if (seq < 0 || seq >= s->n_seq) return fail(LNB_EINVAL, "sequence %d out of range (session has %d)", seq, s->n_seq);
   std::lock_guard<std::mutex> lk(s->mu);
+  if (seq != s->active_seq) drop_graph(s);
   s->active_seq = seq;
   return 0;
 }
@@ -1583,8 +1788,10 @@ extern "C" int lnb_forward_batch(lnb_session* s, const int32_t* tokens, const in
   }
   int32_t* npin = s->h_pin + s->max_rows + 16;
   if (argmax_out) CU(cudaMemcpyAsync(npin, s->d_next_arr, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
+  if ((rc = p2p_err_enqueue(s))) return rc;
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
+  if ((rc = p2p_err_check(s))) return rc;
   if (argmax_out) memcpy(argmax_out, npin, (size_t)n * 4);
   return 0;
 }
@@ -1639,8 +1846,10 @@ extern "C" int lnb_decode_run(lnb_session* s, int32_t first_token, int start_pos
   }
   CU(cudaEventRecord(s->ev1, s->stream));
   CU(cudaMemcpyAsync(s->h_pin + s->max_rows + 8, s->d_tok_out, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, s->stream));
+  { int rce = p2p_err_enqueue(s); if (rce) return rce; }
   CU(cudaStreamSynchronize(s->stream));
   CU(cudaGetLastError());
+  { int rce = p2p_err_check(s); if (rce) return rce; }
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
   if (ms_out) *ms_out = ms;

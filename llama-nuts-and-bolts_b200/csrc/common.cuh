@@ -103,7 +103,8 @@ struct LnbDevState {
   int32_t step;                  // decode-run step counter
   int32_t safe_rows;             // KV rows [0, safe_rows) were complete before this call was enqueued (host-synchronised)
   uint32_t ar_epoch;             // sequence number of the next peer all-reduce (same on every rank)
-  uint32_t ar_done;              // (unused)
+  uint32_t ar_error;             // sticky: 0 = ok, else 0x80000000 | (epoch & 0xffffff) << 4 | late rank  (a peer never delivered
+                                 // within LnbP2P.timeout_ns: every later peer kernel of the session exits at once)
   uint32_t ar_done2;             // CTAs of the reducing kernel that have finished
   uint32_t pad2;
 };
@@ -119,4 +120,36 @@ struct LnbDevState {
 struct LnbP2P {
   uint2* data[8];      // peer r's region base (device pointers valid on this GPU)
   int rank, n, slot_elems;
+  unsigned long long timeout_ns;   // budget of one wait for a peer's words (%globaltimer); 0 = wait forever
 };
+
+LNB_DEVINL unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+LNB_DEVINL uint2 ld_volatile_u2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// Bounded wait for one LL word of `epoch` from rank r.  A late or dead peer must not hang the GPU (and with it
+// the whole box): after timeout_ns the first waiter records (epoch, rank) in st->ar_error, every other waiter
+// sees the flag within 1024 polls, and all of them return false.  The host turns the flag into LNB_ETIMEOUT.
+LNB_DEVINL bool p2p_wait_word(const uint2* src, uint32_t epoch, int r, const LnbP2P& pp, LnbDevState* st,
+                              unsigned long long t_start, uint2* out) {
+  uint2 w = ld_volatile_u2(src);
+  uint32_t spins = 0;
+  while (w.y != epoch) {
+    if ((++spins & 1023u) == 0u) {
+      if (*reinterpret_cast<volatile uint32_t*>(&st->ar_error)) return false;
+      if (pp.timeout_ns && global_timer_ns() - t_start > pp.timeout_ns) {
+        atomicCAS(&st->ar_error, 0u, 0x80000000u | ((epoch & 0xffffffu) << 4) | (uint32_t)(r & 15));
+        return false;
+      }
+    }
+    w = ld_volatile_u2(src);
+  }
+  *out = w;
+  return true;
+}

@@ -473,27 +473,24 @@ __global__ void resid_from_f32_kernel(const float* __restrict__ sum, const uint1
 // Reducer of the peer-memory all-reduce (see LnbP2P in common.cuh): polls the N local slots until the
 // words of this epoch have arrived, adds them in rank order and applies the residual:
 // out = t( res + t( ((p0 + p1) + p2) + ... ) )   (ml.Add after Wo / w2, llamatransformer.go:232,248).
-// The last CTA advances the epoch (local counter only).
-LNB_DEVINL uint2 ld_volatile_u2(const uint2* p) {
-  uint2 v;
-  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
-}
+// The last CTA advances the epoch (local counter only).  Every wait is bounded (p2p_wait_word, common.cuh).
 __global__ void __launch_bounds__(256) p2p_reduce_resid_kernel(LnbP2P pp, LnbDevState* st, const uint16_t* __restrict__ res,
                                                                uint16_t* __restrict__ out, int n_elems) {
   pdl_launch_dependents();
   pdl_wait();
+  if (*reinterpret_cast<volatile uint32_t*>(&st->ar_error)) return;   // an earlier wait of this session timed out
   const uint32_t epoch = st->ar_epoch;
+  const unsigned long long t0 = global_timer_ns();
   const uint2* base = pp.data[pp.rank] + (size_t)(epoch & 1u) * pp.n * pp.slot_elems;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += gridDim.x * blockDim.x) {
+  bool ok = true;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elems && ok; i += gridDim.x * blockDim.x) {
     float sum = 0.f;
     for (int r = 0; r < pp.n; r++) {
-      const uint2* src = base + (size_t)r * pp.slot_elems + i;
-      uint2 w = ld_volatile_u2(src);
-      while (w.y != epoch) w = ld_volatile_u2(src);
+      uint2 w;
+      if (!p2p_wait_word(base + (size_t)r * pp.slot_elems + i, epoch, r, pp, st, t0, &w)) { ok = false; break; }
       sum = (r == 0) ? __uint_as_float(w.x) : __fadd_rn(sum, __uint_as_float(w.x));
     }
-    out[i] = f2bf(__fadd_rn(bf2f(res[i]), trunc_bf(sum)));
+    if (ok) out[i] = f2bf(__fadd_rn(bf2f(res[i]), trunc_bf(sum)));
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -513,7 +510,9 @@ __global__ void __launch_bounds__(256) p2p_reduce_resid_kernel(LnbP2P pp, LnbDev
 __global__ void p2p_argmax_kernel(LnbP2P pp, LnbDevState* st, int advance, int32_t* tok_out) {
   pdl_launch_dependents();
   pdl_wait();
+  if (*reinterpret_cast<volatile uint32_t*>(&st->ar_error)) return;
   const uint32_t epoch = st->ar_epoch;
+  const unsigned long long t0 = global_timer_ns();
   const int lane = threadIdx.x;
   const unsigned long long mykey = st->amax_key;
   const size_t myoff = ((size_t)((epoch & 1u) * pp.n + pp.rank)) * pp.slot_elems;
@@ -522,13 +521,14 @@ __global__ void p2p_argmax_kernel(LnbP2P pp, LnbDevState* st, int advance, int32
     pp.data[lane][myoff + 1] = make_uint2((uint32_t)(mykey >> 32), epoch);
   }
   unsigned long long key = LNB_ARGMAX_EMPTY;
+  bool ok = true;
   if (lane < pp.n) {
     const uint2* src = pp.data[pp.rank] + ((size_t)((epoch & 1u) * pp.n + lane)) * pp.slot_elems;
-    uint2 lo = ld_volatile_u2(src), hi = ld_volatile_u2(src + 1);
-    while (lo.y != epoch) lo = ld_volatile_u2(src);
-    while (hi.y != epoch) hi = ld_volatile_u2(src + 1);
+    uint2 lo = make_uint2(0, 0), hi = make_uint2(0, 0);
+    ok = p2p_wait_word(src, epoch, lane, pp, st, t0, &lo) && p2p_wait_word(src + 1, epoch, lane, pp, st, t0, &hi);
     key = ((unsigned long long)hi.x << 32) | lo.x;
   }
+  if (__any_sync(0xffffffffu, !ok)) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);

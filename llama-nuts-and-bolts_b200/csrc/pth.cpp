@@ -419,13 +419,29 @@ bool PthFile::unpickle(const ZipEntry& pkl, std::string& err) {
             if (t.shape[d] != 1 && t.stride[d] != expect) t.contiguous = false;
             expect *= t.shape[d];
           }
-          if (t.storage_offset < 0 || t.storage_offset > t.storage_numel || (t.contiguous && numel > t.storage_numel - t.storage_offset) ||
-              (uint64_t)t.storage_numel * (uint64_t)isz > e->size) {
+          // elements of the storage the tensor can touch: [offset, offset + sum((shape[d]-1)*stride[d]) + 1), every
+          // product checked against the storage size (a view such as zeros(1).expand(65536, 4096) has numel >> span)
+          int64_t span = numel ? 1 : 0;
+          bool bad = t.storage_offset < 0 || t.storage_offset > t.storage_numel || isz <= 0 ||
+                     (uint64_t)t.storage_numel > (uint64_t)e->size / (uint64_t)isz;          // by division: no wrap-around
+          for (size_t d = 0; d < t.shape.size() && !bad && numel; d++) {
+            const int64_t st = t.stride[d], ext = t.shape[d] - 1;
+            if (st < 0) bad = true;                                                          // torch never pickles negative strides
+            else if (ext > 0 && st > 0) {
+              if (st > t.storage_numel / ext) bad = true;
+              else span += st * ext;
+            }
+            if (span > t.storage_numel) bad = true;
+          }
+          if (!bad && span > t.storage_numel - t.storage_offset) bad = true;
+          if (bad) {
             err = fmt("tensor \"%s\" exceeds its storage", t.name.c_str());
             return false;
           }
           t.file_offset = (int64_t)e->data_offset + t.storage_offset * isz;
-          t.nbytes = numel * isz;
+          // bytes reachable from file_offset: the dense size for contiguous tensors, the touched span of the storage
+          // for strided views (callers that want a dense copy must gather through shape/stride themselves)
+          t.nbytes = (t.contiguous ? numel : span) * isz;
           if (found >= 0) tensors_.erase(tensors_.begin() + found);
           tensors_.push_back(std::move(t));
         }

@@ -239,15 +239,63 @@ def Softmax(input: Tensor, dim: int) -> Tensor:  # operations_impl.go:478-511
 
 
 def Argmax(input: Tensor, dim: int) -> Tensor:  # operations_impl.go:513-548
-    if dim != input.RawData.ndim - 1:
+    if dim != len(input.Size) - 1:
         raise MlError("currenlty Argmax supports only last dimension of input tensor as dim argument")
     if input.DataType is not DT_F32:
         raise MlError(f"unsupported tensor datatype {input.DataType}")
+    if isinstance(input, DeviceLogits) and input.on_device():
+        # the logits never left HBM: argmax them there (4 bytes come back), no re-upload of [rows, vocab] floats
+        out = np.empty(input.rows, np.int32)
+        check(lib.lnb_session_logits_argmax(input.ctx.h, input.generation, input.row0, input.rows, ptr(out, _capi.i32p)))
+        return Tensor(out, DT_INT32)
     cols = input.RawData.shape[-1]
     rows = input.RawData.size // cols
     out = np.empty(input.RawData.shape[:-1], np.int32)
     check(lib.lnb_op_argmax_f32(ptr(input.RawData, _capi.f32p), rows, cols, ptr(out, _capi.i32p)))
     return Tensor(out, DT_INT32)
+
+
+class DeviceLogits(Tensor):
+    """The f32 logits tensor LlamaTransformer.Forward returns (llamatransformer.go:175), still in HBM: Size / DataType /
+    Slice / ml.Argmax work on the handle (lnb_forward_device); the first access to RawData copies the rows to the host
+    (lnb_session_logits_read) and from then on it is an ordinary host tensor.  The handle is valid until the
+    InferenceContext's next Forward -- exactly the lifetime generateTokensInternal needs (inference.go:202-216)."""
+
+    def __init__(self, ctx, generation: int, row0: int, rows: int, vocab: int, name: str = ""):
+        self.ctx, self.generation, self.row0, self.rows, self.vocab = ctx, generation, row0, rows, vocab
+        self._host = None
+        self.DataType = DT_F32
+        self.Name = name
+
+    def on_device(self) -> bool:
+        return self._host is None and self.ctx.h and self.ctx.generation == self.generation
+
+    @property
+    def RawData(self):
+        if self._host is None:
+            if not (self.ctx.h and self.ctx.generation == self.generation):
+                raise MlError("logits tensor outlived the Forward call that produced it (its rows were never read)")
+            out = np.empty((self.rows, self.vocab), np.float32)
+            check(lib.lnb_session_logits_read(self.ctx.h, self.generation, self.row0, self.rows, ptr(out, _capi.f32p)))
+            self._host = out
+        return self._host
+
+    @RawData.setter
+    def RawData(self, v):
+        self._host = v
+
+    @property
+    def Size(self):
+        return [self.rows, self.vocab]
+
+    def GetElementCount(self) -> int:
+        return self.rows * self.vocab
+
+    def Slice(self, loc_start, loc_end) -> "Tensor":
+        # row ranges keep the handle (tensor.go:266-343 semantics: one leading dimension, start < end)
+        if self._host is None and len(loc_start) == 1 and len(loc_end) == 1 and 0 <= loc_start[0] < loc_end[0] <= self.rows:
+            return DeviceLogits(self.ctx, self.generation, self.row0 + loc_start[0], loc_end[0] - loc_start[0], self.vocab, self.Name)
+        return Tensor(self.RawData, DT_F32, self.Name).Slice(loc_start, loc_end)
 
 
 def Fwd_Get_Rows(embedding: Tensor, tokens: Tensor) -> Tensor:  # operations_impl.go:142-173

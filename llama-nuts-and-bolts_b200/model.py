@@ -111,10 +111,11 @@ class LlamaTransformer:
         S = inputTokens.RawData.shape[0]
         if S == 0:
             raise ml.MlError("empty token array")
-        logits = np.empty((S, self.args.VocabSize), np.float32)
-        check(lib.lnb_forward(infContext.h, ptr(inputTokens.RawData, _capi.i32p), S, startPos,
-                              ptr(logits, _capi.f32p), 1, None))
-        return ml.Tensor(logits, ml.DT_F32)
+        # the [S, vocab] f32 result stays in HBM behind a handle; reading it (RawData) copies it to the host
+        gen = C.c_int64(0)
+        check(lib.lnb_forward_device(infContext.h, ptr(inputTokens.RawData, _capi.i32p), S, startPos, S, None, C.byref(gen)))
+        infContext.generation = gen.value
+        return ml.DeviceLogits(infContext, gen.value, 0, S, self.args.VocabSize)
 
     def forward_argmax(self, infContext: "InferenceContext", tokens, startPos: int, want_logits: str = "none"):
         """Fast path of the generate loop: forward + last-row argmax in one call.
@@ -159,6 +160,8 @@ class InferenceContext:
         else:
             check(lib.lnb_session_create(transformer.h, self.SequenceLength, max_rows, acc_mode, C.byref(h)))
         self.h = h
+        self.generation = 0        # forward calls made through lnb_forward_device (validity of ml.DeviceLogits handles)
+        self.pre_close_hook = None  # tensor-parallel sessions: barrier before the peer-mapped region is freed
 
     def Logf(self, fmt, *v):
         if self.logFn:
@@ -228,8 +231,14 @@ class InferenceContext:
 
     def close(self):
         if self.h:
+            if self.pre_close_hook is not None:
+                self.pre_close_hook(self)   # peers may still be storing into this session's all-reduce region
             lib.lnb_session_destroy(self.h)
             self.h = None
+
+    def disable_peer_allreduce(self):
+        """back to ncclAllReduce (e.g. after LNB_ETIMEOUT); every rank must do the same"""
+        check(lib.lnb_session_p2p_disable(self.h))
 
 
 class Model:

@@ -402,3 +402,64 @@ def test_generate_tokens_batch_equals_per_prompt_generation(L, tiny, mode):
             list(eng.GenerateTokensBatch([list(range(seq))]))
     finally:
         gm.Vocabulary.StopTokenIds = saved
+
+
+def test_captured_decode_graph_follows_active_sequence_and_layer_limit(L, tiny):
+    """round-1 advisor finding: the decode graph bakes in the active sequence's cache pointers and the layer count;
+    changing either must re-capture, not silently replay the first capture"""
+    args, _, om, gm = tiny
+    seq = 32
+    prompts = [[1, 50, 999, 7], [3, 4, 5, 6, 7, 8]]
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(seq), max_rows=8, acc_mode=L._capi.LNB_ACC_STRICT, n_seq=2)
+    try:
+        firsts = []
+        for i, p in enumerate(prompts):
+            ctx.set_active_sequence(i)
+            first, _ = gm.Transformer.forward_argmax(ctx, np.array(p, np.int32), 0)
+            firsts.append(first)
+        for i, p in enumerate(prompts):                      # graph captured on sequence 0, then used on sequence 1
+            ctx.set_active_sequence(i)
+            toks, _, graphed = ctx.decode_run(firsts[i], len(p), 8, use_graph=True)
+            assert graphed
+            exp = list(om.generate(p, len(p) + 9, stop_ids=(10**9,)))
+            assert [firsts[i]] + list(toks) == exp, f"sequence {i}"
+        ctx.set_active_sequence(0)
+        ctx.set_layer_limit(1)                               # one layer only: the graph path must agree with the eager path
+        a, _, _ = ctx.decode_run(firsts[0], len(prompts[0]), 4, use_graph=True)
+        b, _, _ = ctx.decode_run(firsts[0], len(prompts[0]), 4, use_graph=False)
+        assert list(a) == list(b)
+        ctx.set_layer_limit(0)
+        c, _, _ = ctx.decode_run(firsts[0], len(prompts[0]), 8, use_graph=True)
+        assert [firsts[0]] + list(c) == list(om.generate(prompts[0], len(prompts[0]) + 9, stop_ids=(10**9,)))
+    finally:
+        ctx.close()
+
+
+def test_forward_returns_a_device_handle_that_reads_like_the_host_tensor(L, tiny):
+    """Transformer.Forward keeps the [S, vocab] logits in HBM (ml.DeviceLogits): Size / Slice / ml.Argmax work on the handle,
+    RawData copies the rows out, and the handle dies with the context's next Forward (inference.go:202-216 never needs more)"""
+    args, _, om, gm = tiny
+    toks = np.array([1, 50, 999, 7, 300], np.int32)
+    ctx = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(16), acc_mode=L._capi.LNB_ACC_STRICT)
+    osess = om.new_session(16)
+    try:
+        exp = osess.forward(toks, 0, all_rows=True)
+        lg = gm.Transformer.Forward(ctx, L.ml.Tensor(toks, L.ml.DT_INT32), 0)
+        assert isinstance(lg, L.ml.DeviceLogits) and lg.Size == [5, args["vocab_size"]] and lg.on_device()
+        last = lg.Slice([4], [5])
+        assert last.Size == [1, args["vocab_size"]] and last.on_device()
+        assert int(L.ml.Argmax(last, 1).Item()) == O.argmax_f32(exp[4])          # fused argmax of the kept last row
+        mid = lg.Slice([1], [4])
+        assert L.ml.Argmax(mid, 1).RawData.tolist() == [O.argmax_f32(exp[r]) for r in (1, 2, 3)]   # device argmax of kept rows
+        assert np.array_equal(mid.RawData, exp[1:4]) and not mid.on_device()      # materialised on first touch
+        assert np.array_equal(lg.RawData, exp)
+        lg2 = gm.Transformer.Forward(ctx, L.ml.Tensor(toks[:1] + 1, L.ml.DT_INT32), 5)
+        stale = lg.Slice([0], [1])                                                # lg itself was read: still a host tensor
+        assert np.array_equal(stale.RawData, exp[0:1])
+        lg3 = gm.Transformer.Forward(ctx, L.ml.Tensor(toks[:1] + 2, L.ml.DT_INT32), 6)
+        with pytest.raises(L.ml.MlError):
+            lg2.RawData                                                           # never read, and a newer Forward ran
+        assert lg3.Size == [1, args["vocab_size"]]
+    finally:
+        ctx.close()
+        osess.close()

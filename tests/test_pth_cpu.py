@@ -71,6 +71,20 @@ def test_reads_module_state_dicts_views_and_flags_non_contiguous(tmp_path):
         assert np.array_equal(t["v1"].RawData, base[4:12].view(2, 4).numpy())     # storage offset honoured
         assert np.array_equal(t["v2"].RawData, base[12:].numpy())
         assert not t["nc"].contiguous and t["nc"].Size == (6, 4)
+        assert t["nc"].nbytes == 24 * 4 and t["nc"].RawData.size == 24     # the touched span of the storage, not numel
+
+
+def test_strided_views_never_map_past_their_storage(tmp_path):
+    """an expanded view has numel >> storage: the reader must hand out the storage span only (round-1 advisor
+    finding: nbytes = numel * itemsize mapped 512 MiB over a 1.8 KB file and segfaulted on first touch)"""
+    p = str(tmp_path / "x.pth")
+    torch.save({"x": torch.zeros(1, dtype=torch.bfloat16).expand(65536, 4096), "col": torch.arange(12.).view(3, 4)[:, 1]}, p)
+    with TorchModelReader(p) as r:
+        t = r.Load()
+        assert t["x"].Size == (65536, 4096) and not t["x"].contiguous
+        assert t["x"].nbytes == 2 and int(t["x"].RawData.sum()) == 0       # one element reachable; touching it is safe
+        assert not t["col"].contiguous and t["col"].nbytes == 9 * 4        # 1 + 2*4 elements from the offset
+        assert np.array_equal(t["col"].RawData[::4], np.array([1., 5., 9.], np.float32))
 
 
 @pytest.mark.parametrize("force_zip64", [False, True])
