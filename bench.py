@@ -149,7 +149,7 @@ class ParityAcc:
     def __init__(self, np, vs: str, tol: float = 1e-2):
         self.np, self.vs, self.tol = np, vs, tol
         self.maxabs, self.n, self.ndiff, self.agree, self.steps = 0.0, 0, 0, 0, 0
-        self.hist = [0, 0, 0, 0]     # 0 / 1 / 2 / >=3 bf16 ulps
+        self.hist = [0, 0, 0, 0, 0]  # |diff| = 0 / <= 2^-8 / <= 2^-7 (one bf16 ulp of a logit in [1,2)) / <= 2^-6 / larger
         self.max_logit = 0.0
         self.first_bad_step = None
 
@@ -162,9 +162,9 @@ class ParityAcc:
         self.maxabs = max(self.maxabs, m)
         self.ndiff += int((d > 0).sum())
         self.n += d.size
-        u = bf16_ulps(g, o, np)
-        self.hist[0] += int((u == 0).sum()); self.hist[1] += int((u == 1).sum())
-        self.hist[2] += int((u == 2).sum()); self.hist[3] += int((u >= 3).sum())
+        self.hist[0] += int((d == 0).sum()); self.hist[1] += int(((d > 0) & (d <= 2.0 ** -8)).sum())
+        self.hist[2] += int(((d > 2.0 ** -8) & (d <= 2.0 ** -7)).sum()); self.hist[3] += int(((d > 2.0 ** -7) & (d <= 2.0 ** -6)).sum())
+        self.hist[4] += int((d > 2.0 ** -6).sum())
         self.max_logit = max(self.max_logit, float(np.abs(o).max()))
         self.agree += int(g_tok == o_tok)
         self.steps += 1
@@ -172,7 +172,8 @@ class ParityAcc:
     def block(self, acc: str, free_equal=None):
         return {"vs": self.vs, "acc": acc, "tokens_compared": self.steps, "logits_max_abs": round(self.maxabs, 6),
                 "logits_differing": self.ndiff, "logits_compared": self.n,
-                "bf16_ulp_histogram": {"0": self.hist[0], "1": self.hist[1], "2": self.hist[2], ">=3": self.hist[3]},
+                "abs_diff_histogram": {"0": self.hist[0], "<=2^-8": self.hist[1], "<=2^-7": self.hist[2], "<=2^-6": self.hist[3],
+                                       ">2^-6": self.hist[4], "note": "2^-7 = one bf16 ulp of a logit in [1, 2)"},
                 "max_abs_logit": round(self.max_logit, 4), "argmax_agree": f"{self.agree}/{self.steps}",
                 "free_running_tokens_equal": free_equal, "tolerance": self.tol,
                 "within_tolerance": bool(self.maxabs <= self.tol),

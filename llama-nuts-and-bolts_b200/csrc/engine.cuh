@@ -1,0 +1,721 @@
+// engine.cuh -- the persistent decode engine: ONE kernel launch runs n_steps complete S=1 forward passes
+// (LlamaTransformer.Forward, src/model/llamatransformer.go:145-180, driven like generateTokensInternal,
+// src/inference/inference.go:194-253) on a grid of one CTA per SM.
+//
+// Why: a decode step is 160+ short dependent kernels.  As separate launches every one of them pays its own
+// launch gap, its own barrier init, its own pipeline ramp (the first weight tile arrives ~1.5 us after the
+// kernel starts) and -- with rows / 32 CTAs -- its own wave quantisation (28672 rows of w1|w3 = 896 CTAs on 296
+// slots = 3.03 waves: the dominant kernel sat at 0.78 of the HBM roofline for that reason alone).  At 8 GPUs the
+// per-kernel work shrinks 8x and the fixed costs are all that is left (round 1: 1.35 ms per token against a
+// 0.29 ms roofline).  Here:
+//   * the step is a PHASE LIST in device memory (EnginePhase[]: projection, attention, all-reduce, argmax exchange);
+//     every CTA walks the same list, phases are separated by a grid barrier (one atomic + one spin per CTA);
+//   * every projection's rows are split STATICALLY and evenly over the CTAs at 8-row panel granularity
+//     (3584 panels of w1|w3 over 148 CTAs = 24 or 25 each: balance 0.97 instead of 0.76);
+//   * warp 0 of every CTA is a bulk-copy producer that walks the phase list AHEAD of the consumers: weights do not
+//     depend on activations, so while the consumers wait at a grid barrier (or for a peer GPU) the ring already
+//     fills with the next projection's first tiles -- no ramp;
+//   * the arithmetic is the arithmetic of gemv.cuh / kernels.cuh, expression for expression (same truncation points,
+//     same summation orders in both accumulation modes): the engine path and the kernel-chain path produce identical
+//     bits (tests/test_gpu_engine.py), and LNB_ACC_STRICT stays bit-identical to the oracle.
+//
+// Thread roles (288 threads): warp 0 = producer (lane 0 issues cp.async.bulk into an NST-stage ring), 256 consumers.
+//   LNB_ACC_FAST   (KS = 8): row tile = 4 panels (32 rows); consumer (r = c % 32, j = c / 32) = row r, k-stream j.
+//   LNB_ACC_STRICT (KS = 1): row tile = up to 32 panels; consumer c = row c of the tile, one sequential chain per row
+//                            (a CTA that owns <= 4 panels of a latency-bound projection runs ONE chain warp on its own
+//                            scheduler; the other consumer warps sleep on the stage barrier with nanosleep back-off).
+// Shared memory: 1 KB header (mbarriers, scalars, the phase's GemvParams) + 128 KB weight ring + 84 KB work area
+// (the activation vector as f32 / the attention phase's K, V, scores).
+//
+// Everything that can wait on another CTA or another GPU is bounded: grid barrier and peer waits give up after
+// timeout_ns, set the sticky LnbDevState.ar_error and make every loop of the CTA (producer included) fall through.
+#pragma once
+#include "gemv.cuh"
+#include "kernels.cuh"
+#include "seqsum.cuh"
+
+namespace lnb {
+
+enum { EP_GEMV = 0, EP_SDPA = 1, EP_REDUCE = 2, EP_ARGMAX = 3 };
+enum {
+  EF_X_TOKEN = 1,    // x   = embedding row of the step's input token (ml.Fwd_Get_Rows, operations_impl.go:142-173)
+  EF_RES_TOKEN = 2,  // res = the same row (the residual stream of layer 0 is the embedding)
+  EF_NO_SYNC = 4     // no grid barrier after this phase (kernel-alone timing: the phases are independent)
+};
+
+struct EnginePhase {
+  int type, pro, epi, flags;
+  int N, K, kt, ldx;
+  const uint16_t* W;
+  const uint16_t* x;        // GEMV: activations [K] / REDUCE: residual [dim]
+  const uint16_t* norm_w;
+  const uint16_t* res;
+  uint16_t* out_bf16;       // GEMV output / REDUCE output
+  float* out_f32;
+  int ldo, n_offset;
+  uint16_t* cache_k;        // this layer's caches (offset to the active sequence): QKV epilogue, SDPA
+  uint16_t* cache_v;
+  const uint16_t* q;        // SDPA in / out
+  uint16_t* o;
+  int q_dim, kv_dim;        // local widths (per tensor-parallel rank)
+};
+
+struct EngineParams {
+  const EnginePhase* phases;
+  int n_phases, n_steps;
+  LnbDevState* st;
+  const uint16_t* emb;
+  int dim, head_dim, n_rep, seq_len;
+  const float* cis;
+  const uint16_t* silu_tab;
+  float eps, attn_scale;
+  int strict;
+  int32_t* tok_out;
+  unsigned int* bar_ctr;    // grid barrier counter, zeroed by the host before the launch
+  LnbP2P p2p;
+  int tp;
+  unsigned long long timeout_ns;
+  int advance;              // 1: decode-loop bookkeeping (tok_out[step], st->pos / st->step advance)
+};
+
+constexpr int ENG_NCONS = 256;
+constexpr int ENG_THREADS = ENG_NCONS + 32;
+constexpr int ENG_RING = 128 * 1024;
+constexpr int ENG_WORK = 84 * 1024;
+constexpr int ENG_XMAX = 56 * 1024;                       // f32 activation vector: K <= 14336
+constexpr int ENG_PART_OFF = ENG_XMAX;                    // [8][32] f32 stream partials (FAST)
+constexpr int ENG_SCAN_OFF = ENG_XMAX + 1024;             // seg-scan scratch (STRICT RMSNorm), 4 KB
+constexpr int ENG_SMEM = 1024 + ENG_RING + ENG_WORK;
+template <int KS> struct EngCfg {
+  static constexpr int kNST = (KS == 1) ? 4 : 8;
+  static constexpr int kStage = ENG_RING / kNST;          // 32 KB / 16 KB
+  static constexpr int kPT = (KS == 1) ? 32 : 4;          // panels per row tile
+};
+
+// host + device: panels [lo, hi) of a matrix with P panels owned by CTA b of G
+__host__ __device__ inline void eng_split(int P, int b, int G, int* lo, int* hi) {
+  *lo = (int)(((long long)P * b) / G);
+  *hi = (int)(((long long)P * (b + 1)) / G);
+}
+// shared-memory need of the attention phase for T_max rows
+__host__ __device__ inline size_t eng_sdpa_smem(int T_max, int hd, int n_rep) {
+  return (size_t)T_max * ((hd + 8) + hd) * 2 + (size_t)n_rep * ((size_t)T_max * 12 + (size_t)hd * 4) + (size_t)n_rep * 5 * 8 + 64;
+}
+
+struct EngCtl {            // in the header, after the barriers
+  volatile int abort_flag;
+  int pos;
+  int tok;
+  int pad;
+};
+
+LNB_DEVINL uint32_t ld_acquire_u32(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+LNB_DEVINL uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+LNB_DEVINL uint32_t ldcg_u32(const void* p) { return __ldcg(reinterpret_cast<const unsigned int*>(p)); }
+LNB_DEVINL uint16_t ldcg_u16(const void* p) { return __ldcg(reinterpret_cast<const unsigned short*>(p)); }
+
+// bounded mbarrier wait: false when the CTA is aborting
+LNB_DEVINL bool eng_mbar_wait(uint64_t* bar, uint32_t parity, EngCtl* ctl, bool backoff) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (backoff) __nanosleep(LNB_BACKOFF_NS);
+    if ((++spins & 255u) == 0u && ctl->abort_flag) return false;
+  }
+  return true;
+}
+
+// Grid barrier among the consumers of all CTAs (the producer warps never take part).  Called by all ENG_NCONS
+// consumer threads; `target` = barriers so far * gridDim.x.  Returns false on abort / timeout.
+LNB_DEVINL bool eng_grid_barrier(const EngineParams& P, EngCtl* ctl, unsigned int target, int c) {
+  named_bar_sync(1, ENG_NCONS);
+  if (c == 0) {
+    __threadfence();
+    atomicAdd(P.bar_ctr, 1u);
+    const unsigned long long t0 = global_timer_ns();
+    uint32_t spins = 0;
+    while (ld_acquire_u32(P.bar_ctr) < target) {
+      if ((++spins & 127u) == 0u) {
+        if (*reinterpret_cast<volatile uint32_t*>(&P.st->ar_error)) { ctl->abort_flag = 1; break; }
+        if (P.timeout_ns && global_timer_ns() - t0 > P.timeout_ns) {
+          atomicCAS(&P.st->ar_error, 0u, 0xC0000000u | (target & 0xffffffu));   // 0xC...: grid barrier (a CTA is missing)
+          ctl->abort_flag = 1;
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  named_bar_sync(1, ENG_NCONS);
+  return ctl->abort_flag == 0;
+}
+
+// ---- LNB_ACC_STRICT RMSNorm sum of squares: the one-pass binade scan of seqsum.cuh (rms_scale_seg_kernel) for the
+// consumers of an engine CTA.  s_x = the row as f32 in shared memory (D = NT * CH elements); threads t >= NT only
+// take part in the barriers.  Returns the reference's sequential fp32 sum (valid on every thread via *s_out).
+template <int CH>
+LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch, float* s_out) {
+  uint32_t* s_run_i0 = reinterpret_cast<uint32_t*>(scratch);            // [256]
+  uint32_t* s_run_i1 = s_run_i0 + 256;                                   // [256]
+  uint16_t* s_run_end = reinterpret_cast<uint16_t*>(s_run_i1 + 256);     // [256]
+  uint8_t* s_code = reinterpret_cast<uint8_t*>(s_run_end + 256);         // [256]
+  float* s_wsum = reinterpret_cast<float*>(s_code + 256);                // [8]
+  uint32_t* s_wflag = reinterpret_cast<uint32_t*>(s_wsum + 8);           // [8] x 4
+  uint32_t* s_whead = s_wflag + 8;
+  uint32_t* s_wi0 = s_whead + 8;
+  uint32_t* s_wi1 = s_wi0 + 8;
+  const int lane = t & 31, wid = t >> 5, nw = NT >> 5;
+  const bool on = t < NT;
+  float sq[CH];
+  float inc = 0.f;
+  if (on) {
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      const float v = s_x[t * CH + k];
+      sq[k] = __fmul_rn(v, v);
+    }
+    float cs = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; k++) cs = __fadd_rn(cs, sq[k]);
+    inc = cs;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc = __fadd_rn(inc, v);
+    }
+    if (lane == 31) s_wsum[wid] = inc;
+    s_run_end[t] = 0;
+  }
+  named_bar_sync(1, ENG_NCONS);
+  int code = 0, pc = 0, nc = 0;
+  SeqSeg v;
+  v.m.i0 = v.m.i1 = 0u;
+  v.flag = 1u;
+  v.head = (uint32_t)t;
+  if (on) {
+    float wpre = 0.f;
+    {
+      float wv = (lane < nw) ? s_wsum[lane] : 0.f;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, wv, d);
+        if (lane >= d) wv = __fadd_rn(wv, u);
+      }
+      const float p = __shfl_sync(0xffffffffu, wv, (wid + 31) & 31);
+      if (wid > 0) wpre = p;
+    }
+    float before = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) before = 0.f;
+    before = __fadd_rn(before, wpre);
+    const float after = __fadd_rn(inc, wpre);
+    code = (t == 0) ? 0 : seq_predict(before, after);
+    s_code[t] = (uint8_t)code;
+    if (code) {
+#pragma unroll
+      for (int k = 0; k < CH; k++) v.m = seq_compose(v.m, seq_term(__float_as_uint(sq[k]), code));
+    }
+    pc = __shfl_up_sync(0xffffffffu, code, 1);
+    nc = __shfl_down_sync(0xffffffffu, code, 1);
+  }
+  named_bar_sync(1, ENG_NCONS);
+  if (on) {
+    if (lane == 0) pc = t ? (int)s_code[t - 1] : 0;
+    if (lane == 31) nc = (t + 1 < NT) ? (int)s_code[t + 1] : 0;
+    v.flag = (code == 0 || pc != code) ? 1u : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      SeqSeg o;
+      o.flag = __shfl_up_sync(0xffffffffu, v.flag, d);
+      o.head = __shfl_up_sync(0xffffffffu, v.head, d);
+      o.m.i0 = __shfl_up_sync(0xffffffffu, v.m.i0, d);
+      o.m.i1 = __shfl_up_sync(0xffffffffu, v.m.i1, d);
+      if (lane >= d) v = seq_seg_op(o, v);
+    }
+    if (lane == 31) { s_wflag[wid] = v.flag; s_whead[wid] = v.head; s_wi0[wid] = v.m.i0; s_wi1[wid] = v.m.i1; }
+  }
+  named_bar_sync(1, ENG_NCONS);
+  if (on) {
+    SeqSeg a;
+    a.flag = (lane < nw) ? s_wflag[lane] : 1u;
+    a.head = (lane < nw) ? s_whead[lane] : 0u;
+    a.m.i0 = (lane < nw) ? s_wi0[lane] : 0u;
+    a.m.i1 = (lane < nw) ? s_wi1[lane] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      SeqSeg o;
+      o.flag = __shfl_up_sync(0xffffffffu, a.flag, d);
+      o.head = __shfl_up_sync(0xffffffffu, a.head, d);
+      o.m.i0 = __shfl_up_sync(0xffffffffu, a.m.i0, d);
+      o.m.i1 = __shfl_up_sync(0xffffffffu, a.m.i1, d);
+      if (lane >= d) a = seq_seg_op(o, a);
+    }
+    SeqSeg p;
+    const int src = (wid + 31) & 31;
+    p.flag = __shfl_sync(0xffffffffu, a.flag, src);
+    p.head = __shfl_sync(0xffffffffu, a.head, src);
+    p.m.i0 = __shfl_sync(0xffffffffu, a.m.i0, src);
+    p.m.i1 = __shfl_sync(0xffffffffu, a.m.i1, src);
+    if (wid > 0) v = seq_seg_op(p, v);
+    if (code && nc != code) {                        // last chunk of a run: publish the run at its head
+      s_run_end[v.head] = (uint16_t)(t + 1);
+      s_run_i0[v.head] = v.m.i0;
+      s_run_i1[v.head] = v.m.i1;
+    }
+  }
+  named_bar_sync(1, ENG_NCONS);
+  if (t == 0) {                                      // the walk: jump over runs, real FADDs everywhere else
+    uint32_t sb = 0u;
+    int cidx = 0;
+    while (cidx < NT) {
+      const int e = (int)s_run_end[cidx];
+      const int E = (int)s_code[cidx];
+      SeqInc run;
+      run.i0 = s_run_i0[cidx]; run.i1 = s_run_i1[cidx];
+      uint32_t nb;
+      if (e > cidx && seq_try_jump(sb, E, run, &nb)) { sb = nb; cidx = e; continue; }
+      float s = __uint_as_float(sb);
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        const float xv = s_x[cidx * CH + k];
+        s = __fadd_rn(s, __fmul_rn(xv, xv));
+      }
+      sb = __float_as_uint(s);
+      cidx++;
+    }
+    *s_out = __uint_as_float(sb);
+  }
+  named_bar_sync(1, ENG_NCONS);
+}
+// (CH, NT) for a row of D elements with at most 256 threads; false: no engine for this model width
+__host__ __device__ inline bool eng_scan_shape(int D, int* ch, int* nt) {
+  const int cand[4] = {16, 8, 4, 2};
+  for (int i = 0; i < 4; i++) {
+    const int c = cand[i];
+    if (D % c == 0 && (D / c) % 32 == 0 && D / c <= ENG_NCONS && D / c >= 32) { *ch = c; *nt = D / c; return true; }
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const EngineParams P) {
+  using Cfg = EngCfg<KS>;
+  constexpr int NST = Cfg::kNST, STAGE = Cfg::kStage, PT = Cfg::kPT;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);              // [NST]
+  uint64_t* empty_bar = full_bar + NST;                                // [NST]
+  float* s_scalar = reinterpret_cast<float*>(smem + 256);              // rms scale etc.
+  EngCtl* ctl = reinterpret_cast<EngCtl*>(smem + 320);
+  GemvParams* gp = reinterpret_cast<GemvParams*>(smem + 512);          // the running phase as the epilogues see it
+  uint8_t* s_ring = smem + 1024;
+  uint8_t* s_work = s_ring + ENG_RING;
+  float* s_x = reinterpret_cast<float*>(s_work);
+  float* s_part = reinterpret_cast<float*>(s_work + ENG_PART_OFF);
+  static_assert(sizeof(GemvParams) <= 512, "GemvParams must fit the header");
+
+  const int tid = threadIdx.x;
+  const int G = gridDim.x, bid = blockIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < NST; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], ENG_NCONS / 32);
+    }
+    mbar_fence_init();
+    ctl->abort_flag = 0;
+  }
+  __syncthreads();
+
+  if (tid < 32) {
+    // =========================== producer: walks the phase list ahead of the consumers ===========================
+    if (tid == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      uint32_t seq = 0;
+      for (int step = 0; step < P.n_steps; step++) {
+        for (int ph = 0; ph < P.n_phases; ph++) {
+          const EnginePhase* E = P.phases + ph;
+          if (E->type != EP_GEMV) continue;
+          const int K = E->K, kt = E->kt;
+          const int n_tiles = (K + kt - 1) / kt;
+          int p0, p1;
+          eng_split(E->N / 8, bid, G, &p0, &p1);
+          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(E->W);
+          for (int rt = p0; rt < p1; rt += PT) {
+            const int np = min(PT, p1 - rt);
+            for (int t = 0; t < n_tiles; t++, seq++) {
+              const int s = seq % NST;
+              const uint32_t par = (seq / NST) & 1u;
+              if (!eng_mbar_wait(&empty_bar[s], par ^ 1u, ctl, false)) return;
+              const int k0 = t * kt;
+              const uint32_t bytes_per_panel = (uint32_t)min(kt, K - k0) * 16u;
+              mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)np);
+              for (int pp = 0; pp < np; pp++)
+                bulk_g2s(s_ring + (size_t)s * STAGE + (size_t)pp * ((size_t)kt * 16), wbase + ((size_t)(rt + pp) * (size_t)K + (size_t)k0) * 16u,
+                         bytes_per_panel, &full_bar[s], pol);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ======================================= consumers =============================================================
+  const int c = tid - 32;
+  const int lane = tid & 31;
+  const int cw = c >> 5;
+  const int r = (KS == 1) ? c : (c & 31);     // row within the row tile
+  const int j = (KS == 1) ? 0 : (c >> 5);     // k-stream
+  uint32_t seq = 0;                           // stages consumed so far (same count as the producer's)
+  unsigned int n_bar = 0;                     // grid barriers passed
+  uint32_t epoch = (P.tp > 1) ? P.st->ar_epoch : 0u;
+  int pos = P.st->pos;
+  int tok = P.st->next_token;
+  bool key_reset_due = false;
+  if (bid == 0 && c == 0) P.st->amax_key = LNB_ARGMAX_EMPTY;   // nobody touches the key before the first LM head
+
+  for (int step = 0; step < P.n_steps; step++) {
+    if (c == 0) { ctl->pos = pos; ctl->tok = tok; }
+    for (int ph = 0; ph < P.n_phases; ph++) {
+      const EnginePhase* E = P.phases + ph;
+      const int type = E->type;
+      if (type == EP_GEMV) {
+        const int K = E->K, kt = E->kt;
+        const int n_tiles = (K + kt - 1) / kt;
+        int p0, p1;
+        eng_split(E->N / 8, bid, G, &p0, &p1);
+        const int flags = E->flags;
+        const uint16_t* xg = (flags & EF_X_TOKEN) ? P.emb + (size_t)tok * P.dim : E->x;
+        if (p1 > p0) {
+          // ---- the phase as gemv_epilogue sees it ------------------------------------------------------------
+          if (c == 0) {
+            GemvParams g{};
+            g.W = E->W; g.N = E->N; g.K = K; g.M = 1;
+            g.x = xg; g.ldx = E->ldx; g.norm_w = E->norm_w; g.eps = P.eps;
+            g.out_bf16 = E->out_bf16; g.out_f32 = E->out_f32; g.ldo = E->ldo;
+            g.res = (flags & EF_RES_TOKEN) ? P.emb + (size_t)tok * P.dim : E->res;
+            g.q_dim = E->q_dim; g.kv_dim = E->kv_dim; g.head_dim = P.head_dim;
+            g.cache_k = E->cache_k; g.cache_v = E->cache_v; g.pos_arr = nullptr; g.cache_seq_stride = 0;
+            g.cis = P.cis; g.silu_tab = P.silu_tab;
+            g.n_offset = E->n_offset; g.st = P.st; g.argmax_row = 0; g.publish = 0; g.advance = 0; g.tok_out = nullptr;
+            g.pos_ptr = &ctl->pos; g.m_off = 0;
+            g.p2p = P.p2p;
+            g.ar_epoch_override = epoch;
+            *gp = g;
+          }
+          // ---- prologue: activations -> f32 in shared memory (gemv.cuh prologue, MB = 1) -----------------------
+          for (int k = c * 2; k < K; k += ENG_NCONS * 2) {
+            const uint32_t w = ldcg_u32(xg + k);
+            *reinterpret_cast<float2*>(s_x + k) = make_float2(bf_lo(w), bf_hi(w));
+          }
+          named_bar_sync(1, ENG_NCONS);
+          if (E->pro == PRO_RMSNORM) {
+            if (P.strict) {
+              int ch = 0, nt = 0;
+              eng_scan_shape(K, &ch, &nt);
+              uint8_t* scr = s_work + ENG_SCAN_OFF;
+              float* s_sum = s_scalar + 4;
+              switch (ch) {
+                case 16: eng_seq_sumsq<16>(s_x, c, nt, scr, s_sum); break;
+                case 8: eng_seq_sumsq<8>(s_x, c, nt, scr, s_sum); break;
+                case 4: eng_seq_sumsq<4>(s_x, c, nt, scr, s_sum); break;
+                default: eng_seq_sumsq<2>(s_x, c, nt, scr, s_sum); break;
+              }
+              if (c == 0) {
+                const float me = __fadd_rn(__fdiv_rn(*s_sum, (float)K), P.eps);
+                s_scalar[0] = (float)(1.0 / sqrt((double)me));
+              }
+            } else {
+              // FAST: 256 interleaved partial sums, butterfly within each warp, then sequentially over the 8 warps
+              float sum = 0.f;
+              for (int k = c; k < K; k += ENG_NCONS) sum = __fmaf_rn(s_x[k], s_x[k], sum);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+              if (lane == 0) s_part[cw] = sum;
+              named_bar_sync(1, ENG_NCONS);
+              if (c == 0) {
+                float tot = 0.f;
+                for (int w = 0; w < ENG_NCONS / 32; w++) tot = __fadd_rn(tot, s_part[w]);
+                const float me = __fadd_rn(__fdiv_rn(tot, (float)K), P.eps);
+                s_scalar[0] = (float)(1.0 / sqrt((double)me));
+              }
+            }
+            named_bar_sync(1, ENG_NCONS);
+            const float rs = s_scalar[0];
+            for (int k = c; k < K; k += ENG_NCONS) {
+              const float n1 = trunc_bf(__fmul_rn(s_x[k], rs));
+              s_x[k] = trunc_bf(__fmul_rn(n1, bf2f(E->norm_w[k])));
+            }
+            named_bar_sync(1, ENG_NCONS);
+          }
+          // ---- row tiles --------------------------------------------------------------------------------------
+          for (int rt = p0; rt < p1; rt += PT) {
+            const int np = min(PT, p1 - rt);
+            const int pp = r >> 3, rr = r & 7;
+            const bool row_on = pp < np;
+            float acc = 0.f;
+            for (int t = 0; t < n_tiles; t++, seq++) {
+              const int s = seq % NST;
+              const uint32_t par = (seq / NST) & 1u;
+              // warps without rows in this tile only keep the ring moving: wait politely
+              const bool warp_on = (KS == 1) ? ((cw * 4) < np) : true;
+              if (!eng_mbar_wait(&full_bar[s], par, ctl, !warp_on)) return;
+              const int k0 = t * kt;
+              const int nchunks = min(kt, K - k0) / 8;
+              if (row_on) {
+                const uint8_t* tile = s_ring + (size_t)s * STAGE + (size_t)pp * ((size_t)kt * 16) + rr * 16;
+                const float* xt = s_x + k0;
+                if (KS == 1 && (nchunks & 3) == 0) {
+                  // groups of 4 chunks, register double-buffered: the LDS of group g+1 are in flight while the 32
+                  // dependent FMAs of group g issue (gemv.cuh, MB == 1 branch)
+                  const int ng = nchunks >> 2;
+                  uint4 wa[4], wb[4];
+                  float4 xa0[4], xa1[4], xb0[4], xb1[4];
+#define ENG_LOAD(gi, W_, X0_, X1_)                                            \
+  _Pragma("unroll") for (int q_ = 0; q_ < 4; q_++) {                          \
+    const int ch_ = (gi) * 4 + q_;                                            \
+    W_[q_] = *reinterpret_cast<const uint4*>(tile + ch_ * 128);               \
+    X0_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8);                 \
+    X1_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8 + 4);             \
+  }
+#define ENG_FMA(W_, X0_, X1_)                                                 \
+  _Pragma("unroll") for (int q_ = 0; q_ < 4; q_++) {                          \
+    float a_ = acc;                                                           \
+    a_ = __fmaf_rn(X0_[q_].x, bf_lo(W_[q_].x), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].y, bf_hi(W_[q_].x), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].z, bf_lo(W_[q_].y), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].w, bf_hi(W_[q_].y), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].x, bf_lo(W_[q_].z), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].y, bf_hi(W_[q_].z), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].z, bf_lo(W_[q_].w), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].w, bf_hi(W_[q_].w), a_);                           \
+    acc = a_;                                                                 \
+  }
+                  ENG_LOAD(0, wa, xa0, xa1)
+                  for (int gi = 0; gi < ng; gi += 2) {
+                    if (gi + 1 < ng) { ENG_LOAD(gi + 1, wb, xb0, xb1) }
+                    ENG_FMA(wa, xa0, xa1)
+                    if (gi + 2 < ng) { ENG_LOAD(gi + 2, wa, xa0, xa1) }
+                    if (gi + 1 < ng) { ENG_FMA(wb, xb0, xb1) }
+                  }
+#undef ENG_LOAD
+#undef ENG_FMA
+                } else {
+#pragma unroll 4
+                  for (int ch = j; ch < nchunks; ch += KS) {
+                    const uint4 wv = *reinterpret_cast<const uint4*>(tile + ch * 128);
+                    const float4 xa = *reinterpret_cast<const float4*>(xt + ch * 8);
+                    const float4 xb = *reinterpret_cast<const float4*>(xt + ch * 8 + 4);
+                    float a = acc;
+                    a = __fmaf_rn(xa.x, bf_lo(wv.x), a);
+                    a = __fmaf_rn(xa.y, bf_hi(wv.x), a);
+                    a = __fmaf_rn(xa.z, bf_lo(wv.y), a);
+                    a = __fmaf_rn(xa.w, bf_hi(wv.y), a);
+                    a = __fmaf_rn(xb.x, bf_lo(wv.z), a);
+                    a = __fmaf_rn(xb.y, bf_hi(wv.z), a);
+                    a = __fmaf_rn(xb.z, bf_lo(wv.w), a);
+                    a = __fmaf_rn(xb.w, bf_hi(wv.w), a);
+                    acc = a;
+                  }
+                }
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty_bar[s]);
+            }
+            // ---- combine the KS streams in stream order, then the fused epilogue -------------------------------
+            float v = acc;
+            if (KS > 1) {
+              s_part[j * 32 + r] = acc;
+              named_bar_sync(1, ENG_NCONS);
+              if (c < 32) {
+                v = s_part[r];
+#pragma unroll
+                for (int jj = 1; jj < KS; jj++) v = __fadd_rn(v, s_part[jj * 32 + r]);
+              }
+            }
+            if (KS == 1 || c < 32) {
+              const int n = (rt + pp) * 8 + rr;                // global row of W
+              const bool valid = row_on;
+              switch (E->epi) {
+                case EPI_BF16: gemv_epilogue<EPI_BF16>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
+                case EPI_RESID: gemv_epilogue<EPI_RESID>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
+                case EPI_LOGITS: gemv_epilogue<EPI_LOGITS>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
+                case EPI_QKV_ROPE: gemv_epilogue<EPI_QKV_ROPE>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
+                case EPI_SWIGLU: gemv_epilogue<EPI_SWIGLU>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
+                case EPI_P2P: gemv_epilogue<EPI_P2P>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
+                default: gemv_epilogue<EPI_F32RAW>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
+              }
+            }
+            if (KS > 1) named_bar_sync(1, ENG_NCONS);          // s_part is reused by the next row tile
+          }
+        }
+        if (flags & EF_NO_SYNC) { named_bar_sync(1, ENG_NCONS); continue; }
+      } else if (type == EP_SDPA) {
+        // ---- decode attention for one KV head per CTA: sdpa_decode_kernel's arithmetic (kernels.cuh), with the 128
+        // threads per query head of that kernel mapped onto 256 consumers (each takes query heads hh, hh + 2, ...) ----
+        const int hd = P.head_dim, n_rep = P.n_rep;
+        const int n_kvh = E->kv_dim / hd;
+        if (bid < n_kvh) {
+          const int h = bid;
+          const int T = pos + 1, T_max = P.seq_len;
+          const int kstride = hd + 8, cpr = hd / 8;
+          uint16_t* sK = reinterpret_cast<uint16_t*>(s_work);
+          uint16_t* sV = sK + (size_t)T_max * kstride;
+          double* sE = reinterpret_cast<double*>(sV + (size_t)T_max * hd);
+          float* sP = reinterpret_cast<float*>(sE + (size_t)n_rep * T_max);
+          float* sQ = sP + (size_t)n_rep * T_max;
+          double* sZ = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sQ + (size_t)n_rep * hd) + 15) & ~(uintptr_t)15);
+          for (int i = c; i < T * cpr; i += ENG_NCONS) {
+            const int t = i / cpr, cc = i % cpr;
+            *reinterpret_cast<uint4*>(sK + (size_t)t * kstride + cc * 8) = ldcg_u4(E->cache_k + (size_t)t * E->kv_dim + (size_t)h * hd + cc * 8);
+            *reinterpret_cast<uint4*>(sV + (size_t)t * hd + cc * 8) = ldcg_u4(E->cache_v + (size_t)t * E->kv_dim + (size_t)h * hd + cc * 8);
+          }
+          for (int i = c; i < n_rep * hd; i += ENG_NCONS) sQ[i] = bf2f(ldcg_u16(E->q + (size_t)(h * n_rep) * hd + i));
+          named_bar_sync(1, ENG_NCONS);
+          const int tt = c & 127;
+          for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128) {
+            const float* qh = sQ + hh * hd;
+            for (int t = tt; t < T; t += 128) {
+              const uint16_t* kr = sK + (size_t)t * kstride;
+              float a = 0.f;
+              for (int d = 0; d < hd; d += 8) {
+                const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
+                a = __fmaf_rn(qh[d + 0], bf_lo(kv.x), a);
+                a = __fmaf_rn(qh[d + 1], bf_hi(kv.x), a);
+                a = __fmaf_rn(qh[d + 2], bf_lo(kv.y), a);
+                a = __fmaf_rn(qh[d + 3], bf_hi(kv.y), a);
+                a = __fmaf_rn(qh[d + 4], bf_lo(kv.z), a);
+                a = __fmaf_rn(qh[d + 5], bf_hi(kv.z), a);
+                a = __fmaf_rn(qh[d + 6], bf_lo(kv.w), a);
+                a = __fmaf_rn(qh[d + 7], bf_hi(kv.w), a);
+              }
+              float sc = trunc_bf(a);
+              sc = trunc_bf(__fdiv_rn(sc, P.attn_scale));
+              sE[(size_t)hh * T_max + t] = exp((double)sc);
+            }
+          }
+          named_bar_sync(1, ENG_NCONS);
+          for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128) {
+            double* eh = sE + (size_t)hh * T_max;
+            if (P.strict) {
+              if (tt == 0) {
+                double z = 0.0;
+                for (int t = 0; t < T; t++) z = __dadd_rn(z, eh[t]);
+                sZ[n_rep * 4 + hh] = z;
+              }
+            } else {
+              double z = 0.0;
+              for (int t = tt; t < T; t += 128) z = __dadd_rn(z, eh[t]);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, o));
+              if ((tt & 31) == 0) sZ[hh * 4 + (tt >> 5)] = z;
+            }
+          }
+          named_bar_sync(1, ENG_NCONS);
+          if (!P.strict)
+            for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128)
+              if (tt == 0) sZ[n_rep * 4 + hh] = __dadd_rn(__dadd_rn(__dadd_rn(sZ[hh * 4 + 0], sZ[hh * 4 + 1]), sZ[hh * 4 + 2]), sZ[hh * 4 + 3]);
+          named_bar_sync(1, ENG_NCONS);
+          for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128) {
+            const double Z = sZ[n_rep * 4 + hh];
+            const double* eh = sE + (size_t)hh * T_max;
+            float* phh = sP + (size_t)hh * T_max;
+            for (int t = tt; t < T; t += 128) phh[t] = trunc_bf((float)__ddiv_rn(eh[t], Z));
+          }
+          named_bar_sync(1, ENG_NCONS);
+          for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128) {
+            if (tt < hd) {
+              const float* phh = sP + (size_t)hh * T_max;
+              const uint16_t* vc = sV + tt;
+              float a = 0.f;
+#pragma unroll 4
+              for (int t = 0; t < T; t++) a = __fmaf_rn(phh[t], bf2f(vc[(size_t)t * hd]), a);
+              E->o[(size_t)(h * n_rep + hh) * hd + tt] = f2bf(a);
+            }
+          }
+        }
+      } else if (type == EP_REDUCE) {
+        // ---- peer all-reduce of the partials the previous phase pushed: out = t(res + t(p0 + p1 + ...)), rank order ----
+        const int per = (P.dim + G - 1) / G;
+        const int i = bid * per + c;
+        bool ok = true;
+        if (c < per && i < P.dim) {
+          const unsigned long long t0 = global_timer_ns();
+          const uint2* base = P.p2p.data[P.p2p.rank] + (size_t)(epoch & 1u) * P.p2p.n * P.p2p.slot_elems;
+          float sum = 0.f;
+          for (int rk = 0; rk < P.p2p.n; rk++) {
+            uint2 w;
+            if (!p2p_wait_word(base + (size_t)rk * P.p2p.slot_elems + i, epoch, rk, P.p2p, P.st, t0, &w)) { ok = false; break; }
+            sum = (rk == 0) ? __uint_as_float(w.x) : __fadd_rn(sum, __uint_as_float(w.x));
+          }
+          const uint16_t* resp = (E->flags & EF_RES_TOKEN) ? P.emb + (size_t)tok * P.dim : E->res;
+          if (ok) E->out_bf16[i] = f2bf(__fadd_rn(bf2f(ldcg_u16(resp + i)), trunc_bf(sum)));
+        }
+        if (!ok) ctl->abort_flag = 1;
+        epoch++;
+      } else if (type == EP_ARGMAX) {
+        // ---- tensor-parallel greedy argmax: CTA 0 pushes this rank's key to every peer; every CTA takes the max ----
+        // (runs after the LM head's grid barrier: st->amax_key is final)
+        const unsigned long long t0 = global_timer_ns();
+        const size_t myoff = ((size_t)((epoch & 1u) * P.p2p.n + P.p2p.rank)) * P.p2p.slot_elems;
+        if (bid == 0 && c < P.p2p.n) {
+          const unsigned long long mykey = __ldcg(&P.st->amax_key);
+          P.p2p.data[c][myoff] = make_uint2((uint32_t)(mykey & 0xffffffffull), epoch);
+          P.p2p.data[c][myoff + 1] = make_uint2((uint32_t)(mykey >> 32), epoch);
+        }
+        if (c < 32) {
+          unsigned long long key = LNB_ARGMAX_EMPTY;
+          bool ok = true;
+          if (c < P.p2p.n) {
+            const uint2* src = P.p2p.data[P.p2p.rank] + ((size_t)((epoch & 1u) * P.p2p.n + c)) * P.p2p.slot_elems;
+            uint2 lo = make_uint2(0, 0), hi = make_uint2(0, 0);
+            ok = p2p_wait_word(src, epoch, c, P.p2p, P.st, t0, &lo) && p2p_wait_word(src + 1, epoch, c, P.p2p, P.st, t0, &hi);
+            key = ((unsigned long long)hi.x << 32) | lo.x;
+          }
+          if (__any_sync(0xffffffffu, !ok)) ctl->abort_flag = 1;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+          }
+          if (c == 0) ctl->tok = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+        }
+        epoch++;
+        named_bar_sync(1, ENG_NCONS);
+        if (ctl->abort_flag) return;
+        tok = ctl->tok;
+        continue;                                  // purely local result: no grid barrier
+      }
+      // ---- end of phase: everybody's outputs become visible to everybody ----------------------------------------
+      n_bar++;
+      if (!eng_grid_barrier(P, ctl, n_bar * (unsigned int)G, c)) return;
+      if (key_reset_due) {                         // every CTA has read the previous step's key by now
+        if (bid == 0 && c == 0) P.st->amax_key = LNB_ARGMAX_EMPTY;
+        key_reset_due = false;
+      }
+      if (type == EP_GEMV && E->epi == EPI_LOGITS && P.tp == 1) {
+        const unsigned long long key = __ldcg(&P.st->amax_key);
+        tok = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+      }
+    }
+    // ---- end of step: greedy token known to every CTA ------------------------------------------------------------
+    key_reset_due = true;
+    if (bid == 0 && c == 0 && P.advance && P.tok_out) P.tok_out[P.st->step + step] = tok;
+    pos += 1;
+  }
+  if (bid == 0 && c == 0) {
+    // n_bar >= 1 barriers have passed since any CTA read the state at the top
+    P.st->next_token = tok;
+    P.st->amax_key = LNB_ARGMAX_EMPTY;
+    P.st->done_ctr = 0;
+    if (P.tp > 1) P.st->ar_epoch = epoch;
+    if (P.advance) {
+      P.st->step += P.n_steps;
+      P.st->pos += P.n_steps;
+    }
+  }
+}
+
+}  // namespace lnb
