@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -19,6 +20,7 @@
 #include "gemv.cuh"
 #include "kernels.cuh"
 #include "seqsum.cuh"
+#include "engine.cuh"
 #include "pth.hpp"
 #include "tokenizer.hpp"
 
@@ -1051,6 +1053,14 @@ struct lnb_session {
   bool sdpa_smem_decode = false;  // the whole K/V history of one KV head fits in shared memory
   size_t sdpa_decode_smem = 0;
   int64_t launches = 0;
+  // persistent decode engine (engine.cuh): the phase list of one S=1 step in device memory
+  EnginePhase* d_phases = nullptr;
+  int n_phases = 0, phases_cap = 0;
+  unsigned int* d_bar = nullptr;
+  int eng_state = 0;             // 0 = not probed, 1 = usable, -1 = this session uses the kernel chain
+  std::string eng_why;           // why not
+  int eng_key_seq = -1, eng_key_layers = -1, eng_key_kind = -2;
+  const float* eng_key_logits = nullptr;
   cudaGraphExec_t graph = nullptr;
   bool graph_tried = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1149,6 +1159,7 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   for (int r = 0; r < 8; r++)
     if (s->p2p_peer[r]) cudaIpcCloseMemHandle(s->p2p_peer[r]);
   cudaFree(s->p2p_region);
+  cudaFree(s->d_phases); cudaFree(s->d_bar);
   cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out); cudaFree(s->d_pos_arr); cudaFree(s->d_next_arr);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
@@ -1282,6 +1293,205 @@ static int ensure_logits(lnb_session* s, size_t rows) {
   if (s->m->tp_size > 1) CU(cudaMalloc((void**)&s->logits_full, rows * (size_t)s->m->a.vocab_size * 4));
   s->logits_rows = rows;
   return 0;
+}
+
+// ---- persistent decode engine (engine.cuh) ---------------------------------------------------------------------
+static float attn_scale_bf16(int head_dim) {  // dtype.BFloat16fromFloat32(float32(math.Sqrt(float64(HeadDim)))) :464
+  float f = (float)sqrt((double)head_dim);
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u &= 0xffff0000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// Can this session's S=1 steps run as ONE persistent kernel?  (LNB_ENGINE=0 forces the kernel chain.)
+static bool engine_probe(lnb_session* s) {
+  if (s->eng_state) return s->eng_state > 0;
+  lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  auto no = [&](const char* why) { s->eng_state = -1; s->eng_why = why; return false; };
+  const char* e = getenv("LNB_ENGINE");
+  if (e && !strcmp(e, "0")) return no("LNB_ENGINE=0");
+  const int kmax = std::max(a.dim, std::max(m->q_l, m->ffn_l));
+  if ((size_t)kmax * 4 > (size_t)ENG_XMAX) return no("activation vector exceeds the engine's shared-memory work area");
+  if (a.dim % 8 || m->q_l % 8 || m->ffn_l % 8) return no("widths must be multiples of 8");
+  const int n_rep = a.n_heads / a.n_kv_heads;
+  if (a.head_dim > 128 || a.head_dim % 8 || n_rep > 8) return no("head shape");
+  if (eng_sdpa_smem(s->seq_len, a.head_dim, n_rep) > (size_t)ENG_WORK) return no("SequenceLength too long for the in-engine attention phase");
+  int ch, nt;
+  if (s->mode == LNB_ACC_STRICT && !eng_scan_shape(a.dim, &ch, &nt)) return no("dim does not fit the engine's binade scan");
+  if (m->kv_l / a.head_dim > m->sm_count) return no("more KV heads than SMs");
+  int occ = 0;
+  cudaError_t ce;
+  if (s->mode == LNB_ACC_STRICT) {
+    ce = cudaFuncSetAttribute(decode_engine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENG_SMEM);
+    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_engine_kernel<1>, ENG_THREADS, ENG_SMEM);
+  } else {
+    ce = cudaFuncSetAttribute(decode_engine_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENG_SMEM);
+    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_engine_kernel<8>, ENG_THREADS, ENG_SMEM);
+  }
+  if (ce != cudaSuccess || occ < 1) { cudaGetLastError(); return no("the engine kernel does not fit an SM"); }
+  if (cudaMalloc((void**)&s->d_bar, 256) != cudaSuccess) { cudaGetLastError(); return no("cudaMalloc"); }
+  s->eng_state = 1;
+  return true;
+}
+// the engine needs the peer all-reduce under tensor parallelism (NCCL calls cannot be issued from inside a kernel)
+static bool engine_ok(lnb_session* s) { return engine_probe(s) && (s->m->tp_size == 1 || s->p2p_ready); }
+
+static int eng_kt(int mode, int N, int K, int G) {
+  if (mode != LNB_ACC_STRICT) return std::min(256, K);
+  const int per = (N / 8 + G - 1) / G;                      // most panels one CTA owns
+  const int maxp = std::max(1, std::min(32, per));
+  int kt = (EngCfg<1>::kStage / (maxp * 16)) / 32 * 32;     // multiple of 32: whole groups of 4 chunks
+  kt = std::max(32, std::min(512, kt));
+  return std::min(kt, K);
+}
+// kind -1: the full step; 0..4: `reps` independent copies of one projection of every layer (kernel-alone timing)
+static int engine_build(lnb_session* s, int kind, const float* logits_out) {
+  lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  const int n_layers = (s->layer_limit > 0 && s->layer_limit < a.n_layers) ? s->layer_limit : a.n_layers;
+  if (s->d_phases && s->eng_key_seq == s->active_seq && s->eng_key_layers == n_layers && s->eng_key_kind == kind &&
+      s->eng_key_logits == logits_out)
+    return 0;
+  const int G = m->sm_count, mode = s->mode;
+  const size_t cache_off = (size_t)s->active_seq * s->seq_len * m->kv_l;
+  std::vector<EnginePhase> ph;
+  auto gemv = [&](int pro, int epi, const uint16_t* W, int N, int K, const uint16_t* x, const uint16_t* norm_w, uint16_t* out, int ldo,
+                  const uint16_t* res) {
+    EnginePhase e{};
+    e.type = EP_GEMV; e.pro = pro; e.epi = epi; e.W = W; e.N = N; e.K = K; e.kt = eng_kt(mode, N, K, G); e.x = x; e.ldx = K;
+    e.norm_w = norm_w; e.out_bf16 = out; e.ldo = ldo; e.res = res;
+    return e;
+  };
+  const bool tp = m->tp_size > 1;
+  for (int l = 0; l < n_layers; l++) {
+    LayerW& W = m->layers[l];
+    if (kind < 0 || kind == 0) {  // attn_norm -> wq|wk|wv -> RoPE -> KV append
+      EnginePhase e = gemv(PRO_RMSNORM, EPI_QKV_ROPE, W.wqkv, m->q_l + 2 * m->kv_l, a.dim, s->x, W.attn_norm, s->q, m->q_l, nullptr);
+      e.q_dim = m->q_l; e.kv_dim = m->kv_l; e.cache_k = s->ck[l] + cache_off; e.cache_v = s->cv[l] + cache_off;
+      if (kind < 0 && l == 0) e.flags |= EF_X_TOKEN;
+      ph.push_back(e);
+    }
+    if (kind < 0) {
+      EnginePhase e{};
+      e.type = EP_SDPA; e.q = s->q; e.o = s->o; e.kv_dim = m->kv_l; e.q_dim = m->q_l;
+      e.cache_k = s->ck[l] + cache_off; e.cache_v = s->cv[l] + cache_off;
+      ph.push_back(e);
+    }
+    if (kind < 0 || kind == 1) {  // wo + residual
+      EnginePhase e = gemv(PRO_PLAIN, tp ? EPI_P2P : EPI_RESID, W.wo, a.dim, m->q_l, s->o, nullptr, s->h1, a.dim, s->x);
+      if (kind < 0 && l == 0) e.flags |= EF_RES_TOKEN;
+      if (kind < 0 && tp) e.flags |= EF_NO_SYNC;   // the reduce phase polls the peers' words itself: no grid barrier in between
+      ph.push_back(e);
+      if (tp) {
+        EnginePhase r{};
+        r.type = EP_REDUCE; r.res = s->x; r.out_bf16 = s->h1; r.flags = (kind < 0 && l == 0) ? EF_RES_TOKEN : 0;
+        ph.push_back(r);
+      }
+    }
+    if (kind < 0 || kind == 2)    // ffn_norm -> w1|w3 -> SiLU * up
+      ph.push_back(gemv(PRO_RMSNORM, EPI_SWIGLU, W.w13, 2 * m->ffn_l, a.dim, s->h1, W.ffn_norm, s->mbuf, m->ffn_l, nullptr));
+    if (kind < 0 || kind == 3) {  // w2 + residual
+      ph.push_back(gemv(PRO_PLAIN, tp ? EPI_P2P : EPI_RESID, W.w2, a.dim, m->ffn_l, s->mbuf, nullptr, s->x, a.dim, s->h1));
+      if (kind < 0 && tp) ph.back().flags |= EF_NO_SYNC;
+      if (tp) {
+        EnginePhase r{};
+        r.type = EP_REDUCE; r.res = s->h1; r.out_bf16 = s->x;
+        ph.push_back(r);
+      }
+    }
+  }
+  if (kind < 0 || kind == 4) {
+    const int reps = kind == 4 ? 4 : 1;
+    for (int i = 0; i < reps; i++) {
+      EnginePhase e = gemv(PRO_RMSNORM, EPI_LOGITS, m->output, m->vocab_l, a.dim, s->x, m->norm, nullptr, m->vocab_l, nullptr);
+      e.out_f32 = const_cast<float*>(logits_out); e.n_offset = m->tp_rank * m->vocab_l;
+      ph.push_back(e);
+    }
+    if (kind < 0 && tp) {
+      EnginePhase r{};
+      r.type = EP_ARGMAX;
+      ph.push_back(r);
+    }
+  }
+  if (kind >= 0)   // kernel-alone timing: outputs of a projection must not feed the next copy through the EPI_P2P path
+    for (auto& e : ph)
+      if (e.type == EP_GEMV && e.epi == EPI_P2P) e.epi = EPI_RESID;
+  if (kind >= 0) ph.erase(std::remove_if(ph.begin(), ph.end(), [](const EnginePhase& e) { return e.type != EP_GEMV; }), ph.end());
+  if ((int)ph.size() > s->phases_cap) {
+    cudaFree(s->d_phases);
+    s->d_phases = nullptr;
+    s->phases_cap = 0;
+    CU(cudaMalloc((void**)&s->d_phases, ph.size() * sizeof(EnginePhase)));
+    s->phases_cap = (int)ph.size();
+  }
+  CU(cudaStreamSynchronize(s->stream));   // a running engine may still read the old list
+  CU(cudaMemcpy(s->d_phases, ph.data(), ph.size() * sizeof(EnginePhase), cudaMemcpyHostToDevice));
+  s->n_phases = (int)ph.size();
+  s->eng_key_seq = s->active_seq; s->eng_key_layers = n_layers; s->eng_key_kind = kind; s->eng_key_logits = logits_out;
+  return 0;
+}
+// n_steps S=1 forwards in one launch; the first input token and position come from the device state (set_state_kernel)
+static int engine_launch(lnb_session* s, int n_steps, bool advance) {
+  lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  EngineParams P{};
+  P.phases = s->d_phases; P.n_phases = s->n_phases; P.n_steps = n_steps; P.st = s->st;
+  P.emb = m->tok_embd; P.dim = a.dim; P.head_dim = a.head_dim; P.n_rep = a.n_heads / a.n_kv_heads; P.seq_len = s->seq_len;
+  P.cis = m->cis; P.silu_tab = m->silu_tab; P.eps = a.norm_eps; P.attn_scale = attn_scale_bf16(a.head_dim);
+  P.strict = s->mode == LNB_ACC_STRICT ? 1 : 0;
+  P.tok_out = s->d_tok_out; P.bar_ctr = s->d_bar;
+  P.p2p = s->p2p; P.tp = m->tp_size;
+  P.timeout_ns = s->p2p.timeout_ns ? s->p2p.timeout_ns : 1500000000ull;
+  {
+    const char* e = getenv("LNB_P2P_TIMEOUT_MS");
+    if (e) P.timeout_ns = atol(e) > 0 ? (unsigned long long)atol(e) * 1000000ull : 0ull;
+  }
+  P.err_host = s->h_err;
+  P.advance = advance ? 1 : 0;
+  CU(cudaMemsetAsync(s->d_bar, 0, 4, s->stream));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(m->sm_count);
+  cfg.blockDim = dim3(ENG_THREADS);
+  cfg.dynamicSmemBytes = ENG_SMEM;
+  cfg.stream = s->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident (the grid barrier needs it), or the launch fails
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (s->mode == LNB_ACC_STRICT) CU(cudaLaunchKernelEx(&cfg, decode_engine_kernel<1>, P));
+  else CU(cudaLaunchKernelEx(&cfg, decode_engine_kernel<8>, P));
+  s->launches++;
+  return 0;
+}
+// after a failed stream sync: did the engine trap, and why?
+static int engine_fault(lnb_session* s, cudaError_t e) {
+  const uint32_t c = s->h_err ? *s->h_err : 0u;
+  if ((c >> 28) == 0x8u)
+    return fail(LNB_ETIMEOUT, "peer all-reduce timed out inside the decode engine: rank %d never received the words of rank %u for "
+                "all-reduce #%u (a peer is late or dead); the kernel trapped, this process's CUDA context is gone (%s)",
+                s->m->tp_rank, c & 15u, (c >> 4) & 0xffffffu, cudaGetErrorString(e));
+  if ((c >> 28) == 0xCu) return fail(LNB_ECUDA, "decode engine: a CTA never reached grid barrier target %u (%s)", c & 0xffffffu, cudaGetErrorString(e));
+  if ((c >> 28) == 0xDu) return fail(LNB_ECUDA, "decode engine: weight stage %u never completed (%s)", c & 0xffffffu, cudaGetErrorString(e));
+  return fail(LNB_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
+}
+
+static int sync_stream(lnb_session* s) {
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return engine_fault(s, e);
+  return 0;
+}
+// one S=1 forward through the engine; the token travels in the device state (set_state_kernel)
+static int enqueue_decode_engine(lnb_session* s, int32_t token, int start_pos, int n_steps, bool advance, bool reset_step, const float* logits_out) {
+  int rc = engine_build(s, -1, logits_out);
+  if (rc) return rc;
+  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, 1, token, reset_step ? 1 : 0);
+  s->launches++;
+  *s->h_err = 0;
+  return engine_launch(s, n_steps, advance);
 }
 
 // Enqueue one LlamaTransformer.Forward (llamatransformer.go:145-180) for S rows on the
@@ -1590,12 +1800,20 @@ extern "C" int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int sta
     int rc = ensure_logits(s, (size_t)(all_rows ? s->max_rows : 1));
     if (rc) return rc;
   }
-  memcpy(s->h_pin, tokens, (size_t)S * 4);
-  CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)S * 4, cudaMemcpyHostToDevice, s->stream));
-  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, S, -1, 0);
-  s->launches++;
-  int rc = forward_tc_ok(s, S) ? enqueue_forward_tc(s, S, lrows) : enqueue_forward(s, S, false, lrows, false, true);
-  if (rc) return rc;
+  int rc;
+  if (S == 1 && engine_ok(s)) {
+    // decode step: ONE persistent kernel; the token id rides in the launch of set_state_kernel (4 bytes of kernel arguments)
+    if ((rc = enqueue_decode_engine(s, tokens[0], start_pos, 1, false, false, lrows ? s->logits : nullptr))) return rc;
+    if (lrows && m->tp_size > 1)
+      NC(g_nccl.AllGather(s->logits, s->logits_full, m->vocab_l, ncclFloat32_, m->comm, s->stream));
+  } else {
+    memcpy(s->h_pin, tokens, (size_t)S * 4);
+    CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)S * 4, cudaMemcpyHostToDevice, s->stream));
+    set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, S, -1, 0);
+    s->launches++;
+    rc = forward_tc_ok(s, S) ? enqueue_forward_tc(s, S, lrows) : enqueue_forward(s, S, false, lrows, false, true);
+    if (rc) return rc;
+  }
   if (lrows) {
     const float* src = (m->tp_size > 1) ? s->logits_full : s->logits;
     CU(cudaMemcpyAsync(logits, src, (size_t)lrows * m->a.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -1603,8 +1821,7 @@ extern "C" int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int sta
   int32_t* tokpin = s->h_pin + s->max_rows;
   if (argmax_last) CU(cudaMemcpyAsync(tokpin, &s->st->next_token, 4, cudaMemcpyDeviceToHost, s->stream));
   if ((rc = p2p_err_enqueue(s))) return rc;
-  CU(cudaStreamSynchronize(s->stream));
-  CU(cudaGetLastError());
+  if ((rc = sync_stream(s))) return rc;
   if ((rc = p2p_err_check(s))) return rc;
   if (argmax_last) *argmax_last = *tokpin;
   return 0;
@@ -1633,18 +1850,21 @@ extern "C" int lnb_forward_device(lnb_session* s, const int32_t* tokens, int S, 
   CU(cudaSetDevice(m->device));
   int rc = ensure_logits(s, (size_t)(rows_kept > 1 ? s->max_rows : 1));
   if (rc) return rc;
-  memcpy(s->h_pin, tokens, (size_t)S * 4);
-  CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)S * 4, cudaMemcpyHostToDevice, s->stream));
-  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, S, -1, 0);
-  s->launches++;
   s->kept_rows = 0;
-  rc = forward_tc_ok(s, S) ? enqueue_forward_tc(s, S, rows_kept, false) : enqueue_forward(s, S, false, rows_kept, false, true, false, false);
-  if (rc) return rc;
+  if (S == 1 && engine_ok(s)) {
+    if ((rc = enqueue_decode_engine(s, tokens[0], start_pos, 1, false, false, s->logits))) return rc;
+  } else {
+    memcpy(s->h_pin, tokens, (size_t)S * 4);
+    CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)S * 4, cudaMemcpyHostToDevice, s->stream));
+    set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, S, -1, 0);
+    s->launches++;
+    rc = forward_tc_ok(s, S) ? enqueue_forward_tc(s, S, rows_kept, false) : enqueue_forward(s, S, false, rows_kept, false, true, false, false);
+    if (rc) return rc;
+  }
   int32_t* tokpin = s->h_pin + s->max_rows;
   CU(cudaMemcpyAsync(tokpin, &s->st->next_token, 4, cudaMemcpyDeviceToHost, s->stream));
   if ((rc = p2p_err_enqueue(s))) return rc;
-  CU(cudaStreamSynchronize(s->stream));
-  CU(cudaGetLastError());
+  if ((rc = sync_stream(s))) return rc;
   if ((rc = p2p_err_check(s))) return rc;
   if (argmax_last) *argmax_last = *tokpin;
   s->kept_last_token = *tokpin;
@@ -1804,6 +2024,24 @@ extern "C" int lnb_decode_run(lnb_session* s, int32_t first_token, int start_pos
   if (first_token < 0 || first_token >= s->m->a.vocab_size) return fail(LNB_EINVAL, "token id %d out of range", first_token);
   std::lock_guard<std::mutex> lk(s->mu);
   CU(cudaSetDevice(s->m->device));
+  if (engine_ok(s)) {
+    // the whole run is ONE launch of the persistent engine: n_steps forwards, the greedy token fed back on the device
+    int rc = engine_build(s, -1, nullptr);
+    if (rc) return rc;
+    set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, start_pos, 1, first_token, 1);
+    s->launches++;
+    *s->h_err = 0;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = engine_launch(s, n_steps, true))) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaMemcpyAsync(s->h_pin + s->max_rows + 8, s->d_tok_out, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, s->stream));
+    if ((rc = sync_stream(s))) return rc;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    if (ms_out) *ms_out = ms;
+    if (tokens_out) memcpy(tokens_out, s->h_pin + s->max_rows + 8, (size_t)n_steps * 4);
+    return use_graph ? 1 : 0;   // (no graph is needed: there is nothing left to replay)
+  }
   if (use_graph && !s->graph && !s->graph_tried) {
     s->graph_tried = true;
     cudaGraph_t g = nullptr;
@@ -1868,6 +2106,36 @@ extern "C" int lnb_session_bench_kernel(lnb_session* s, int kind, int reps, floa
   lnb_model* m = s->m;
   const lnb_model_args& a = m->a;
   CU(cudaSetDevice(m->device));
+  if (engine_ok(s)) {
+    // the projection as the decode step runs it: a phase of the persistent engine (balanced static row split, weights
+    // prefetched across the grid barrier).  One launch walks all layers' copies `reps` times; time per phase.
+    int rc = engine_build(s, kind, nullptr);
+    if (rc) return rc;
+    set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, 0, 1, 0, 0);
+    *s->h_err = 0;
+    if ((rc = engine_launch(s, 1, false))) return rc;     // warm-up sweep
+    set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, 0, 1, 0, 0);
+    CU(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = engine_launch(s, reps, false))) return rc;
+    CU(cudaEventRecord(s->ev1, s->stream));
+    if ((rc = sync_stream(s))) return rc;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    const int n = s->n_phases * reps;
+    int64_t bytes = 0;
+    switch (kind) {
+      case 0: bytes = (int64_t)(m->q_l + 2 * m->kv_l) * a.dim * 2; break;
+      case 1: bytes = (int64_t)a.dim * m->q_l * 2; break;
+      case 2: bytes = (int64_t)2 * m->ffn_l * a.dim * 2; break;
+      case 3: bytes = (int64_t)a.dim * m->ffn_l * 2; break;
+      default: bytes = (int64_t)m->vocab_l * a.dim * 2; break;
+    }
+    if (ms_per_launch) *ms_per_launch = ms / (float)n;
+    if (bytes_per_launch) *bytes_per_launch = bytes;
+    if (launches) *launches = n;
+    s->eng_key_kind = -2;   // the next decode call rebuilds the step's phase list
+    return 0;
+  }
   Launcher L{s->stream, true, &s->launches};
   set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, 0, 1, 0, 0);
   int n_launch = 0;

@@ -27,8 +27,9 @@
 // Shared memory: 1 KB header (mbarriers, scalars, the phase's GemvParams) + 128 KB weight ring + 84 KB work area
 // (the activation vector as f32 / the attention phase's K, V, scores).
 //
-// Everything that can wait on another CTA or another GPU is bounded: grid barrier and peer waits give up after
-// timeout_ns, set the sticky LnbDevState.ar_error and make every loop of the CTA (producer included) fall through.
+// Everything that can wait on another CTA or another GPU is bounded: grid barrier, stage barriers and peer waits give up
+// after (a multiple of) timeout_ns, write the reason to a host-mapped word and trap -- a late or dead rank becomes an
+// error on its peers (LNB_ETIMEOUT / LNB_ECUDA with the reason in lnb_last_error), never a hung GPU.
 #pragma once
 #include "gemv.cuh"
 #include "kernels.cuh"
@@ -75,6 +76,7 @@ struct EngineParams {
   LnbP2P p2p;
   int tp;
   unsigned long long timeout_ns;
+  volatile uint32_t* err_host;   // host-mapped word: why the engine trapped (see eng_fail)
   int advance;              // 1: decode-loop bookkeeping (tok_out[step], st->pos / st->step advance)
 };
 
@@ -103,11 +105,20 @@ __host__ __device__ inline size_t eng_sdpa_smem(int T_max, int hd, int n_rep) {
 }
 
 struct EngCtl {            // in the header, after the barriers
-  volatile int abort_flag;
   int pos;
   int tok;
-  int pad;
 };
+
+// Fatal, loud, never a hang: the reason goes to a host-mapped word (readable after the context died), then trap.
+// codes: 0xC0000000 | barrier target  = a CTA never reached a grid barrier;  0xD0000000 | stage  = a weight tile never
+// arrived / was never released;  0x80000000 | epoch << 4 | rank  = a tensor-parallel peer never delivered (common.cuh).
+LNB_DEVINL void eng_fail(volatile uint32_t* err_host, uint32_t code) {
+  if (err_host) {
+    *err_host = code;
+    __threadfence_system();
+  }
+  __trap();
+}
 
 LNB_DEVINL uint32_t ld_acquire_u32(const unsigned int* p) {
   uint32_t v;
@@ -118,39 +129,46 @@ LNB_DEVINL uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const u
 LNB_DEVINL uint32_t ldcg_u32(const void* p) { return __ldcg(reinterpret_cast<const unsigned int*>(p)); }
 LNB_DEVINL uint16_t ldcg_u16(const void* p) { return __ldcg(reinterpret_cast<const unsigned short*>(p)); }
 
-// bounded mbarrier wait: false when the CTA is aborting
-LNB_DEVINL bool eng_mbar_wait(uint64_t* bar, uint32_t parity, EngCtl* ctl, bool backoff) {
+// bounded mbarrier wait (a stage that never completes is a bug or a dead copy engine: trap instead of hanging the GPU)
+LNB_DEVINL void eng_mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* err_host, unsigned long long timeout_ns, bool backoff,
+                              uint32_t what) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (backoff) __nanosleep(LNB_BACKOFF_NS);
-    if ((++spins & 255u) == 0u && ctl->abort_flag) return false;
+    if ((++spins & 4095u) == 0u && timeout_ns) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4 * timeout_ns) eng_fail(err_host, 0xD0000000u | (what & 0xffffffu));
+    }
   }
-  return true;
 }
 
 // Grid barrier among the consumers of all CTAs (the producer warps never take part).  Called by all ENG_NCONS
-// consumer threads; `target` = barriers so far * gridDim.x.  Returns false on abort / timeout.
-LNB_DEVINL bool eng_grid_barrier(const EngineParams& P, EngCtl* ctl, unsigned int target, int c) {
+// consumer threads; `target` = barriers so far * gridDim.x.
+LNB_DEVINL void eng_grid_barrier(const EngineParams& P, unsigned int target, int c) {
   named_bar_sync(1, ENG_NCONS);
   if (c == 0) {
     __threadfence();
     atomicAdd(P.bar_ctr, 1u);
-    const unsigned long long t0 = global_timer_ns();
+    unsigned long long t0 = 0;
     uint32_t spins = 0;
     while (ld_acquire_u32(P.bar_ctr) < target) {
-      if ((++spins & 127u) == 0u) {
-        if (*reinterpret_cast<volatile uint32_t*>(&P.st->ar_error)) { ctl->abort_flag = 1; break; }
-        if (P.timeout_ns && global_timer_ns() - t0 > P.timeout_ns) {
-          atomicCAS(&P.st->ar_error, 0u, 0xC0000000u | (target & 0xffffffu));   // 0xC...: grid barrier (a CTA is missing)
-          ctl->abort_flag = 1;
-          break;
-        }
+      if ((++spins & 1023u) == 0u && P.timeout_ns) {
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2 * P.timeout_ns) eng_fail(P.err_host, 0xC0000000u | (target & 0xffffffu));
       }
     }
     __threadfence();
   }
   named_bar_sync(1, ENG_NCONS);
-  return ctl->abort_flag == 0;
+}
+// peer wait inside the engine: the bounded wait of common.cuh, fatal on timeout
+LNB_DEVINL uint2 eng_wait_word(const EngineParams& P, const uint2* src, uint32_t epoch, int r, unsigned long long t0) {
+  uint2 w;
+  if (!p2p_wait_word(src, epoch, r, P.p2p, P.st, t0, &w)) eng_fail(P.err_host, 0x80000000u | ((epoch & 0xffffffu) << 4) | (uint32_t)(r & 15));
+  return w;
 }
 
 // ---- LNB_ACC_STRICT RMSNorm sum of squares: the one-pass binade scan of seqsum.cuh (rms_scale_seg_kernel) for the
@@ -324,7 +342,6 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
       mbar_init(&empty_bar[s], ENG_NCONS / 32);
     }
     mbar_fence_init();
-    ctl->abort_flag = 0;
   }
   __syncthreads();
 
@@ -347,7 +364,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             for (int t = 0; t < n_tiles; t++, seq++) {
               const int s = seq % NST;
               const uint32_t par = (seq / NST) & 1u;
-              if (!eng_mbar_wait(&empty_bar[s], par ^ 1u, ctl, false)) return;
+              eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
               const int k0 = t * kt;
               const uint32_t bytes_per_panel = (uint32_t)min(kt, K - k0) * 16u;
               mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)np);
@@ -461,7 +478,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
               const uint32_t par = (seq / NST) & 1u;
               // warps without rows in this tile only keep the ring moving: wait politely
               const bool warp_on = (KS == 1) ? ((cw * 4) < np) : true;
-              if (!eng_mbar_wait(&full_bar[s], par, ctl, !warp_on)) return;
+              eng_mbar_wait(&full_bar[s], par, P.err_host, P.timeout_ns, !warp_on, seq);
               const int k0 = t * kt;
               const int nchunks = min(kt, K - k0) / 8;
               if (row_on) {
@@ -640,20 +657,17 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         // ---- peer all-reduce of the partials the previous phase pushed: out = t(res + t(p0 + p1 + ...)), rank order ----
         const int per = (P.dim + G - 1) / G;
         const int i = bid * per + c;
-        bool ok = true;
         if (c < per && i < P.dim) {
           const unsigned long long t0 = global_timer_ns();
           const uint2* base = P.p2p.data[P.p2p.rank] + (size_t)(epoch & 1u) * P.p2p.n * P.p2p.slot_elems;
           float sum = 0.f;
           for (int rk = 0; rk < P.p2p.n; rk++) {
-            uint2 w;
-            if (!p2p_wait_word(base + (size_t)rk * P.p2p.slot_elems + i, epoch, rk, P.p2p, P.st, t0, &w)) { ok = false; break; }
+            const uint2 w = eng_wait_word(P, base + (size_t)rk * P.p2p.slot_elems + i, epoch, rk, t0);
             sum = (rk == 0) ? __uint_as_float(w.x) : __fadd_rn(sum, __uint_as_float(w.x));
           }
           const uint16_t* resp = (E->flags & EF_RES_TOKEN) ? P.emb + (size_t)tok * P.dim : E->res;
-          if (ok) E->out_bf16[i] = f2bf(__fadd_rn(bf2f(ldcg_u16(resp + i)), trunc_bf(sum)));
+          E->out_bf16[i] = f2bf(__fadd_rn(bf2f(ldcg_u16(resp + i)), trunc_bf(sum)));
         }
-        if (!ok) ctl->abort_flag = 1;
         epoch++;
       } else if (type == EP_ARGMAX) {
         // ---- tensor-parallel greedy argmax: CTA 0 pushes this rank's key to every peer; every CTA takes the max ----
@@ -667,14 +681,11 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         }
         if (c < 32) {
           unsigned long long key = LNB_ARGMAX_EMPTY;
-          bool ok = true;
           if (c < P.p2p.n) {
             const uint2* src = P.p2p.data[P.p2p.rank] + ((size_t)((epoch & 1u) * P.p2p.n + c)) * P.p2p.slot_elems;
-            uint2 lo = make_uint2(0, 0), hi = make_uint2(0, 0);
-            ok = p2p_wait_word(src, epoch, c, P.p2p, P.st, t0, &lo) && p2p_wait_word(src + 1, epoch, c, P.p2p, P.st, t0, &hi);
+            const uint2 lo = eng_wait_word(P, src, epoch, c, t0), hi = eng_wait_word(P, src + 1, epoch, c, t0);
             key = ((unsigned long long)hi.x << 32) | lo.x;
           }
-          if (__any_sync(0xffffffffu, !ok)) ctl->abort_flag = 1;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
@@ -684,13 +695,12 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         }
         epoch++;
         named_bar_sync(1, ENG_NCONS);
-        if (ctl->abort_flag) return;
         tok = ctl->tok;
         continue;                                  // purely local result: no grid barrier
       }
       // ---- end of phase: everybody's outputs become visible to everybody ----------------------------------------
       n_bar++;
-      if (!eng_grid_barrier(P, ctl, n_bar * (unsigned int)G, c)) return;
+      eng_grid_barrier(P, n_bar * (unsigned int)G, c);
       if (key_reset_due) {                         // every CTA has read the previous step's key by now
         if (bid == 0 && c == 0) P.st->amax_key = LNB_ARGMAX_EMPTY;
         key_reset_due = false;
@@ -707,9 +717,8 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
   }
   if (bid == 0 && c == 0) {
     // n_bar >= 1 barriers have passed since any CTA read the state at the top
-    P.st->next_token = tok;
-    P.st->amax_key = LNB_ARGMAX_EMPTY;
-    P.st->done_ctr = 0;
+    P.st->next_token = tok;      // (amax_key is reset by set_state_kernel / at the start of the next launch: other CTAs may
+    P.st->done_ctr = 0;          //  still be reading it here)
     if (P.tp > 1) P.st->ar_epoch = epoch;
     if (P.advance) {
       P.st->step += P.n_steps;

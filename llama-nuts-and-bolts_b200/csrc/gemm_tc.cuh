@@ -326,8 +326,8 @@ __global__ void rope_kv_kernel(const uint16_t* __restrict__ qkv, int ld, uint16_
   }
 }
 
-// After the fused w1|w3 GEMM (columns follow the panel-interleaved row order of the stacked matrix:
-// 16 gate columns, then the 16 up columns of the same rows): m = t( t(TABLE_SILU[g]) * u )
+// After the fused w1|w3 GEMM (columns follow the half-panel interleave of the stacked matrix:
+// 4 gate columns, then the 4 up columns of the same hidden units): m = t( t(TABLE_SILU[g]) * u )
 // (llamatransformer.go:601-614), written in X8 layout for the w2 GEMM.  Rows in [M, Mpad) -> 0.
 __global__ void swiglu_x8_kernel(const uint16_t* __restrict__ gu, int ld, const uint16_t* __restrict__ silu_tab,
                                  uint16_t* __restrict__ out_x8, int M, int Mpad, int ffn) {
@@ -338,9 +338,9 @@ __global__ void swiglu_x8_kernel(const uint16_t* __restrict__ gu, int ld, const 
     const int row = (int)(i / ffn), c = (int)(i % ffn);
     uint16_t o = 0;
     if (row < M) {
-      const size_t base = (size_t)row * ld + (size_t)(c >> 4) * 32 + (c & 15);
+      const size_t base = (size_t)row * ld + (size_t)(c >> 2) * 8 + (c & 3);
       const uint16_t sg = silu_tab[gu[base]];
-      o = f2bf(__fmul_rn(bf2f(sg), bf2f(gu[base + 16])));
+      o = f2bf(__fmul_rn(bf2f(sg), bf2f(gu[base + 4])));
     }
     out_x8[x8_index(row, c, ffn)] = o;
   }

@@ -74,6 +74,7 @@ struct GemvParams {
   const int32_t* pos_ptr;  // == &st->pos (kept separate so op-level calls can pass a plain int buffer)
   int m_off;               // index of activation row 0 of this launch inside the forward call (row blocking)
   LnbP2P p2p;              // EPI_P2P: peer regions (st must be set: epoch / done counters live in the device state)
+  uint32_t ar_epoch_override;  // EPI_P2P inside the persistent engine: the epoch is tracked per CTA, not in st (0: use st)
 };
 
 template <int TN, int KS, int MB, int KT, int NST>
@@ -107,7 +108,7 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
     if (valid) p.out_f32[(size_t)em * p.ldo + n] = v;
   } else if (EPI == EPI_P2P) {
     if (valid) {
-      const uint32_t epoch = p.st->ar_epoch;
+      const uint32_t epoch = p.ar_epoch_override ? p.ar_epoch_override : p.st->ar_epoch;   // epochs start at 1
       const size_t off = ((size_t)((epoch & 1u) * p.p2p.n + p.p2p.rank)) * p.p2p.slot_elems + (size_t)(p.m_off + em) * p.ldo + n;
       const uint2 w = make_uint2(__float_as_uint(v), epoch);
 #pragma unroll
@@ -164,15 +165,15 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
       }
     }
   } else if (EPI == EPI_SWIGLU) {
-    // the stacked w1|w3 matrix alternates 16 gate rows (two panels) with the same 16 up rows (next two
-    // panels); `panel` = first panel of this row; the partner of tile row er (er % 32 < 16) is er + 16 ==
-    // lane + 16 of the same warp
+    // every panel of the stacked w1|w3 matrix holds the gate rows of hidden units 4*panel .. 4*panel+3 in its rows
+    // 0..3 and their up rows in rows 4..7 (retile_kernel, dpanel_stride == 2); `panel` = the panel of this row; the
+    // partner of tile row er (er % 8 < 4) is er + 4 == lane + 4 of the same warp
     const float mine = trunc_bf(v);
-    const float up = __shfl_down_sync(0xffffffffu, mine, 16);
-    if (valid && (er & 16) == 0) {
+    const float up = __shfl_down_sync(0xffffffffu, mine, 4);
+    if (valid && (er & 4) == 0) {
       const uint16_t sg = p.silu_tab[f2bf(mine)];                       // t(TABLE_SILU[bits]) activations.go:38
       const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
-      p.out_bf16[(size_t)em * p.ldo + (size_t)(panel >> 2) * 16 + (er & 15)] = f2bf(mm);
+      p.out_bf16[(size_t)em * p.ldo + (size_t)panel * 4 + (er & 3)] = f2bf(mm);
     }
   }
 }

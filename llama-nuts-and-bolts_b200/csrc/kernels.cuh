@@ -8,10 +8,16 @@ namespace lnb {
 
 // ------------------------------------------------------------------------------------------
 // Upload-time layout change: row-major W[rows x ld] (a [row0.., col0..] window of it) ->
-// panel-major (8-row panels, see gemv.cuh).  Source panel q lands in destination panel
-// dpanel0 + (q / 2) * 2 * dpanel_stride + (q % 2): dpanel_stride == 1 keeps the order; w1 / w3 use
-// stride 2 with dpanel0 = 0 / 2 so that 16 gate rows alternate with the same 16 up rows (fused SwiGLU).
+// panel-major (8-row panels, see gemv.cuh).  dpanel_stride == 1: source row i lands in destination row
+// dpanel0 * 8 + i (wq | wk | wv stacked).  dpanel_stride == 2: the w1 | w3 half-panel interleave of the fused
+// SwiGLU -- panel p holds the GATE rows of hidden units 4p..4p+3 (w1, dpanel0 == 0) in its rows 0..3 and their UP
+// rows (w3, dpanel0 != 0) in rows 4..7, so that gate and up of one unit always meet inside one warp (lane, lane + 4)
+// whatever panel range a CTA owns (the persistent engine splits rows at single-panel granularity).
 // One thread moves one 16-byte chunk (8 bf16).
+LNB_DEVINL int64_t panel_dest_row(int64_t row, int dpanel0, int dpanel_stride) {
+  if (dpanel_stride == 2) return (row >> 2) * 8 + (dpanel0 ? 4 : 0) + (row & 3);
+  return (int64_t)dpanel0 * 8 + row;
+}
 __global__ void retile_kernel(const uint16_t* __restrict__ src, int64_t ld, int64_t row0, int64_t col0, int rows,
                               int K, uint16_t* __restrict__ dst, int dpanel0, int dpanel_stride) {
   const int64_t chunks_per_row = K / 8;
@@ -19,8 +25,8 @@ __global__ void retile_kernel(const uint16_t* __restrict__ src, int64_t ld, int6
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / chunks_per_row, ch = i % chunks_per_row;
     const uint4 v = *reinterpret_cast<const uint4*>(src + (row0 + row) * ld + col0 + ch * 8);
-    const int64_t q = row / 8, rr = row % 8;
-    const int64_t dp = dpanel0 + (q / 2) * 2 * dpanel_stride + (q % 2);
+    const int64_t d = panel_dest_row(row, dpanel0, dpanel_stride);
+    const int64_t dp = d / 8, rr = d % 8;
     *reinterpret_cast<uint4*>(dst + ((dp * chunks_per_row + ch) * 8 + rr) * 8) = v;
   }
 }
@@ -32,8 +38,8 @@ __global__ void untile_kernel(const uint16_t* __restrict__ src, int rows, int K,
   const int64_t total = (int64_t)rows * chunks_per_row;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / chunks_per_row, ch = i % chunks_per_row;
-    const int64_t q = row / 8, rr = row % 8;
-    const int64_t sp = spanel0 + (q / 2) * 2 * spanel_stride + (q % 2);
+    const int64_t d = panel_dest_row(row, spanel0, spanel_stride);
+    const int64_t sp = d / 8, rr = d % 8;
     *reinterpret_cast<uint4*>(dst + row * K + ch * 8) =
         *reinterpret_cast<const uint4*>(src + ((sp * chunks_per_row + ch) * 8 + rr) * 8);
   }
@@ -64,8 +70,8 @@ __global__ void synth_fill_kernel(uint64_t seed, float scale, float offset, int6
     const int64_t row = i / K, col = i % K;
     const uint16_t v = synth_value(seed, (uint64_t)((row0 + row) * ld + col0 + col), scale, offset);
     if (panel_major) {
-      const int64_t q = row / 8, rr = row % 8, ch = col / 8, e = col % 8;
-      const int64_t dp = dpanel0 + (q / 2) * 2 * dpanel_stride + (q % 2);
+      const int64_t d = panel_dest_row(row, dpanel0, dpanel_stride);
+      const int64_t dp = d / 8, rr = d % 8, ch = col / 8, e = col % 8;
       dst[((dp * (K / 8) + ch) * 8 + rr) * 8 + e] = v;
     } else {
       dst[i] = v;

@@ -52,6 +52,7 @@ for mode, acc, p2p in (("strict", L._capi.LNB_ACC_STRICT, False), ("fast", L._ca
     ctx = L.model.InferenceContext(m.Transformer, L.model.InferenceArgs(24), max_rows=8, acc_mode=acc)
     if p2p:
         ctx.enable_peer_allreduce(all_gather_bytes)
+        ctx.pre_close_hook = lambda c: (torch.cuda.synchronize(), dist.barrier())   # peers may still store into this rank's region
     prompt = np.array([5, 900, 33, 7, 64], np.int32) % args["vocab_size"]
     outs, pos, cur = [], 0, prompt
     for _ in range(5):
@@ -94,6 +95,7 @@ for mode, acc, p2p in (("strict", L._capi.LNB_ACC_STRICT, False), ("fast", L._ca
     bctx = L.model.InferenceContext(m.Transformer, L.model.InferenceArgs(24), max_rows=8, acc_mode=acc, n_seq=3)
     if p2p:
         bctx.enable_peer_allreduce(all_gather_bytes)
+        bctx.pre_close_hook = lambda c: (torch.cuda.synchronize(), dist.barrier())
     prompts = [np.array(q, np.int32) % args["vocab_size"] for q in ([5, 900, 33], [1, 2, 3, 4, 5, 6], [77])]
     cur, bpos, steps = [], [], []
     for i, q in enumerate(prompts):
