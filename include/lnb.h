@@ -249,6 +249,9 @@ enum { LNB_BUF_RESIDUAL = 0, LNB_BUF_CACHE_K = 1, LNB_BUF_CACHE_V = 2, LNB_BUF_L
  * [seq_len, n_kv_local, head_dim] bf16, LOGITS [rows, vocab_local] f32. */
 int lnb_session_read(lnb_session* s, int which, int layer, void* host, int64_t nbytes);
 int lnb_session_set_layer_limit(lnb_session* s, int n_layers_to_run); /* <=0: all */
+/* profiling aid of the persistent decode engine (LNB_ENGINE_PROF=1 when the session first decodes): cycles of consumer
+ * thread 0 per section, {mean, max} over the CTAs, reset on read.  out[16]. */
+int lnb_session_engine_profile(lnb_session* s, double* out16);
 /* number of kernels launched by this session since creation (bench.py gpu_launches) */
 int64_t lnb_session_launch_count(lnb_session* s);
 int lnb_session_sync(lnb_session* s);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "lnb_session_p2p_export": (C.c_int, [vp, vp]),
     "lnb_session_p2p_import": (C.c_int, [vp, vp, C.c_int]),
     "lnb_session_p2p_disable": (C.c_int, [vp]),
+    "lnb_session_engine_profile": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "lnb_session_read": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64]),
     "lnb_session_set_layer_limit": (C.c_int, [vp, C.c_int]),
     "lnb_session_launch_count": (C.c_int64, [vp]),

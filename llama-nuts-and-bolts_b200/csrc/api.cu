@@ -1057,6 +1057,7 @@ struct lnb_session {
   EnginePhase* d_phases = nullptr;
   int n_phases = 0, phases_cap = 0;
   unsigned int* d_bar = nullptr;
+  unsigned long long* d_prof = nullptr;   // LNB_ENGINE_PROF=1: per-CTA cycle counters of the engine's consumer thread 0
   int eng_state = 0;             // 0 = not probed, 1 = usable, -1 = this session uses the kernel chain
   std::string eng_why;           // why not
   int eng_key_seq = -1, eng_key_layers = -1, eng_key_kind = -2;
@@ -1159,7 +1160,7 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   for (int r = 0; r < 8; r++)
     if (s->p2p_peer[r]) cudaIpcCloseMemHandle(s->p2p_peer[r]);
   cudaFree(s->p2p_region);
-  cudaFree(s->d_phases); cudaFree(s->d_bar);
+  cudaFree(s->d_phases); cudaFree(s->d_bar); cudaFree(s->d_prof);
   cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out); cudaFree(s->d_pos_arr); cudaFree(s->d_next_arr);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
@@ -1315,6 +1316,7 @@ static bool engine_probe(lnb_session* s) {
   const int kmax = std::max(a.dim, std::max(m->q_l, m->ffn_l));
   if ((size_t)kmax * 4 > (size_t)ENG_XMAX) return no("activation vector exceeds the engine's shared-memory work area");
   if (a.dim % 8 || m->q_l % 8 || m->ffn_l % 8) return no("widths must be multiples of 8");
+  if ((size_t)a.dim * 8 > (size_t)ENG_XMAX) return no("dim too wide for the engine's RMSNorm prologue");
   const int n_rep = a.n_heads / a.n_kv_heads;
   if (a.head_dim > 128 || a.head_dim % 8 || n_rep > 8) return no("head shape");
   if (eng_sdpa_smem(s->seq_len, a.head_dim, n_rep) > (size_t)ENG_WORK) return no("SequenceLength too long for the in-engine attention phase");
@@ -1332,6 +1334,14 @@ static bool engine_probe(lnb_session* s) {
   }
   if (ce != cudaSuccess || occ < 1) { cudaGetLastError(); return no("the engine kernel does not fit an SM"); }
   if (cudaMalloc((void**)&s->d_bar, 256) != cudaSuccess) { cudaGetLastError(); return no("cudaMalloc"); }
+  {
+    const char* pe = getenv("LNB_ENGINE_PROF");
+    if (pe && strcmp(pe, "0")) {
+      const size_t nb = (size_t)m->sm_count * ENG_NPROF * 8;
+      if (cudaMalloc((void**)&s->d_prof, nb) == cudaSuccess) cudaMemset(s->d_prof, 0, nb);
+      else { s->d_prof = nullptr; cudaGetLastError(); }
+    }
+  }
   s->eng_state = 1;
   return true;
 }
@@ -1339,11 +1349,13 @@ static bool engine_probe(lnb_session* s) {
 static bool engine_ok(lnb_session* s) { return engine_probe(s) && (s->m->tp_size == 1 || s->p2p_ready); }
 
 static int eng_kt(int mode, int N, int K, int G) {
-  if (mode != LNB_ACC_STRICT) return std::min(256, K);
   const int per = (N / 8 + G - 1) / G;                      // most panels one CTA owns
-  const int maxp = std::max(1, std::min(32, per));
-  int kt = (EngCfg<1>::kStage / (maxp * 16)) / 32 * 32;     // multiple of 32: whole groups of 4 chunks
-  kt = std::max(32, std::min(512, kt));
+  const int PT = mode == LNB_ACC_STRICT ? EngCfg<1>::kPT : EngCfg<8>::kPT;
+  const int maxp = std::max(1, std::min(PT, per));
+  // the largest of 512 / 256 / 128 / 64 whose tile (maxp panels x kt x 16 B) fits a 32 KB stage: few, large bulk copies, and
+  // k-tiles the STRICT chain can unroll completely (eng_chain_tile<NG>)
+  int kt = 512;
+  while (kt > 64 && maxp * kt * 16 > EngCfg<1>::kStage) kt >>= 1;
   return std::min(kt, K);
 }
 // kind -1: the full step; 0..4: `reps` independent copies of one projection of every layer (kernel-alone timing)
@@ -1449,6 +1461,12 @@ static int engine_launch(lnb_session* s, int n_steps, bool advance) {
     if (e) P.timeout_ns = atol(e) > 0 ? (unsigned long long)atol(e) * 1000000ull : 0ull;
   }
   P.err_host = s->h_err;
+  {
+    // L2 prefetch window per CTA: 148 x 256 KB = 37 MB of the 126 MB L2 by default (LNB_ENGINE_PF_KB, 0 = off)
+    static const int pf_kb = [] { const char* e = getenv("LNB_ENGINE_PF_KB"); return e ? atoi(e) : 256; }();
+    P.pf_window = pf_kb > 0 ? (unsigned int)pf_kb * 1024u : 0u;
+  }
+  P.prof = s->d_prof;
   P.advance = advance ? 1 : 0;
   CU(cudaMemsetAsync(s->d_bar, 0, 4, s->stream));
   cudaLaunchConfig_t cfg{};
@@ -2197,6 +2215,30 @@ extern "C" int lnb_session_bench_kernel(lnb_session* s, int kind, int reps, floa
   if (ms_per_launch) *ms_per_launch = ms / (float)n_launch;
   if (bytes_per_launch) *bytes_per_launch = bytes;
   if (launches) *launches = n_launch;
+  return 0;
+}
+
+// LNB_ENGINE_PROF=1: cycle sums of the engine's consumer thread 0, averaged and maximised over the CTAs, since the last
+// call; out[2 * 8] = {mean, max} x {grid barrier, prologue, main loop, combine + epilogue, attention, peer reduce, -, -}
+extern "C" int lnb_session_engine_profile(lnb_session* s, double* out16) {
+  if (!s || !out16) return fail(LNB_EINVAL, "NULL argument");
+  if (!s->d_prof) return fail(LNB_ESTATE, "no engine profile (set LNB_ENGINE_PROF=1 before the session's first decode)");
+  CU(cudaSetDevice(s->m->device));
+  CU(cudaStreamSynchronize(s->stream));
+  const int G = s->m->sm_count;
+  std::vector<unsigned long long> h((size_t)G * ENG_NPROF);
+  CU(cudaMemcpy(h.data(), s->d_prof, h.size() * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemset(s->d_prof, 0, h.size() * 8));
+  for (int k = 0; k < ENG_NPROF; k++) {
+    double sum = 0, mx = 0;
+    for (int b = 0; b < G; b++) {
+      const double v = (double)h[(size_t)b * ENG_NPROF + k];
+      sum += v;
+      mx = std::max(mx, v);
+    }
+    out16[2 * k] = sum / G;
+    out16[2 * k + 1] = mx;
+  }
   return 0;
 }
 

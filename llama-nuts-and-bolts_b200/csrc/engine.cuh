@@ -19,11 +19,13 @@
 //     same summation orders in both accumulation modes): the engine path and the kernel-chain path produce identical
 //     bits (tests/test_gpu_engine.py), and LNB_ACC_STRICT stays bit-identical to the oracle.
 //
-// Thread roles (288 threads): warp 0 = producer (lane 0 issues cp.async.bulk into an NST-stage ring), 256 consumers.
-//   LNB_ACC_FAST   (KS = 8): row tile = 4 panels (32 rows); consumer (r = c % 32, j = c / 32) = row r, k-stream j.
-//   LNB_ACC_STRICT (KS = 1): row tile = up to 32 panels; consumer c = row c of the tile, one sequential chain per row
-//                            (a CTA that owns <= 4 panels of a latency-bound projection runs ONE chain warp on its own
-//                            scheduler; the other consumer warps sleep on the stage barrier with nanosleep back-off).
+// Thread roles (288 threads): warp 0 = producer (every lane issues one panel's cp.async.bulk per stage of a 4 x 32 KB
+// ring), 256 consumers.
+//   LNB_ACC_FAST   (KS = 8): row tile = 8 panels (64 rows); consumer (r = c % 32, j = c / 32) owns rows r and r + 32 of the
+//                            tile (two independent accumulation chains per thread) in k-stream j.
+//   LNB_ACC_STRICT (KS = 1): row tile = up to 16 panels; consumer c < 128 = row c of the tile, one sequential chain per row,
+//                            the four chain warps sit on four different schedulers (a CTA that owns <= 4 panels of a
+//                            latency-bound projection runs ONE chain warp with its scheduler to itself).
 // Shared memory: 1 KB header (mbarriers, scalars, the phase's GemvParams) + 128 KB weight ring + 84 KB work area
 // (the activation vector as f32 / the attention phase's K, V, scores).
 //
@@ -77,6 +79,9 @@ struct EngineParams {
   int tp;
   unsigned long long timeout_ns;
   volatile uint32_t* err_host;   // host-mapped word: why the engine trapped (see eng_fail)
+  unsigned int pf_window;        // bytes of the weight stream each CTA keeps prefetched in L2 ahead of its ring (0: none)
+  unsigned long long* prof;      // NULL, or [gridDim.x][ENG_NPROF] cycle sums of consumer thread 0: 0 grid barrier, 1 prologue,
+                                 // 2 main loop (stage waits included), 3 combine + epilogue, 4 attention, 5 peer reduce / argmax
   int advance;              // 1: decode-loop bookkeeping (tok_out[step], st->pos / st->step advance)
 };
 
@@ -85,13 +90,17 @@ constexpr int ENG_THREADS = ENG_NCONS + 32;
 constexpr int ENG_RING = 128 * 1024;
 constexpr int ENG_WORK = 84 * 1024;
 constexpr int ENG_XMAX = 56 * 1024;                       // f32 activation vector: K <= 14336
-constexpr int ENG_PART_OFF = ENG_XMAX;                    // [8][32] f32 stream partials (FAST)
-constexpr int ENG_SCAN_OFF = ENG_XMAX + 1024;             // seg-scan scratch (STRICT RMSNorm), 4 KB
+constexpr int ENG_PART_OFF = ENG_XMAX;                    // [8][64] f32 stream partials (FAST), 2 KB
+constexpr int ENG_SCAN_OFF = ENG_XMAX + 2048;             // seg-scan scratch (STRICT RMSNorm), 4 KB
+constexpr int ENG_NPROF = 8;                              // per-CTA cycle counters (LNB_ENGINE_PROF): see EngineParams.prof
 constexpr int ENG_SMEM = 1024 + ENG_RING + ENG_WORK;
 template <int KS> struct EngCfg {
-  static constexpr int kNST = (KS == 1) ? 4 : 8;
-  static constexpr int kStage = ENG_RING / kNST;          // 32 KB / 16 KB
-  static constexpr int kPT = (KS == 1) ? 32 : 4;          // panels per row tile
+  static constexpr int kNST = 4;
+  static constexpr int kStage = ENG_RING / kNST;          // 32 KB
+  static constexpr int kPT = (KS == 1) ? 16 : 8;          // panels per row tile
+  // STRICT: consumer warps 0..3 are the chain warps (hardware warps 1..4 = one per scheduler); warps 4..7 only help with
+  // prologues / attention / reductions and park at the phase's closing barrier meanwhile (bar.sync costs no issue slots)
+  static constexpr int kChainWarps = (KS == 1) ? 4 : 8;
 };
 
 // host + device: panels [lo, hi) of a matrix with P panels owned by CTA b of G
@@ -147,10 +156,14 @@ LNB_DEVINL void eng_mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t*
 // Grid barrier among the consumers of all CTAs (the producer warps never take part).  Called by all ENG_NCONS
 // consumer threads; `target` = barriers so far * gridDim.x.
 LNB_DEVINL void eng_grid_barrier(const EngineParams& P, unsigned int target, int c) {
-  named_bar_sync(1, ENG_NCONS);
+  named_bar_sync(1, ENG_NCONS);                      // every consumer's stores happen-before thread 0's release
   if (c == 0) {
+#ifdef ENG_OLD_BARRIER
     __threadfence();
     atomicAdd(P.bar_ctr, 1u);
+#else
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.bar_ctr) : "memory");
+#endif
     unsigned long long t0 = 0;
     uint32_t spins = 0;
     while (ld_acquire_u32(P.bar_ctr) < target) {
@@ -160,7 +173,9 @@ LNB_DEVINL void eng_grid_barrier(const EngineParams& P, unsigned int target, int
         else if (now - t0 > 2 * P.timeout_ns) eng_fail(P.err_host, 0xC0000000u | (target & 0xffffffu));
       }
     }
+#ifdef ENG_OLD_BARRIER
     __threadfence();
+#endif
   }
   named_bar_sync(1, ENG_NCONS);
 }
@@ -317,6 +332,93 @@ __host__ __device__ inline bool eng_scan_shape(int D, int* ch, int* nt) {
   return false;
 }
 
+// One k-tile of NG groups of 4 chunks (NG * 32 elements) of ONE row's sequential accumulation chain: register
+// double-buffered like gemv.cuh's MB == 1 branch -- the LDS of group g+1 are in flight while the 32 dependent FMAs of
+// group g issue -- and fully unrolled (a run-time group loop left ptxas with two rotating temporaries and a chain that
+// ran at 12 cycles per element instead of 5).
+template <int NG>
+LNB_DEVINL float eng_chain_tile(const uint8_t* __restrict__ tile, const float* __restrict__ xt, float acc) {
+  uint4 wa[4], wb[4];
+  float4 xa0[4], xa1[4], xb0[4], xb1[4];
+#define ENG_LOAD(gi, W_, X0_, X1_)                                            \
+  _Pragma("unroll") for (int q_ = 0; q_ < 4; q_++) {                          \
+    const int ch_ = (gi) * 4 + q_;                                            \
+    W_[q_] = *reinterpret_cast<const uint4*>(tile + ch_ * 128);               \
+    X0_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8);                 \
+    X1_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8 + 4);             \
+  }
+#define ENG_FMA(W_, X0_, X1_)                                                 \
+  _Pragma("unroll") for (int q_ = 0; q_ < 4; q_++) {                          \
+    float a_ = acc;                                                           \
+    a_ = __fmaf_rn(X0_[q_].x, bf_lo(W_[q_].x), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].y, bf_hi(W_[q_].x), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].z, bf_lo(W_[q_].y), a_);                           \
+    a_ = __fmaf_rn(X0_[q_].w, bf_hi(W_[q_].y), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].x, bf_lo(W_[q_].z), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].y, bf_hi(W_[q_].z), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].z, bf_lo(W_[q_].w), a_);                           \
+    a_ = __fmaf_rn(X1_[q_].w, bf_hi(W_[q_].w), a_);                           \
+    acc = a_;                                                                 \
+  }
+  ENG_LOAD(0, wa, xa0, xa1)
+#pragma unroll
+  for (int gi = 0; gi < NG; gi += 2) {
+    if (gi + 1 < NG) { ENG_LOAD(gi + 1, wb, xb0, xb1) }
+    ENG_FMA(wa, xa0, xa1)
+    if (gi + 2 < NG) { ENG_LOAD(gi + 2, wa, xa0, xa1) }
+    if (gi + 1 < NG) { ENG_FMA(wb, xb0, xb1) }
+  }
+#undef ENG_LOAD
+#undef ENG_FMA
+  return acc;
+}
+
+// The producer's view of the weight stream: every (step, projection phase, row tile, k-tile) of this CTA, in order.
+// Two cursors walk it: the bulk-copy cursor feeds the shared-memory ring, the L2-prefetch cursor runs ahead of it.
+template <int PT>
+struct EngTileIter {
+  const EngineParams* P;
+  int bid, G;
+  int step, ph, rt, t;
+  int p1, K, kt, n_tiles;
+  const uint8_t* wbase;
+  bool valid;
+  LNB_DEVINL bool load_phase() {          // ph = a phase index to start searching from
+    for (; step < P->n_steps; step++, ph = 0) {
+      for (; ph < P->n_phases; ph++) {
+        const EnginePhase* E = P->phases + ph;
+        if (E->type != EP_GEMV) continue;
+        int p0;
+        eng_split(E->N / 8, bid, G, &p0, &p1);
+        if (p1 <= p0) continue;
+        K = E->K; kt = E->kt; n_tiles = (K + kt - 1) / kt;
+        wbase = reinterpret_cast<const uint8_t*>(E->W);
+        rt = p0; t = 0;
+        return true;
+      }
+    }
+    return false;
+  }
+  LNB_DEVINL void init(const EngineParams* P_, int bid_, int G_) {
+    P = P_; bid = bid_; G = G_; step = 0; ph = 0;
+    valid = load_phase();
+  }
+  LNB_DEVINL int np() const { return min(PT, p1 - rt); }
+  LNB_DEVINL uint32_t bytes_per_panel() const { return (uint32_t)min(kt, K - t * kt) * 16u; }
+  LNB_DEVINL const uint8_t* src(int panel_in_tile) const { return wbase + ((size_t)(rt + panel_in_tile) * (size_t)K + (size_t)t * kt) * 16u; }
+  LNB_DEVINL void advance() {
+    if (++t < n_tiles) return;
+    t = 0;
+    rt += PT;
+    if (rt < p1) return;
+    ph++;
+    valid = load_phase();
+  }
+};
+LNB_DEVINL void l2_prefetch_bulk(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const EngineParams P) {
@@ -339,7 +441,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
   if (tid == 0) {
     for (int s = 0; s < NST; s++) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], ENG_NCONS / 32);
+      mbar_init(&empty_bar[s], Cfg::kChainWarps);
     }
     mbar_fence_init();
   }
@@ -347,8 +449,13 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
 
   if (tid < 32) {
     // =========================== producer: walks the phase list ahead of the consumers ===========================
-    if (tid == 0) {
-      const uint64_t pol = l2_policy_evict_first();
+    // every lane issues one panel's copy of a stage (a single thread issuing 16-32 small copies per stage was the
+    // bottleneck of the first version: ~56 cycles per copy); lane 0 owns the barrier bookkeeping.  A second cursor
+    // prefetches the stream into L2 up to pf_window bytes ahead of the ring: HBM keeps streaming while the consumers sit
+    // in a grid barrier, a prologue or the attention phase, and the ring then refills from L2.
+    const uint64_t pol = l2_policy_evict_first();
+    if (P.pf_window == 0) {
+      // no prefetch cursor: plain nested loops (A/B twin of the iterator-driven loop below)
       uint32_t seq = 0;
       for (int step = 0; step < P.n_steps; step++) {
         for (int ph = 0; ph < P.n_phases; ph++) {
@@ -361,20 +468,51 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
           const uint8_t* wbase = reinterpret_cast<const uint8_t*>(E->W);
           for (int rt = p0; rt < p1; rt += PT) {
             const int np = min(PT, p1 - rt);
+            const uint8_t* src_row = wbase + (size_t)(rt + tid) * (size_t)K * 16u;
             for (int t = 0; t < n_tiles; t++, seq++) {
               const int s = seq % NST;
               const uint32_t par = (seq / NST) & 1u;
-              eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
               const int k0 = t * kt;
               const uint32_t bytes_per_panel = (uint32_t)min(kt, K - k0) * 16u;
-              mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)np);
-              for (int pp = 0; pp < np; pp++)
-                bulk_g2s(s_ring + (size_t)s * STAGE + (size_t)pp * ((size_t)kt * 16), wbase + ((size_t)(rt + pp) * (size_t)K + (size_t)k0) * 16u,
-                         bytes_per_panel, &full_bar[s], pol);
+              if (tid == 0) {
+                eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
+                mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)np);
+              }
+              __syncwarp();
+              if (tid < np)
+                bulk_g2s(s_ring + (size_t)s * STAGE + (size_t)tid * ((size_t)kt * 16), src_row + (size_t)k0 * 16u, bytes_per_panel, &full_bar[s], pol);
             }
           }
         }
       }
+      return;
+    }
+    EngTileIter<PT> ld, pf;
+    ld.init(&P, bid, G);
+    pf = ld;
+    long long ahead = 0;                       // bytes prefetched and not yet copied
+    uint32_t seq = 0;
+    while (ld.valid) {
+      while (pf.valid && ahead < (long long)P.pf_window) {
+        const uint32_t bpp = pf.bytes_per_panel();
+        const int np = pf.np();
+        if (tid < np) l2_prefetch_bulk(pf.src(tid), bpp);
+        ahead += (long long)bpp * np;
+        pf.advance();
+      }
+      const int s = seq % NST;
+      const uint32_t par = (seq / NST) & 1u;
+      const uint32_t bpp = ld.bytes_per_panel();
+      const int np = ld.np();
+      if (tid == 0) {
+        eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
+        mbar_expect_tx(&full_bar[s], bpp * (uint32_t)np);
+      }
+      __syncwarp();
+      if (tid < np) bulk_g2s(s_ring + (size_t)s * STAGE + (size_t)tid * ((size_t)ld.kt * 16), ld.src(tid), bpp, &full_bar[s], pol);
+      ahead -= (long long)bpp * np;
+      ld.advance();
+      seq++;
     }
     return;
   }
@@ -392,6 +530,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
   int tok = P.st->next_token;
   bool key_reset_due = false;
   if (bid == 0 && c == 0) P.st->amax_key = LNB_ARGMAX_EMPTY;   // nobody touches the key before the first LM head
+  long long t_mark = (P.prof && c == 0) ? clock64() : 0;       // LNB_ENGINE_PROF: where consumer thread 0 spends its cycles
 
   for (int step = 0; step < P.n_steps; step++) {
     if (c == 0) { ctl->pos = pos; ctl->tok = tok; }
@@ -423,9 +562,37 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             *gp = g;
           }
           // ---- prologue: activations -> f32 in shared memory (gemv.cuh prologue, MB = 1) -----------------------
-          for (int k = c * 2; k < K; k += ENG_NCONS * 2) {
-            const uint32_t w = ldcg_u32(xg + k);
-            *reinterpret_cast<float2*>(s_x + k) = make_float2(bf_lo(w), bf_hi(w));
+          // all global loads of a thread are issued before the first shared-memory store (the compiler cannot prove
+          // that the generic pointers do not alias shared memory and would serialise them, one L2 round trip each)
+          float* s_nw = s_x + K;                              // RMSNorm weights as f32 (K = dim here: 2 * K * 4 <= ENG_XMAX)
+          {
+            const int n_ch = K / 8;
+            const bool with_w = (E->pro == PRO_RMSNORM);
+            for (int base = 0; base < n_ch; base += ENG_NCONS * 4) {
+              uint4 xv[4], wv[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const int ch = base + u * ENG_NCONS + c;
+                if (ch < n_ch) {
+                  xv[u] = ldcg_u4(xg + (size_t)ch * 8);
+                  if (with_w) wv[u] = __ldg(reinterpret_cast<const uint4*>(E->norm_w + (size_t)ch * 8));
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const int ch = base + u * ENG_NCONS + c;
+                if (ch < n_ch) {
+                  float4* d = reinterpret_cast<float4*>(s_x + (size_t)ch * 8);
+                  d[0] = make_float4(bf_lo(xv[u].x), bf_hi(xv[u].x), bf_lo(xv[u].y), bf_hi(xv[u].y));
+                  d[1] = make_float4(bf_lo(xv[u].z), bf_hi(xv[u].z), bf_lo(xv[u].w), bf_hi(xv[u].w));
+                  if (with_w) {
+                    float4* dw = reinterpret_cast<float4*>(s_nw + (size_t)ch * 8);
+                    dw[0] = make_float4(bf_lo(wv[u].x), bf_hi(wv[u].x), bf_lo(wv[u].y), bf_hi(wv[u].y));
+                    dw[1] = make_float4(bf_lo(wv[u].z), bf_hi(wv[u].z), bf_lo(wv[u].w), bf_hi(wv[u].w));
+                  }
+                }
+              }
+            }
           }
           named_bar_sync(1, ENG_NCONS);
           if (E->pro == PRO_RMSNORM) {
@@ -463,109 +630,152 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             const float rs = s_scalar[0];
             for (int k = c; k < K; k += ENG_NCONS) {
               const float n1 = trunc_bf(__fmul_rn(s_x[k], rs));
-              s_x[k] = trunc_bf(__fmul_rn(n1, bf2f(E->norm_w[k])));
+              s_x[k] = trunc_bf(__fmul_rn(n1, s_nw[k]));
             }
             named_bar_sync(1, ENG_NCONS);
           }
+          if (P.prof && c == 0) { const long long t_now = clock64(); P.prof[bid * ENG_NPROF + 1] += (unsigned long long)(t_now - t_mark); t_mark = t_now; }
           // ---- row tiles --------------------------------------------------------------------------------------
-          for (int rt = p0; rt < p1; rt += PT) {
-            const int np = min(PT, p1 - rt);
-            const int pp = r >> 3, rr = r & 7;
-            const bool row_on = pp < np;
-            float acc = 0.f;
-            for (int t = 0; t < n_tiles; t++, seq++) {
-              const int s = seq % NST;
-              const uint32_t par = (seq / NST) & 1u;
-              // warps without rows in this tile only keep the ring moving: wait politely
-              const bool warp_on = (KS == 1) ? ((cw * 4) < np) : true;
-              eng_mbar_wait(&full_bar[s], par, P.err_host, P.timeout_ns, !warp_on, seq);
-              const int k0 = t * kt;
-              const int nchunks = min(kt, K - k0) / 8;
-              if (row_on) {
-                const uint8_t* tile = s_ring + (size_t)s * STAGE + (size_t)pp * ((size_t)kt * 16) + rr * 16;
+          if (KS > 1 || cw < Cfg::kChainWarps) {
+            for (int rt = p0; rt < p1; rt += PT) {
+              const int np = min(PT, p1 - rt);
+              // FAST: this thread's rows are r and r + 32 of the 64-row tile; STRICT: row c of the 128-row tile
+              const int pp0 = r >> 3, rr = r & 7;
+              const int pp1 = pp0 + 4;
+              const bool on0 = pp0 < np;
+              const bool on1 = (KS > 1) && (pp1 < np);
+              float acc0 = 0.f, acc1 = 0.f;
+              const bool warp_on = (KS == 1) ? ((cw * 4) < np) : true;   // a chain warp without rows only keeps the ring moving
+              for (int t = 0; t < n_tiles; t++, seq++) {
+                const int s = seq % NST;
+                const uint32_t par = (seq / NST) & 1u;
+                eng_mbar_wait(&full_bar[s], par, P.err_host, P.timeout_ns, !warp_on, seq);
+                const int k0 = t * kt;
+                const int nchunks = min(kt, K - k0) / 8;
+                const uint8_t* tile0 = s_ring + (size_t)s * STAGE + (size_t)pp0 * ((size_t)kt * 16) + rr * 16;
                 const float* xt = s_x + k0;
-                if (KS == 1 && (nchunks & 3) == 0) {
-                  // groups of 4 chunks, register double-buffered: the LDS of group g+1 are in flight while the 32
-                  // dependent FMAs of group g issue (gemv.cuh, MB == 1 branch)
-                  const int ng = nchunks >> 2;
-                  uint4 wa[4], wb[4];
-                  float4 xa0[4], xa1[4], xb0[4], xb1[4];
-#define ENG_LOAD(gi, W_, X0_, X1_)                                            \
-  _Pragma("unroll") for (int q_ = 0; q_ < 4; q_++) {                          \
-    const int ch_ = (gi) * 4 + q_;                                            \
-    W_[q_] = *reinterpret_cast<const uint4*>(tile + ch_ * 128);               \
-    X0_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8);                 \
-    X1_[q_] = *reinterpret_cast<const float4*>(xt + ch_ * 8 + 4);             \
-  }
-#define ENG_FMA(W_, X0_, X1_)                                                 \
-  _Pragma("unroll") for (int q_ = 0; q_ < 4; q_++) {                          \
-    float a_ = acc;                                                           \
-    a_ = __fmaf_rn(X0_[q_].x, bf_lo(W_[q_].x), a_);                           \
-    a_ = __fmaf_rn(X0_[q_].y, bf_hi(W_[q_].x), a_);                           \
-    a_ = __fmaf_rn(X0_[q_].z, bf_lo(W_[q_].y), a_);                           \
-    a_ = __fmaf_rn(X0_[q_].w, bf_hi(W_[q_].y), a_);                           \
-    a_ = __fmaf_rn(X1_[q_].x, bf_lo(W_[q_].z), a_);                           \
-    a_ = __fmaf_rn(X1_[q_].y, bf_hi(W_[q_].z), a_);                           \
-    a_ = __fmaf_rn(X1_[q_].z, bf_lo(W_[q_].w), a_);                           \
-    a_ = __fmaf_rn(X1_[q_].w, bf_hi(W_[q_].w), a_);                           \
-    acc = a_;                                                                 \
-  }
-                  ENG_LOAD(0, wa, xa0, xa1)
-                  for (int gi = 0; gi < ng; gi += 2) {
-                    if (gi + 1 < ng) { ENG_LOAD(gi + 1, wb, xb0, xb1) }
-                    ENG_FMA(wa, xa0, xa1)
-                    if (gi + 2 < ng) { ENG_LOAD(gi + 2, wa, xa0, xa1) }
-                    if (gi + 1 < ng) { ENG_FMA(wb, xb0, xb1) }
+                if (KS == 1) {
+                  if (on0) {
+                    if (nchunks == 64) acc0 = eng_chain_tile<16>(tile0, xt, acc0);
+                    else if (nchunks == 32) acc0 = eng_chain_tile<8>(tile0, xt, acc0);
+                    else if (nchunks == 16) acc0 = eng_chain_tile<4>(tile0, xt, acc0);
+                    else if (nchunks == 8) acc0 = eng_chain_tile<2>(tile0, xt, acc0);
+                    else {
+                      for (int ch = 0; ch < nchunks; ch++) {
+                        const uint4 wv = *reinterpret_cast<const uint4*>(tile0 + ch * 128);
+                        const float4 xa = *reinterpret_cast<const float4*>(xt + ch * 8);
+                        const float4 xb = *reinterpret_cast<const float4*>(xt + ch * 8 + 4);
+                        float a = acc0;
+                        a = __fmaf_rn(xa.x, bf_lo(wv.x), a); a = __fmaf_rn(xa.y, bf_hi(wv.x), a);
+                        a = __fmaf_rn(xa.z, bf_lo(wv.y), a); a = __fmaf_rn(xa.w, bf_hi(wv.y), a);
+                        a = __fmaf_rn(xb.x, bf_lo(wv.z), a); a = __fmaf_rn(xb.y, bf_hi(wv.z), a);
+                        a = __fmaf_rn(xb.z, bf_lo(wv.w), a); a = __fmaf_rn(xb.w, bf_hi(wv.w), a);
+                        acc0 = a;
+                      }
+                    }
                   }
-#undef ENG_LOAD
-#undef ENG_FMA
                 } else {
+                  // FAST: stream j owns the chunks ch = j, j + 8, ...; two rows (two independent chains) per thread.
+                  // Rows beyond the tile's panels read whatever the stage holds (finite or not, it is never stored:
+                  // `valid` is false for them) -- unconditional loads keep the loop free of predicates -- and the next
+                  // chunk's operands are loaded before the current chunk's 16 FMAs issue.
+                  const uint8_t* tile1 = tile0 + 4 * ((size_t)kt * 16);
+#ifdef ENG_FAST_SIMPLE
 #pragma unroll 4
                   for (int ch = j; ch < nchunks; ch += KS) {
-                    const uint4 wv = *reinterpret_cast<const uint4*>(tile + ch * 128);
                     const float4 xa = *reinterpret_cast<const float4*>(xt + ch * 8);
                     const float4 xb = *reinterpret_cast<const float4*>(xt + ch * 8 + 4);
-                    float a = acc;
-                    a = __fmaf_rn(xa.x, bf_lo(wv.x), a);
-                    a = __fmaf_rn(xa.y, bf_hi(wv.x), a);
-                    a = __fmaf_rn(xa.z, bf_lo(wv.y), a);
-                    a = __fmaf_rn(xa.w, bf_hi(wv.y), a);
-                    a = __fmaf_rn(xb.x, bf_lo(wv.z), a);
-                    a = __fmaf_rn(xb.y, bf_hi(wv.z), a);
-                    a = __fmaf_rn(xb.z, bf_lo(wv.w), a);
-                    a = __fmaf_rn(xb.w, bf_hi(wv.w), a);
-                    acc = a;
+                    uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+                    if (on0) w0 = *reinterpret_cast<const uint4*>(tile0 + ch * 128);
+                    if (on1) w1 = *reinterpret_cast<const uint4*>(tile1 + ch * 128);
+                    float a = acc0, b = acc1;
+                    a = __fmaf_rn(xa.x, bf_lo(w0.x), a); b = __fmaf_rn(xa.x, bf_lo(w1.x), b);
+                    a = __fmaf_rn(xa.y, bf_hi(w0.x), a); b = __fmaf_rn(xa.y, bf_hi(w1.x), b);
+                    a = __fmaf_rn(xa.z, bf_lo(w0.y), a); b = __fmaf_rn(xa.z, bf_lo(w1.y), b);
+                    a = __fmaf_rn(xa.w, bf_hi(w0.y), a); b = __fmaf_rn(xa.w, bf_hi(w1.y), b);
+                    a = __fmaf_rn(xb.x, bf_lo(w0.z), a); b = __fmaf_rn(xb.x, bf_lo(w1.z), b);
+                    a = __fmaf_rn(xb.y, bf_hi(w0.z), a); b = __fmaf_rn(xb.y, bf_hi(w1.z), b);
+                    a = __fmaf_rn(xb.z, bf_lo(w0.w), a); b = __fmaf_rn(xb.z, bf_lo(w1.w), b);
+                    a = __fmaf_rn(xb.w, bf_hi(w0.w), a); b = __fmaf_rn(xb.w, bf_hi(w1.w), b);
+                    acc0 = a; acc1 = b;
+                  }
+#else
+                  {
+                    int ch = j;
+                    float4 xa, xb;
+                    uint4 w0, w1;
+                    if (ch < nchunks) {
+                      xa = *reinterpret_cast<const float4*>(xt + ch * 8);
+                      xb = *reinterpret_cast<const float4*>(xt + ch * 8 + 4);
+                      w0 = *reinterpret_cast<const uint4*>(tile0 + ch * 128);
+                      w1 = *reinterpret_cast<const uint4*>(tile1 + ch * 128);
+                    }
+#pragma unroll 2
+                    for (; ch < nchunks; ch += KS) {
+                      const float4 ca = xa, cb = xb;
+                      const uint4 c0 = w0, c1 = w1;
+                      const int nx = ch + KS;
+                      if (nx < nchunks) {
+                        xa = *reinterpret_cast<const float4*>(xt + nx * 8);
+                        xb = *reinterpret_cast<const float4*>(xt + nx * 8 + 4);
+                        w0 = *reinterpret_cast<const uint4*>(tile0 + nx * 128);
+                        w1 = *reinterpret_cast<const uint4*>(tile1 + nx * 128);
+                      }
+                      float a = acc0, b = acc1;
+                      a = __fmaf_rn(ca.x, bf_lo(c0.x), a); b = __fmaf_rn(ca.x, bf_lo(c1.x), b);
+                      a = __fmaf_rn(ca.y, bf_hi(c0.x), a); b = __fmaf_rn(ca.y, bf_hi(c1.x), b);
+                      a = __fmaf_rn(ca.z, bf_lo(c0.y), a); b = __fmaf_rn(ca.z, bf_lo(c1.y), b);
+                      a = __fmaf_rn(ca.w, bf_hi(c0.y), a); b = __fmaf_rn(ca.w, bf_hi(c1.y), b);
+                      a = __fmaf_rn(cb.x, bf_lo(c0.z), a); b = __fmaf_rn(cb.x, bf_lo(c1.z), b);
+                      a = __fmaf_rn(cb.y, bf_hi(c0.z), a); b = __fmaf_rn(cb.y, bf_hi(c1.z), b);
+                      a = __fmaf_rn(cb.z, bf_lo(c0.w), a); b = __fmaf_rn(cb.z, bf_lo(c1.w), b);
+                      a = __fmaf_rn(cb.w, bf_hi(c0.w), a); b = __fmaf_rn(cb.w, bf_hi(c1.w), b);
+                      acc0 = a; acc1 = b;
+                    }
+                  }
+#endif
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+              }
+              if (P.prof && c == 0) { const long long t_now = clock64(); P.prof[bid * ENG_NPROF + 2] += (unsigned long long)(t_now - t_mark); t_mark = t_now; }
+              // ---- combine the KS streams in stream order, then the fused epilogue -------------------------------
+              if (KS > 1) {
+                s_part[j * 64 + r] = acc0;
+                s_part[j * 64 + 32 + r] = acc1;
+                named_bar_sync(1, ENG_NCONS);
+                if (c < 64) {
+                  float v = s_part[c];
+#pragma unroll
+                  for (int jj = 1; jj < KS; jj++) v = __fadd_rn(v, s_part[jj * 64 + c]);
+                  const int er = c;                              // row of the 64-row tile; lane == er % 32
+                  const int n = (rt + (er >> 3)) * 8 + (er & 7);
+                  const bool valid = (er >> 3) < np;
+                  switch (E->epi) {
+                    case EPI_BF16: gemv_epilogue<EPI_BF16>(*gp, v, n, 0, valid, rt + (er >> 3), er, lane); break;
+                    case EPI_RESID: gemv_epilogue<EPI_RESID>(*gp, v, n, 0, valid, rt + (er >> 3), er, lane); break;
+                    case EPI_LOGITS: gemv_epilogue<EPI_LOGITS>(*gp, v, n, 0, valid, rt + (er >> 3), er, lane); break;
+                    case EPI_QKV_ROPE: gemv_epilogue<EPI_QKV_ROPE>(*gp, v, n, 0, valid, rt + (er >> 3), er, lane); break;
+                    case EPI_SWIGLU: gemv_epilogue<EPI_SWIGLU>(*gp, v, n, 0, valid, rt + (er >> 3), er, lane); break;
+                    case EPI_P2P: gemv_epilogue<EPI_P2P>(*gp, v, n, 0, valid, rt + (er >> 3), er, lane); break;
+                    default: gemv_epilogue<EPI_F32RAW>(*gp, v, n, 0, valid, rt + (er >> 3), er, lane); break;
                   }
                 }
+                named_bar_sync(1, ENG_NCONS);                    // s_part is reused by the next row tile
+              } else {
+                const int n = (rt + pp0) * 8 + rr;               // global row of W
+                switch (E->epi) {
+                  case EPI_BF16: gemv_epilogue<EPI_BF16>(*gp, acc0, n, 0, on0, rt + pp0, r, lane); break;
+                  case EPI_RESID: gemv_epilogue<EPI_RESID>(*gp, acc0, n, 0, on0, rt + pp0, r, lane); break;
+                  case EPI_LOGITS: gemv_epilogue<EPI_LOGITS>(*gp, acc0, n, 0, on0, rt + pp0, r, lane); break;
+                  case EPI_QKV_ROPE: gemv_epilogue<EPI_QKV_ROPE>(*gp, acc0, n, 0, on0, rt + pp0, r, lane); break;
+                  case EPI_SWIGLU: gemv_epilogue<EPI_SWIGLU>(*gp, acc0, n, 0, on0, rt + pp0, r, lane); break;
+                  case EPI_P2P: gemv_epilogue<EPI_P2P>(*gp, acc0, n, 0, on0, rt + pp0, r, lane); break;
+                  default: gemv_epilogue<EPI_F32RAW>(*gp, acc0, n, 0, on0, rt + pp0, r, lane); break;
+                }
               }
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&empty_bar[s]);
+              if (P.prof && c == 0) { const long long t_now = clock64(); P.prof[bid * ENG_NPROF + 3] += (unsigned long long)(t_now - t_mark); t_mark = t_now; }
             }
-            // ---- combine the KS streams in stream order, then the fused epilogue -------------------------------
-            float v = acc;
-            if (KS > 1) {
-              s_part[j * 32 + r] = acc;
-              named_bar_sync(1, ENG_NCONS);
-              if (c < 32) {
-                v = s_part[r];
-#pragma unroll
-                for (int jj = 1; jj < KS; jj++) v = __fadd_rn(v, s_part[jj * 32 + r]);
-              }
-            }
-            if (KS == 1 || c < 32) {
-              const int n = (rt + pp) * 8 + rr;                // global row of W
-              const bool valid = row_on;
-              switch (E->epi) {
-                case EPI_BF16: gemv_epilogue<EPI_BF16>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
-                case EPI_RESID: gemv_epilogue<EPI_RESID>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
-                case EPI_LOGITS: gemv_epilogue<EPI_LOGITS>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
-                case EPI_QKV_ROPE: gemv_epilogue<EPI_QKV_ROPE>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
-                case EPI_SWIGLU: gemv_epilogue<EPI_SWIGLU>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
-                case EPI_P2P: gemv_epilogue<EPI_P2P>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
-                default: gemv_epilogue<EPI_F32RAW>(*gp, v, n, 0, valid, rt + pp, r, lane); break;
-              }
-            }
-            if (KS > 1) named_bar_sync(1, ENG_NCONS);          // s_part is reused by the next row tile
           }
         }
         if (flags & EF_NO_SYNC) { named_bar_sync(1, ENG_NCONS); continue; }
@@ -699,8 +909,15 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         continue;                                  // purely local result: no grid barrier
       }
       // ---- end of phase: everybody's outputs become visible to everybody ----------------------------------------
+      if (P.prof && c == 0) {
+        const long long t_now = clock64();
+        if (type == EP_SDPA) P.prof[bid * ENG_NPROF + 4] += (unsigned long long)(t_now - t_mark);
+        else if (type == EP_REDUCE) P.prof[bid * ENG_NPROF + 5] += (unsigned long long)(t_now - t_mark);
+        t_mark = t_now;
+      }
       n_bar++;
       eng_grid_barrier(P, n_bar * (unsigned int)G, c);
+      if (P.prof && c == 0) { const long long t_now = clock64(); P.prof[bid * ENG_NPROF + 0] += (unsigned long long)(t_now - t_mark); t_mark = t_now; }
       if (key_reset_due) {                         // every CTA has read the previous step's key by now
         if (bid == 0 && c == 0) P.st->amax_key = LNB_ARGMAX_EMPTY;
         key_reset_due = false;

@@ -236,6 +236,13 @@ class InferenceContext:
             lib.lnb_session_destroy(self.h)
             self.h = None
 
+    def engine_profile(self):
+        """LNB_ENGINE_PROF=1: {section: (mean cycles, max cycles)} of the decode engine's consumer thread 0 since the last call"""
+        out = (C.c_double * 16)()
+        check(lib.lnb_session_engine_profile(self.h, out))
+        names = ["grid_barrier", "prologue", "main_loop", "epilogue", "attention", "peer_reduce"]
+        return {n: (out[2 * i], out[2 * i + 1]) for i, n in enumerate(names)}
+
     def disable_peer_allreduce(self):
         """back to ncclAllReduce (e.g. after LNB_ETIMEOUT); every rank must do the same"""
         check(lib.lnb_session_p2p_disable(self.h))
