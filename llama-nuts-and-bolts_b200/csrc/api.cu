@@ -1057,6 +1057,11 @@ struct lnb_session {
   EnginePhase* d_phases = nullptr;
   int n_phases = 0, phases_cap = 0;
   unsigned int* d_bar = nullptr;
+  // tagged activation vectors of the engine ({tag:16 | bf16:16} words): residual stream x, post-attention stream h1,
+  // q|k|v of the step, attention output o, FFN hidden m
+  uint32_t *x_t = nullptr, *h1_t = nullptr, *qkv_t = nullptr, *o_t = nullptr, *m_t = nullptr;
+  uint32_t eng_tag = 1;          // next free tag (tags of one launch: [eng_tag, eng_tag + n_steps * n_phases))
+  bool last_was_engine = false;  // the residual stream of the last forward lives in x_t
   unsigned long long* d_prof = nullptr;   // LNB_ENGINE_PROF=1: per-CTA cycle counters of the engine's consumer thread 0
   int eng_state = 0;             // 0 = not probed, 1 = usable, -1 = this session uses the kernel chain
   std::string eng_why;           // why not
@@ -1161,6 +1166,7 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
     if (s->p2p_peer[r]) cudaIpcCloseMemHandle(s->p2p_peer[r]);
   cudaFree(s->p2p_region);
   cudaFree(s->d_phases); cudaFree(s->d_bar); cudaFree(s->d_prof);
+  cudaFree(s->x_t); cudaFree(s->h1_t); cudaFree(s->qkv_t); cudaFree(s->o_t); cudaFree(s->m_t);
   cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out); cudaFree(s->d_pos_arr); cudaFree(s->d_next_arr);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
@@ -1322,7 +1328,7 @@ static bool engine_probe(lnb_session* s) {
   if (eng_sdpa_smem(s->seq_len, a.head_dim, n_rep) > (size_t)ENG_WORK) return no("SequenceLength too long for the in-engine attention phase");
   int ch, nt;
   if (s->mode == LNB_ACC_STRICT && !eng_scan_shape(a.dim, &ch, &nt)) return no("dim does not fit the engine's binade scan");
-  if (m->kv_l / a.head_dim > m->sm_count) return no("more KV heads than SMs");
+  if (m->q_l / a.head_dim > m->sm_count) return no("more query heads than SMs");
   int occ = 0;
   cudaError_t ce;
   if (s->mode == LNB_ACC_STRICT) {
@@ -1334,6 +1340,15 @@ static bool engine_probe(lnb_session* s) {
   }
   if (ce != cudaSuccess || occ < 1) { cudaGetLastError(); return no("the engine kernel does not fit an SM"); }
   if (cudaMalloc((void**)&s->d_bar, 256) != cudaSuccess) { cudaGetLastError(); return no("cudaMalloc"); }
+  {
+    cudaError_t e2 = cudaMalloc((void**)&s->x_t, (size_t)a.dim * 4);
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&s->h1_t, (size_t)a.dim * 4);
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&s->qkv_t, (size_t)(m->q_l + 2 * m->kv_l) * 4);
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&s->o_t, (size_t)m->q_l * 4);
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&s->m_t, (size_t)m->ffn_l * 4);
+    if (e2 != cudaSuccess) { cudaGetLastError(); return no("cudaMalloc"); }
+    s->eng_tag = 0;   // forces the zero-fill of the tagged vectors before the first launch
+  }
   {
     const char* pe = getenv("LNB_ENGINE_PROF");
     if (pe && strcmp(pe, "0")) {
@@ -1358,7 +1373,7 @@ static int eng_kt(int mode, int N, int K, int G) {
   while (kt > 64 && maxp * kt * 16 > EngCfg<1>::kStage) kt >>= 1;
   return std::min(kt, K);
 }
-// kind -1: the full step; 0..4: `reps` independent copies of one projection of every layer (kernel-alone timing)
+// kind -1: the full step; 0..4: independent copies of one projection of every layer (kernel-alone timing, plain buffers)
 static int engine_build(lnb_session* s, int kind, const float* logits_out) {
   lnb_model* m = s->m;
   const lnb_model_args& a = m->a;
@@ -1368,7 +1383,10 @@ static int engine_build(lnb_session* s, int kind, const float* logits_out) {
     return 0;
   const int G = m->sm_count, mode = s->mode;
   const size_t cache_off = (size_t)s->active_seq * s->seq_len * m->kv_l;
+  const bool full = kind < 0;
   std::vector<EnginePhase> ph;
+  // which phase of the step wrote a tagged vector last (consumers wait for exactly that phase's tag)
+  int w_x = -1, w_h1 = -1, w_qkv = -1, w_o = -1, w_m = -1;
   auto gemv = [&](int pro, int epi, const uint16_t* W, int N, int K, const uint16_t* x, const uint16_t* norm_w, uint16_t* out, int ldo,
                   const uint16_t* res) {
     EnginePhase e{};
@@ -1376,61 +1394,83 @@ static int engine_build(lnb_session* s, int kind, const float* logits_out) {
     e.norm_w = norm_w; e.out_bf16 = out; e.ldo = ldo; e.res = res;
     return e;
   };
+  auto input = [&](EnginePhase& e, const uint32_t* vec, int writer) {   // tagged input of the phase being appended
+    if (full && writer >= 0) { e.x_t = vec; e.x_delta = (int)ph.size() - writer; }
+  };
+  auto resid = [&](EnginePhase& e, const uint32_t* vec, int writer) {
+    if (full && writer >= 0) { e.res_t = vec; e.res_delta = (int)ph.size() - writer; }
+  };
   const bool tp = m->tp_size > 1;
   for (int l = 0; l < n_layers; l++) {
     LayerW& W = m->layers[l];
-    if (kind < 0 || kind == 0) {  // attn_norm -> wq|wk|wv -> RoPE -> KV append
+    if (full || kind == 0) {  // attn_norm -> wq|wk|wv -> RoPE -> KV append
       EnginePhase e = gemv(PRO_RMSNORM, EPI_QKV_ROPE, W.wqkv, m->q_l + 2 * m->kv_l, a.dim, s->x, W.attn_norm, s->q, m->q_l, nullptr);
       e.q_dim = m->q_l; e.kv_dim = m->kv_l; e.cache_k = s->ck[l] + cache_off; e.cache_v = s->cv[l] + cache_off;
-      if (kind < 0 && l == 0) e.flags |= EF_X_TOKEN;
+      if (full && l == 0) e.flags |= EF_X_TOKEN;
+      else input(e, s->x_t, w_x);
+      if (full) { e.out_t = s->qkv_t; w_qkv = (int)ph.size(); }
       ph.push_back(e);
     }
-    if (kind < 0) {
+    if (full) {
       EnginePhase e{};
-      e.type = EP_SDPA; e.q = s->q; e.o = s->o; e.kv_dim = m->kv_l; e.q_dim = m->q_l;
+      e.type = EP_SDPA; e.kv_dim = m->kv_l; e.q_dim = m->q_l;
       e.cache_k = s->ck[l] + cache_off; e.cache_v = s->cv[l] + cache_off;
+      input(e, s->qkv_t, w_qkv);
+      e.out_t = s->o_t; w_o = (int)ph.size();
       ph.push_back(e);
     }
-    if (kind < 0 || kind == 1) {  // wo + residual
-      EnginePhase e = gemv(PRO_PLAIN, tp ? EPI_P2P : EPI_RESID, W.wo, a.dim, m->q_l, s->o, nullptr, s->h1, a.dim, s->x);
-      if (kind < 0 && l == 0) e.flags |= EF_RES_TOKEN;
-      if (kind < 0 && tp) e.flags |= EF_NO_SYNC;   // the reduce phase polls the peers' words itself: no grid barrier in between
+    if (full || kind == 1) {  // wo + residual
+      EnginePhase e = gemv(PRO_PLAIN, (tp && full) ? EPI_P2P : EPI_RESID, W.wo, a.dim, m->q_l, s->o, nullptr, s->h1, a.dim, s->x);
+      input(e, s->o_t, w_o);
+      if (full && !tp) {
+        if (l == 0) e.flags |= EF_RES_TOKEN; else resid(e, s->x_t, w_x);
+        e.out_t = s->h1_t; w_h1 = (int)ph.size();
+      }
       ph.push_back(e);
-      if (tp) {
+      if (tp && full) {
         EnginePhase r{};
-        r.type = EP_REDUCE; r.res = s->x; r.out_bf16 = s->h1; r.flags = (kind < 0 && l == 0) ? EF_RES_TOKEN : 0;
+        r.type = EP_REDUCE;
+        if (l == 0) r.flags |= EF_RES_TOKEN; else resid(r, s->x_t, w_x);
+        r.out_t = s->h1_t; w_h1 = (int)ph.size();
         ph.push_back(r);
       }
     }
-    if (kind < 0 || kind == 2)    // ffn_norm -> w1|w3 -> SiLU * up
-      ph.push_back(gemv(PRO_RMSNORM, EPI_SWIGLU, W.w13, 2 * m->ffn_l, a.dim, s->h1, W.ffn_norm, s->mbuf, m->ffn_l, nullptr));
-    if (kind < 0 || kind == 3) {  // w2 + residual
-      ph.push_back(gemv(PRO_PLAIN, tp ? EPI_P2P : EPI_RESID, W.w2, a.dim, m->ffn_l, s->mbuf, nullptr, s->x, a.dim, s->h1));
-      if (kind < 0 && tp) ph.back().flags |= EF_NO_SYNC;
-      if (tp) {
+    if (full || kind == 2) {  // ffn_norm -> w1|w3 -> SiLU * up
+      EnginePhase e = gemv(PRO_RMSNORM, EPI_SWIGLU, W.w13, 2 * m->ffn_l, a.dim, s->h1, W.ffn_norm, s->mbuf, m->ffn_l, nullptr);
+      input(e, s->h1_t, w_h1);
+      if (full) { e.out_t = s->m_t; w_m = (int)ph.size(); }
+      ph.push_back(e);
+    }
+    if (full || kind == 3) {  // w2 + residual
+      EnginePhase e = gemv(PRO_PLAIN, (tp && full) ? EPI_P2P : EPI_RESID, W.w2, a.dim, m->ffn_l, s->mbuf, nullptr, s->x, a.dim, s->h1);
+      input(e, s->m_t, w_m);
+      if (full && !tp) { resid(e, s->h1_t, w_h1); e.out_t = s->x_t; w_x = (int)ph.size(); }
+      ph.push_back(e);
+      if (tp && full) {
         EnginePhase r{};
-        r.type = EP_REDUCE; r.res = s->h1; r.out_bf16 = s->x;
+        r.type = EP_REDUCE;
+        resid(r, s->h1_t, w_h1);
+        r.out_t = s->x_t; w_x = (int)ph.size();
         ph.push_back(r);
       }
     }
   }
-  if (kind < 0 || kind == 4) {
+  if (full || kind == 4) {
     const int reps = kind == 4 ? 4 : 1;
     for (int i = 0; i < reps; i++) {
       EnginePhase e = gemv(PRO_RMSNORM, EPI_LOGITS, m->output, m->vocab_l, a.dim, s->x, m->norm, nullptr, m->vocab_l, nullptr);
       e.out_f32 = const_cast<float*>(logits_out); e.n_offset = m->tp_rank * m->vocab_l;
+      if (full && n_layers > 0) input(e, s->x_t, w_x);
+      if (full) e.flags |= EF_GRID_SYNC;
       ph.push_back(e);
     }
-    if (kind < 0 && tp) {
+    if (full && tp) {
       EnginePhase r{};
       r.type = EP_ARGMAX;
       ph.push_back(r);
     }
   }
-  if (kind >= 0)   // kernel-alone timing: outputs of a projection must not feed the next copy through the EPI_P2P path
-    for (auto& e : ph)
-      if (e.type == EP_GEMV && e.epi == EPI_P2P) e.epi = EPI_RESID;
-  if (kind >= 0) ph.erase(std::remove_if(ph.begin(), ph.end(), [](const EnginePhase& e) { return e.type != EP_GEMV; }), ph.end());
+  if (!full) ph.back().flags |= EF_GRID_SYNC;   // one barrier per sweep keeps the CTAs of a timing run together
   if ((int)ph.size() > s->phases_cap) {
     cudaFree(s->d_phases);
     s->d_phases = nullptr;
@@ -1444,12 +1484,13 @@ static int engine_build(lnb_session* s, int kind, const float* logits_out) {
   s->eng_key_seq = s->active_seq; s->eng_key_layers = n_layers; s->eng_key_kind = kind; s->eng_key_logits = logits_out;
   return 0;
 }
-// n_steps S=1 forwards in one launch; the first input token and position come from the device state (set_state_kernel)
+// n_steps S=1 forwards; the first input token and position come from the device state (set_state_kernel).  One launch
+// covers up to 65535 / n_phases steps (16-bit activation tags); longer runs continue from the device state.
 static int engine_launch(lnb_session* s, int n_steps, bool advance) {
   lnb_model* m = s->m;
   const lnb_model_args& a = m->a;
   EngineParams P{};
-  P.phases = s->d_phases; P.n_phases = s->n_phases; P.n_steps = n_steps; P.st = s->st;
+  P.phases = s->d_phases; P.n_phases = s->n_phases; P.st = s->st;
   P.emb = m->tok_embd; P.dim = a.dim; P.head_dim = a.head_dim; P.n_rep = a.n_heads / a.n_kv_heads; P.seq_len = s->seq_len;
   P.cis = m->cis; P.silu_tab = m->silu_tab; P.eps = a.norm_eps; P.attn_scale = attn_scale_bf16(a.head_dim);
   P.strict = s->mode == LNB_ACC_STRICT ? 1 : 0;
@@ -1462,26 +1503,45 @@ static int engine_launch(lnb_session* s, int n_steps, bool advance) {
   }
   P.err_host = s->h_err;
   {
-    // L2 prefetch window per CTA: 148 x 256 KB = 37 MB of the 126 MB L2 by default (LNB_ENGINE_PF_KB, 0 = off)
-    static const int pf_kb = [] { const char* e = getenv("LNB_ENGINE_PF_KB"); return e ? atoi(e) : 256; }();
+    // L2 prefetch per CTA and projection beyond the ring: 148 x 256 KB = 37 MB of the 126 MB L2 by default (LNB_ENGINE_PF_KB, 0 = off)
+    static const int pf_kb = [] { const char* e = getenv("LNB_ENGINE_PF_KB"); return e ? atoi(e) : 0; }();
     P.pf_window = pf_kb > 0 ? (unsigned int)pf_kb * 1024u : 0u;
   }
   P.prof = s->d_prof;
   P.advance = advance ? 1 : 0;
-  CU(cudaMemsetAsync(s->d_bar, 0, 4, s->stream));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(m->sm_count);
-  cfg.blockDim = dim3(ENG_THREADS);
-  cfg.dynamicSmemBytes = ENG_SMEM;
-  cfg.stream = s->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident (the grid barrier needs it), or the launch fails
-  at[0].val.cooperative = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  if (s->mode == LNB_ACC_STRICT) CU(cudaLaunchKernelEx(&cfg, decode_engine_kernel<1>, P));
-  else CU(cudaLaunchKernelEx(&cfg, decode_engine_kernel<8>, P));
-  s->launches++;
+  const int max_steps = std::max(1, 65000 / std::max(1, s->n_phases));
+  if (!advance && n_steps > max_steps) return fail(LNB_EINVAL, "engine: too many steps for one launch");
+  for (int done = 0; done < n_steps;) {
+    const int n = std::min(n_steps - done, max_steps);
+    if (s->eng_tag == 0 || (uint64_t)s->eng_tag + (uint64_t)n * s->n_phases > 65535u) {
+      // the 16-bit tags wrap: kill every old tag first (0 is never issued)
+      CU(cudaMemsetAsync(s->x_t, 0, (size_t)a.dim * 4, s->stream));
+      CU(cudaMemsetAsync(s->h1_t, 0, (size_t)a.dim * 4, s->stream));
+      CU(cudaMemsetAsync(s->qkv_t, 0, (size_t)(m->q_l + 2 * m->kv_l) * 4, s->stream));
+      CU(cudaMemsetAsync(s->o_t, 0, (size_t)m->q_l * 4, s->stream));
+      CU(cudaMemsetAsync(s->m_t, 0, (size_t)m->ffn_l * 4, s->stream));
+      s->eng_tag = 1;
+    }
+    P.n_steps = n;
+    P.tag_base = s->eng_tag;
+    s->eng_tag += (uint32_t)n * (uint32_t)s->n_phases;
+    CU(cudaMemsetAsync(s->d_bar, 0, 4, s->stream));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(m->sm_count);
+    cfg.blockDim = dim3(ENG_THREADS);
+    cfg.dynamicSmemBytes = ENG_SMEM;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident (they wait for each other), or the launch fails
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (s->mode == LNB_ACC_STRICT) CU(cudaLaunchKernelEx(&cfg, decode_engine_kernel<1>, P));
+    else CU(cudaLaunchKernelEx(&cfg, decode_engine_kernel<8>, P));
+    s->launches++;
+    done += n;
+  }
+  s->last_was_engine = true;
   return 0;
 }
 // after a failed stream sync: did the engine trap, and why?
@@ -1493,6 +1553,7 @@ static int engine_fault(lnb_session* s, cudaError_t e) {
                 s->m->tp_rank, c & 15u, (c >> 4) & 0xffffffu, cudaGetErrorString(e));
   if ((c >> 28) == 0xCu) return fail(LNB_ECUDA, "decode engine: a CTA never reached grid barrier target %u (%s)", c & 0xffffffu, cudaGetErrorString(e));
   if ((c >> 28) == 0xDu) return fail(LNB_ECUDA, "decode engine: weight stage %u never completed (%s)", c & 0xffffffu, cudaGetErrorString(e));
+  if ((c >> 28) == 0xEu) return fail(LNB_ECUDA, "decode engine: the activations tagged %u never arrived (%s)", c & 0xffffu, cudaGetErrorString(e));
   return fail(LNB_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
 }
 
@@ -1663,6 +1724,7 @@ static int enqueue_forward(lnb_session* s, int S, bool from_state_token, int log
     }
   }
   s->last_rows = S;
+  s->last_was_engine = false;
   return 0;
 }
 
@@ -2249,7 +2311,17 @@ extern "C" int lnb_session_read(lnb_session* s, int which, int layer, void* host
   const void* src = nullptr;
   int64_t avail = 0;
   switch (which) {
-    case LNB_BUF_RESIDUAL: src = s->x; avail = (int64_t)s->max_rows * m->a.dim * 2; break;
+    case LNB_BUF_RESIDUAL:
+      if (s->last_was_engine) {   // the engine keeps the residual stream as tagged words: strip the tags
+        if (nbytes > (int64_t)m->a.dim * 2) return fail(LNB_EINVAL, "the decode engine keeps one row");
+        std::vector<uint32_t> t((size_t)m->a.dim);
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaMemcpy(t.data(), s->x_t, t.size() * 4, cudaMemcpyDeviceToHost));
+        uint16_t* o = (uint16_t*)host;
+        for (int64_t i = 0; i < nbytes / 2; i++) o[i] = (uint16_t)(t[(size_t)i] & 0xffffu);
+        return 0;
+      }
+      src = s->x; avail = (int64_t)s->max_rows * m->a.dim * 2; break;
     case LNB_BUF_CACHE_K:
     case LNB_BUF_CACHE_V:
       if (layer < 0 || layer >= m->a.n_layers) return fail(LNB_EINVAL, "bad layer %d", layer);

@@ -107,6 +107,7 @@ struct LnbDevState {
                                  // within LnbP2P.timeout_ns: every later peer kernel of the session exits at once)
   uint32_t ar_done2;             // CTAs of the reducing kernel that have finished
   uint32_t pad2;
+  unsigned long long amax_key_b; // persistent engine: the argmax key of odd steps (engine.cuh)
 };
 
 // One-shot all-reduce over NVLink peer memory (tensor-parallel decode), "LL" style: every value travels

@@ -43,7 +43,7 @@ enum { EP_GEMV = 0, EP_SDPA = 1, EP_REDUCE = 2, EP_ARGMAX = 3 };
 enum {
   EF_X_TOKEN = 1,    // x   = embedding row of the step's input token (ml.Fwd_Get_Rows, operations_impl.go:142-173)
   EF_RES_TOKEN = 2,  // res = the same row (the residual stream of layer 0 is the embedding)
-  EF_NO_SYNC = 4     // no grid barrier after this phase (kernel-alone timing: the phases are independent)
+  EF_GRID_SYNC = 4   // grid barrier after this phase (the LM head: its argmax key must be complete before anyone reads it)
 };
 
 struct EnginePhase {
@@ -58,9 +58,16 @@ struct EnginePhase {
   int ldo, n_offset;
   uint16_t* cache_k;        // this layer's caches (offset to the active sequence): QKV epilogue, SDPA
   uint16_t* cache_v;
-  const uint16_t* q;        // SDPA in / out
+  const uint16_t* q;        // SDPA in / out (plain buffers; unused when the tagged vectors are set)
   uint16_t* o;
   int q_dim, kv_dim;        // local widths (per tensor-parallel rank)
+  // Activations between phases of one step travel as self-validating 4-byte words {tag:16 | bf16:16}: the consumer polls
+  // the words of the vector it needs until they carry the producer phase's tag -- no grid barrier, and the wait is the load.
+  // tag(step, phase) = tag_base + step * n_phases + phase (the host keeps it below 2^16 and the buffers' old tags dead).
+  const uint32_t* x_t;      // tagged input vector (GEMV prologue / SDPA: q | k | v of this step), NULL: plain `x` / token
+  const uint32_t* res_t;    // tagged residual (EPI_RESID / REDUCE), NULL: plain `res` / token
+  uint32_t* out_t;          // tagged output vector, NULL: plain outputs
+  int x_delta, res_delta;   // how many phases earlier (same step) the tagged input / residual was produced
 };
 
 struct EngineParams {
@@ -79,14 +86,15 @@ struct EngineParams {
   int tp;
   unsigned long long timeout_ns;
   volatile uint32_t* err_host;   // host-mapped word: why the engine trapped (see eng_fail)
-  unsigned int pf_window;        // bytes of the weight stream each CTA keeps prefetched in L2 ahead of its ring (0: none)
+  unsigned int pf_window;        // bytes of a projection's stream each CTA prefetches into L2 beyond its ring when it reaches the phase (0: none)
+  unsigned int tag_base;         // tag of (step 0, phase 0)
   unsigned long long* prof;      // NULL, or [gridDim.x][ENG_NPROF] cycle sums of consumer thread 0: 0 grid barrier, 1 prologue,
                                  // 2 main loop (stage waits included), 3 combine + epilogue, 4 attention, 5 peer reduce / argmax
   int advance;              // 1: decode-loop bookkeeping (tok_out[step], st->pos / st->step advance)
 };
 
 constexpr int ENG_NCONS = 256;
-constexpr int ENG_THREADS = ENG_NCONS + 32;
+constexpr int ENG_THREADS = ENG_NCONS + 64;                // + producer warp (warp 0) + L2-prefetch warp (warp 9)
 constexpr int ENG_RING = 128 * 1024;
 constexpr int ENG_WORK = 84 * 1024;
 constexpr int ENG_XMAX = 56 * 1024;                       // f32 activation vector: K <= 14336
@@ -116,6 +124,7 @@ __host__ __device__ inline size_t eng_sdpa_smem(int T_max, int hd, int n_rep) {
 struct EngCtl {            // in the header, after the barriers
   int pos;
   int tok;
+  volatile unsigned long long ld_bytes;   // weight bytes the producer has issued so far (the prefetch warp stays ahead of it)
 };
 
 // Fatal, loud, never a hang: the reason goes to a host-mapped word (readable after the context died), then trap.
@@ -373,48 +382,31 @@ LNB_DEVINL float eng_chain_tile(const uint8_t* __restrict__ tile, const float* _
   return acc;
 }
 
-// The producer's view of the weight stream: every (step, projection phase, row tile, k-tile) of this CTA, in order.
-// Two cursors walk it: the bulk-copy cursor feeds the shared-memory ring, the L2-prefetch cursor runs ahead of it.
-template <int PT>
-struct EngTileIter {
-  const EngineParams* P;
-  int bid, G;
-  int step, ph, rt, t;
-  int p1, K, kt, n_tiles;
-  const uint8_t* wbase;
-  bool valid;
-  LNB_DEVINL bool load_phase() {          // ph = a phase index to start searching from
-    for (; step < P->n_steps; step++, ph = 0) {
-      for (; ph < P->n_phases; ph++) {
-        const EnginePhase* E = P->phases + ph;
-        if (E->type != EP_GEMV) continue;
-        int p0;
-        eng_split(E->N / 8, bid, G, &p0, &p1);
-        if (p1 <= p0) continue;
-        K = E->K; kt = E->kt; n_tiles = (K + kt - 1) / kt;
-        wbase = reinterpret_cast<const uint8_t*>(E->W);
-        rt = p0; t = 0;
-        return true;
-      }
+// four consecutive words of a tagged vector, polled until all of them carry `tag_hi`
+LNB_DEVINL uint4 ld_volatile_u4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+LNB_DEVINL bool tags_ok(const uint4& v, uint32_t tag_hi) {
+  return (((v.x ^ tag_hi) | (v.y ^ tag_hi) | (v.z ^ tag_hi) | (v.w ^ tag_hi)) & 0xffff0000u) == 0u;
+}
+LNB_DEVINL uint4 wait_tagged4(const uint32_t* p, uint32_t tag_hi, volatile uint32_t* err_host, unsigned long long timeout_ns) {
+  uint4 v = ld_volatile_u4(p);
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  while (!tags_ok(v, tag_hi)) {
+    if ((++spins & 1023u) == 0u && timeout_ns) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2 * timeout_ns) eng_fail(err_host, 0xE0000000u | (tag_hi >> 16));   // 0xE...: a tagged activation never arrived
     }
-    return false;
+    v = ld_volatile_u4(p);
   }
-  LNB_DEVINL void init(const EngineParams* P_, int bid_, int G_) {
-    P = P_; bid = bid_; G = G_; step = 0; ph = 0;
-    valid = load_phase();
-  }
-  LNB_DEVINL int np() const { return min(PT, p1 - rt); }
-  LNB_DEVINL uint32_t bytes_per_panel() const { return (uint32_t)min(kt, K - t * kt) * 16u; }
-  LNB_DEVINL const uint8_t* src(int panel_in_tile) const { return wbase + ((size_t)(rt + panel_in_tile) * (size_t)K + (size_t)t * kt) * 16u; }
-  LNB_DEVINL void advance() {
-    if (++t < n_tiles) return;
-    t = 0;
-    rt += PT;
-    if (rt < p1) return;
-    ph++;
-    valid = load_phase();
-  }
-};
+  return v;
+}
+LNB_DEVINL float tagged_f32(uint32_t w) { return __uint_as_float(w << 16); }
+
 LNB_DEVINL void l2_prefetch_bulk(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
@@ -444,75 +436,85 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
       mbar_init(&empty_bar[s], Cfg::kChainWarps);
     }
     mbar_fence_init();
+    ctl->ld_bytes = 0ull;
   }
   __syncthreads();
 
   if (tid < 32) {
     // =========================== producer: walks the phase list ahead of the consumers ===========================
-    // every lane issues one panel's copy of a stage (a single thread issuing 16-32 small copies per stage was the
-    // bottleneck of the first version: ~56 cycles per copy); lane 0 owns the barrier bookkeeping.  A second cursor
-    // prefetches the stream into L2 up to pf_window bytes ahead of the ring: HBM keeps streaming while the consumers sit
-    // in a grid barrier, a prologue or the attention phase, and the ring then refills from L2.
+    // lanes 0..np-1 issue one panel's copy of a stage each (ptxas serialises them through the uniform datapath: ~50 cycles
+    // per copy, which is why copies are kept >= 2 KB); lane 0 owns the barrier bookkeeping.
     const uint64_t pol = l2_policy_evict_first();
-    if (P.pf_window == 0) {
-      // no prefetch cursor: plain nested loops (A/B twin of the iterator-driven loop below)
-      uint32_t seq = 0;
-      for (int step = 0; step < P.n_steps; step++) {
-        for (int ph = 0; ph < P.n_phases; ph++) {
-          const EnginePhase* E = P.phases + ph;
-          if (E->type != EP_GEMV) continue;
-          const int K = E->K, kt = E->kt;
-          const int n_tiles = (K + kt - 1) / kt;
-          int p0, p1;
-          eng_split(E->N / 8, bid, G, &p0, &p1);
-          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(E->W);
-          for (int rt = p0; rt < p1; rt += PT) {
-            const int np = min(PT, p1 - rt);
-            const uint8_t* src_row = wbase + (size_t)(rt + tid) * (size_t)K * 16u;
-            for (int t = 0; t < n_tiles; t++, seq++) {
-              const int s = seq % NST;
-              const uint32_t par = (seq / NST) & 1u;
-              const int k0 = t * kt;
-              const uint32_t bytes_per_panel = (uint32_t)min(kt, K - k0) * 16u;
-              if (tid == 0) {
-                eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
-                mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)np);
-              }
-              __syncwarp();
-              if (tid < np)
-                bulk_g2s(s_ring + (size_t)s * STAGE + (size_t)tid * ((size_t)kt * 16), src_row + (size_t)k0 * 16u, bytes_per_panel, &full_bar[s], pol);
+    uint32_t seq = 0;
+    unsigned long long issued = 0;
+    for (int step = 0; step < P.n_steps; step++) {
+      for (int ph = 0; ph < P.n_phases; ph++) {
+        const EnginePhase* E = P.phases + ph;
+        if (E->type != EP_GEMV) continue;
+        const int K = E->K, kt = E->kt;
+        const int n_tiles = (K + kt - 1) / kt;
+        int p0, p1;
+        eng_split(E->N / 8, bid, G, &p0, &p1);
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(E->W);
+        for (int rt = p0; rt < p1; rt += PT) {
+          const int np = min(PT, p1 - rt);
+          const uint8_t* src_row = wbase + (size_t)(rt + tid) * (size_t)K * 16u;
+          for (int t = 0; t < n_tiles; t++, seq++) {
+            const int s = seq % NST;
+            const uint32_t par = (seq / NST) & 1u;
+            const int k0 = t * kt;
+            const uint32_t bytes_per_panel = (uint32_t)min(kt, K - k0) * 16u;
+            if (tid == 0) {
+              eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
+              mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)np);
             }
+            __syncwarp();
+            if (tid < np)
+              bulk_g2s(s_ring + (size_t)s * STAGE + (size_t)tid * ((size_t)kt * 16), src_row + (size_t)k0 * 16u, bytes_per_panel, &full_bar[s], pol);
+            issued += (unsigned long long)bytes_per_panel * (unsigned long long)np;
+            if (tid == 0) ctl->ld_bytes = issued;
           }
         }
       }
-      return;
     }
-    EngTileIter<PT> ld, pf;
-    ld.init(&P, bid, G);
-    pf = ld;
-    long long ahead = 0;                       // bytes prefetched and not yet copied
-    uint32_t seq = 0;
-    while (ld.valid) {
-      while (pf.valid && ahead < (long long)P.pf_window) {
-        const uint32_t bpp = pf.bytes_per_panel();
-        const int np = pf.np();
-        if (tid < np) l2_prefetch_bulk(pf.src(tid), bpp);
-        ahead += (long long)bpp * np;
-        pf.advance();
+    return;
+  }
+  if (tid >= 32 + ENG_NCONS) {
+    // =========================== L2 prefetcher: the same walk, pf_window bytes ahead of the producer ==============
+    // The ring holds 128 KB per SM = 19 MB per chip = 3 us of HBM time, but a phase boundary (inputs of the next projection
+    // still being produced, prologue, attention) stalls the consumers longer than that.  This warp asks L2 for the stream
+    // beyond the ring, so that HBM keeps working through the stall and the ring then refills at L2 speed.
+    if (P.pf_window == 0) return;
+    const int lane = tid & 31;
+    unsigned long long pf = 0;
+    const unsigned long long lead = (unsigned long long)NST * STAGE;   // the ring itself: not worth prefetching
+    for (int step = 0; step < P.n_steps; step++) {
+      for (int ph = 0; ph < P.n_phases; ph++) {
+        const EnginePhase* E = P.phases + ph;
+        if (E->type != EP_GEMV) continue;
+        const int K = E->K, kt = E->kt;
+        const int n_tiles = (K + kt - 1) / kt;
+        int p0, p1;
+        eng_split(E->N / 8, bid, G, &p0, &p1);
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(E->W);
+        for (int rt = p0; rt < p1; rt += PT) {
+          const int np = min(PT, p1 - rt);
+          for (int t = 0; t < n_tiles; t++) {
+            const uint32_t bpp = (uint32_t)min(kt, K - t * kt) * 16u;
+            const unsigned long long tile_bytes = (unsigned long long)bpp * (unsigned long long)np;
+            unsigned long long ld = ctl->ld_bytes;
+            uint32_t spins = 0;
+            while (pf > ld + lead + (unsigned long long)P.pf_window) {   // far enough ahead: wait for the producer
+              __nanosleep(200);
+              ld = ctl->ld_bytes;
+              if (++spins > (1u << 26)) return;
+            }
+            if (pf >= ld + lead && lane < np)
+              l2_prefetch_bulk(wbase + ((size_t)(rt + lane) * (size_t)K + (size_t)t * kt) * 16u, bpp);
+            pf += tile_bytes;
+          }
+        }
       }
-      const int s = seq % NST;
-      const uint32_t par = (seq / NST) & 1u;
-      const uint32_t bpp = ld.bytes_per_panel();
-      const int np = ld.np();
-      if (tid == 0) {
-        eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
-        mbar_expect_tx(&full_bar[s], bpp * (uint32_t)np);
-      }
-      __syncwarp();
-      if (tid < np) bulk_g2s(s_ring + (size_t)s * STAGE + (size_t)tid * ((size_t)ld.kt * 16), ld.src(tid), bpp, &full_bar[s], pol);
-      ahead -= (long long)bpp * np;
-      ld.advance();
-      seq++;
     }
     return;
   }
@@ -528,8 +530,14 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
   uint32_t epoch = (P.tp > 1) ? P.st->ar_epoch : 0u;
   int pos = P.st->pos;
   int tok = P.st->next_token;
-  bool key_reset_due = false;
-  if (bid == 0 && c == 0) P.st->amax_key = LNB_ARGMAX_EMPTY;   // nobody touches the key before the first LM head
+  // the greedy-argmax key is double-buffered by step parity: with ONE grid barrier per step the key of step s can only be
+  // cleared once every CTA has passed the barrier of step s + 1 (everyone read it right after barrier s)
+  unsigned long long* const keys[2] = {&P.st->amax_key, &P.st->amax_key_b};
+  if (bid == 0 && c == 0) {
+    *keys[0] = LNB_ARGMAX_EMPTY;
+    *keys[1] = LNB_ARGMAX_EMPTY;
+    __threadfence();                          // before any of this CTA's outputs, which every LM-head atomicMax depends on
+  }
   long long t_mark = (P.prof && c == 0) ? clock64() : 0;       // LNB_ENGINE_PROF: where consumer thread 0 spends its cycles
 
   for (int step = 0; step < P.n_steps; step++) {
@@ -537,6 +545,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
     for (int ph = 0; ph < P.n_phases; ph++) {
       const EnginePhase* E = P.phases + ph;
       const int type = E->type;
+      const uint32_t tag_now = P.tag_base + (uint32_t)step * (uint32_t)P.n_phases + (uint32_t)ph;
       if (type == EP_GEMV) {
         const int K = E->K, kt = E->kt;
         const int n_tiles = (K + kt - 1) / kt;
@@ -544,6 +553,8 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         eng_split(E->N / 8, bid, G, &p0, &p1);
         const int flags = E->flags;
         const uint16_t* xg = (flags & EF_X_TOKEN) ? P.emb + (size_t)tok * P.dim : E->x;
+        const uint32_t* xtg = (flags & EF_X_TOKEN) ? nullptr : E->x_t;
+        const uint32_t x_tag_hi = (tag_now - (uint32_t)E->x_delta) << 16;
         if (p1 > p0) {
           // ---- the phase as gemv_epilogue sees it ------------------------------------------------------------
           if (c == 0) {
@@ -555,10 +566,12 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             g.q_dim = E->q_dim; g.kv_dim = E->kv_dim; g.head_dim = P.head_dim;
             g.cache_k = E->cache_k; g.cache_v = E->cache_v; g.pos_arr = nullptr; g.cache_seq_stride = 0;
             g.cis = P.cis; g.silu_tab = P.silu_tab;
-            g.n_offset = E->n_offset; g.st = P.st; g.argmax_row = 0; g.publish = 0; g.advance = 0; g.tok_out = nullptr;
+            g.n_offset = E->n_offset; g.st = P.st; g.amax_key_ptr = keys[step & 1]; g.argmax_row = 0; g.publish = 0; g.advance = 0; g.tok_out = nullptr;
             g.pos_ptr = &ctl->pos; g.m_off = 0;
             g.p2p = P.p2p;
             g.ar_epoch_override = epoch;
+            g.out_t = E->out_t; g.tag_hi = tag_now << 16;
+            g.res_t = (flags & EF_RES_TOKEN) ? nullptr : E->res_t; g.res_tag_hi = (tag_now - (uint32_t)E->res_delta) << 16;
             *gp = g;
           }
           // ---- prologue: activations -> f32 in shared memory (gemv.cuh prologue, MB = 1) -----------------------
@@ -569,12 +582,17 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             const int n_ch = K / 8;
             const bool with_w = (E->pro == PRO_RMSNORM);
             for (int base = 0; base < n_ch; base += ENG_NCONS * 4) {
-              uint4 xv[4], wv[4];
+              uint4 xv[4], xv2[4], wv[4];
 #pragma unroll
               for (int u = 0; u < 4; u++) {
                 const int ch = base + u * ENG_NCONS + c;
                 if (ch < n_ch) {
-                  xv[u] = ldcg_u4(xg + (size_t)ch * 8);
+                  if (xtg) {   // tagged words: 8 elements = 2 x 16 bytes; validated below
+                    xv[u] = ld_volatile_u4(xtg + (size_t)ch * 8);
+                    xv2[u] = ld_volatile_u4(xtg + (size_t)ch * 8 + 4);
+                  } else {
+                    xv[u] = ldcg_u4(xg + (size_t)ch * 8);
+                  }
                   if (with_w) wv[u] = __ldg(reinterpret_cast<const uint4*>(E->norm_w + (size_t)ch * 8));
                 }
               }
@@ -583,8 +601,15 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
                 const int ch = base + u * ENG_NCONS + c;
                 if (ch < n_ch) {
                   float4* d = reinterpret_cast<float4*>(s_x + (size_t)ch * 8);
-                  d[0] = make_float4(bf_lo(xv[u].x), bf_hi(xv[u].x), bf_lo(xv[u].y), bf_hi(xv[u].y));
-                  d[1] = make_float4(bf_lo(xv[u].z), bf_hi(xv[u].z), bf_lo(xv[u].w), bf_hi(xv[u].w));
+                  if (xtg) {
+                    if (!tags_ok(xv[u], x_tag_hi)) xv[u] = wait_tagged4(xtg + (size_t)ch * 8, x_tag_hi, P.err_host, P.timeout_ns);
+                    if (!tags_ok(xv2[u], x_tag_hi)) xv2[u] = wait_tagged4(xtg + (size_t)ch * 8 + 4, x_tag_hi, P.err_host, P.timeout_ns);
+                    d[0] = make_float4(tagged_f32(xv[u].x), tagged_f32(xv[u].y), tagged_f32(xv[u].z), tagged_f32(xv[u].w));
+                    d[1] = make_float4(tagged_f32(xv2[u].x), tagged_f32(xv2[u].y), tagged_f32(xv2[u].z), tagged_f32(xv2[u].w));
+                  } else {
+                    d[0] = make_float4(bf_lo(xv[u].x), bf_hi(xv[u].x), bf_lo(xv[u].y), bf_hi(xv[u].y));
+                    d[1] = make_float4(bf_lo(xv[u].z), bf_hi(xv[u].z), bf_lo(xv[u].w), bf_hi(xv[u].w));
+                  }
                   if (with_w) {
                     float4* dw = reinterpret_cast<float4*>(s_nw + (size_t)ch * 8);
                     dw[0] = make_float4(bf_lo(wv[u].x), bf_hi(wv[u].x), bf_lo(wv[u].y), bf_hi(wv[u].y));
@@ -778,89 +803,93 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             }
           }
         }
-        if (flags & EF_NO_SYNC) { named_bar_sync(1, ENG_NCONS); continue; }
       } else if (type == EP_SDPA) {
-        // ---- decode attention for one KV head per CTA: sdpa_decode_kernel's arithmetic (kernels.cuh), with the 128
-        // threads per query head of that kernel mapped onto 256 consumers (each takes query heads hh, hh + 2, ...) ----
+        // ---- decode attention, one CTA per QUERY head (the four heads of a GQA group stage the same K / V rows from L2):
+        // sdpa_decode_kernel's arithmetic (kernels.cuh) -- the same 128 threads per head for the f64 row sum, so the bits
+        // are the kernel chain's in both modes.  The other CTAs go straight on to the next phase's inputs.
         const int hd = P.head_dim, n_rep = P.n_rep;
-        const int n_kvh = E->kv_dim / hd;
-        if (bid < n_kvh) {
-          const int h = bid;
+        const int n_qh = E->q_dim / hd;
+        if (bid < n_qh) {
+          const int H = bid, h = H / n_rep;
           const int T = pos + 1, T_max = P.seq_len;
           const int kstride = hd + 8, cpr = hd / 8;
           uint16_t* sK = reinterpret_cast<uint16_t*>(s_work);
           uint16_t* sV = sK + (size_t)T_max * kstride;
           double* sE = reinterpret_cast<double*>(sV + (size_t)T_max * hd);
-          float* sP = reinterpret_cast<float*>(sE + (size_t)n_rep * T_max);
-          float* sQ = sP + (size_t)n_rep * T_max;
-          double* sZ = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sQ + (size_t)n_rep * hd) + 15) & ~(uintptr_t)15);
-          for (int i = c; i < T * cpr; i += ENG_NCONS) {
+          float* sP = reinterpret_cast<float*>(sE + (size_t)T_max);
+          float* sQ = sP + (size_t)T_max;
+          double* sZ = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sQ + (size_t)hd) + 15) & ~(uintptr_t)15);
+          // rows of earlier positions come from the cache (complete since the previous step's grid barrier); this step's
+          // k / v row and the query head come from the tagged q | k | v vector the projection phase is writing right now
+          for (int i = c; i < (T - 1) * cpr; i += ENG_NCONS) {
             const int t = i / cpr, cc = i % cpr;
             *reinterpret_cast<uint4*>(sK + (size_t)t * kstride + cc * 8) = ldcg_u4(E->cache_k + (size_t)t * E->kv_dim + (size_t)h * hd + cc * 8);
             *reinterpret_cast<uint4*>(sV + (size_t)t * hd + cc * 8) = ldcg_u4(E->cache_v + (size_t)t * E->kv_dim + (size_t)h * hd + cc * 8);
           }
-          for (int i = c; i < n_rep * hd; i += ENG_NCONS) sQ[i] = bf2f(ldcg_u16(E->q + (size_t)(h * n_rep) * hd + i));
-          named_bar_sync(1, ENG_NCONS);
-          const int tt = c & 127;
-          for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128) {
-            const float* qh = sQ + hh * hd;
-            for (int t = tt; t < T; t += 128) {
-              const uint16_t* kr = sK + (size_t)t * kstride;
-              float a = 0.f;
-              for (int d = 0; d < hd; d += 8) {
-                const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
-                a = __fmaf_rn(qh[d + 0], bf_lo(kv.x), a);
-                a = __fmaf_rn(qh[d + 1], bf_hi(kv.x), a);
-                a = __fmaf_rn(qh[d + 2], bf_lo(kv.y), a);
-                a = __fmaf_rn(qh[d + 3], bf_hi(kv.y), a);
-                a = __fmaf_rn(qh[d + 4], bf_lo(kv.z), a);
-                a = __fmaf_rn(qh[d + 5], bf_hi(kv.z), a);
-                a = __fmaf_rn(qh[d + 6], bf_lo(kv.w), a);
-                a = __fmaf_rn(qh[d + 7], bf_hi(kv.w), a);
+          {
+            const uint32_t qtag = (tag_now - (uint32_t)E->x_delta) << 16;
+            const int n4 = hd / 4;
+            for (int i = c; i < 3 * n4; i += ENG_NCONS) {
+              if (i < n4) {
+                const uint4 w = wait_tagged4(E->x_t + (size_t)H * hd + (size_t)i * 4, qtag, P.err_host, P.timeout_ns);
+                *reinterpret_cast<float4*>(sQ + (size_t)i * 4) = make_float4(tagged_f32(w.x), tagged_f32(w.y), tagged_f32(w.z), tagged_f32(w.w));
+              } else {
+                const bool is_v = i >= 2 * n4;
+                const int e4 = i - (is_v ? 2 * n4 : n4);
+                const uint4 w = wait_tagged4(E->x_t + (size_t)E->q_dim + (is_v ? (size_t)E->kv_dim : 0) + (size_t)h * hd + (size_t)e4 * 4, qtag,
+                                             P.err_host, P.timeout_ns);
+                uint16_t* dst = is_v ? sV + (size_t)(T - 1) * hd + e4 * 4 : sK + (size_t)(T - 1) * kstride + e4 * 4;
+                *reinterpret_cast<uint2*>(dst) = make_uint2((w.x & 0xffffu) | (w.y << 16), (w.z & 0xffffu) | (w.w << 16));
               }
-              float sc = trunc_bf(a);
-              sc = trunc_bf(__fdiv_rn(sc, P.attn_scale));
-              sE[(size_t)hh * T_max + t] = exp((double)sc);
             }
           }
           named_bar_sync(1, ENG_NCONS);
-          for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128) {
-            double* eh = sE + (size_t)hh * T_max;
-            if (P.strict) {
-              if (tt == 0) {
-                double z = 0.0;
-                for (int t = 0; t < T; t++) z = __dadd_rn(z, eh[t]);
-                sZ[n_rep * 4 + hh] = z;
-              }
-            } else {
+          for (int t = c; t < T; t += ENG_NCONS) {
+            const uint16_t* kr = sK + (size_t)t * kstride;
+            float a = 0.f;
+            for (int d = 0; d < hd; d += 8) {
+              const uint4 kv = *reinterpret_cast<const uint4*>(kr + d);
+              a = __fmaf_rn(sQ[d + 0], bf_lo(kv.x), a);
+              a = __fmaf_rn(sQ[d + 1], bf_hi(kv.x), a);
+              a = __fmaf_rn(sQ[d + 2], bf_lo(kv.y), a);
+              a = __fmaf_rn(sQ[d + 3], bf_hi(kv.y), a);
+              a = __fmaf_rn(sQ[d + 4], bf_lo(kv.z), a);
+              a = __fmaf_rn(sQ[d + 5], bf_hi(kv.z), a);
+              a = __fmaf_rn(sQ[d + 6], bf_lo(kv.w), a);
+              a = __fmaf_rn(sQ[d + 7], bf_hi(kv.w), a);
+            }
+            float sc = trunc_bf(a);
+            sc = trunc_bf(__fdiv_rn(sc, P.attn_scale));
+            sE[t] = exp((double)sc);
+          }
+          named_bar_sync(1, ENG_NCONS);
+          if (P.strict) {
+            if (c == 0) {
               double z = 0.0;
-              for (int t = tt; t < T; t += 128) z = __dadd_rn(z, eh[t]);
+              for (int t = 0; t < T; t++) z = __dadd_rn(z, sE[t]);
+              sZ[4] = z;
+            }
+          } else if (c < 128) {
+            double z = 0.0;
+            for (int t = c; t < T; t += 128) z = __dadd_rn(z, sE[t]);
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, o));
-              if ((tt & 31) == 0) sZ[hh * 4 + (tt >> 5)] = z;
-            }
+            for (int o = 16; o > 0; o >>= 1) z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, o));
+            if ((c & 31) == 0) sZ[c >> 5] = z;
           }
           named_bar_sync(1, ENG_NCONS);
-          if (!P.strict)
-            for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128)
-              if (tt == 0) sZ[n_rep * 4 + hh] = __dadd_rn(__dadd_rn(__dadd_rn(sZ[hh * 4 + 0], sZ[hh * 4 + 1]), sZ[hh * 4 + 2]), sZ[hh * 4 + 3]);
+          if (!P.strict && c == 0) sZ[4] = __dadd_rn(__dadd_rn(__dadd_rn(sZ[0], sZ[1]), sZ[2]), sZ[3]);
           named_bar_sync(1, ENG_NCONS);
-          for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128) {
-            const double Z = sZ[n_rep * 4 + hh];
-            const double* eh = sE + (size_t)hh * T_max;
-            float* phh = sP + (size_t)hh * T_max;
-            for (int t = tt; t < T; t += 128) phh[t] = trunc_bf((float)__ddiv_rn(eh[t], Z));
+          {
+            const double Z = sZ[4];
+            for (int t = c; t < T; t += ENG_NCONS) sP[t] = trunc_bf((float)__ddiv_rn(sE[t], Z));
           }
           named_bar_sync(1, ENG_NCONS);
-          for (int hh = c >> 7; hh < n_rep; hh += ENG_NCONS / 128) {
-            if (tt < hd) {
-              const float* phh = sP + (size_t)hh * T_max;
-              const uint16_t* vc = sV + tt;
-              float a = 0.f;
+          if (c < hd) {
+            const uint16_t* vc = sV + c;
+            float a = 0.f;
 #pragma unroll 4
-              for (int t = 0; t < T; t++) a = __fmaf_rn(phh[t], bf2f(vc[(size_t)t * hd]), a);
-              E->o[(size_t)(h * n_rep + hh) * hd + tt] = f2bf(a);
-            }
+            for (int t = 0; t < T; t++) a = __fmaf_rn(sP[t], bf2f(vc[(size_t)t * hd]), a);
+            E->out_t[(size_t)H * hd + c] = (tag_now << 16) | f2bf(a);
           }
         }
       } else if (type == EP_REDUCE) {
@@ -875,8 +904,10 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             const uint2 w = eng_wait_word(P, base + (size_t)rk * P.p2p.slot_elems + i, epoch, rk, t0);
             sum = (rk == 0) ? __uint_as_float(w.x) : __fadd_rn(sum, __uint_as_float(w.x));
           }
-          const uint16_t* resp = (E->flags & EF_RES_TOKEN) ? P.emb + (size_t)tok * P.dim : E->res;
-          E->out_bf16[i] = f2bf(__fadd_rn(bf2f(ldcg_u16(resp + i)), trunc_bf(sum)));
+          float rsd;
+          if (E->flags & EF_RES_TOKEN) rsd = bf2f(ldcg_u16(P.emb + (size_t)tok * P.dim + i));
+          else rsd = tagged_f32(wait_tagged_word(E->res_t + i, (tag_now - (uint32_t)E->res_delta) << 16));
+          E->out_t[i] = (tag_now << 16) | f2bf(__fadd_rn(rsd, trunc_bf(sum)));
         }
         epoch++;
       } else if (type == EP_ARGMAX) {
@@ -885,7 +916,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         const unsigned long long t0 = global_timer_ns();
         const size_t myoff = ((size_t)((epoch & 1u) * P.p2p.n + P.p2p.rank)) * P.p2p.slot_elems;
         if (bid == 0 && c < P.p2p.n) {
-          const unsigned long long mykey = __ldcg(&P.st->amax_key);
+          const unsigned long long mykey = __ldcg(keys[step & 1]);
           P.p2p.data[c][myoff] = make_uint2((uint32_t)(mykey & 0xffffffffull), epoch);
           P.p2p.data[c][myoff + 1] = make_uint2((uint32_t)(mykey >> 32), epoch);
         }
@@ -908,27 +939,32 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         tok = ctl->tok;
         continue;                                  // purely local result: no grid barrier
       }
-      // ---- end of phase: everybody's outputs become visible to everybody ----------------------------------------
+      // ---- end of phase ---------------------------------------------------------------------------------------------
       if (P.prof && c == 0) {
         const long long t_now = clock64();
         if (type == EP_SDPA) P.prof[bid * ENG_NPROF + 4] += (unsigned long long)(t_now - t_mark);
         else if (type == EP_REDUCE) P.prof[bid * ENG_NPROF + 5] += (unsigned long long)(t_now - t_mark);
         t_mark = t_now;
       }
+      if (!(E->flags & EF_GRID_SYNC)) {
+        named_bar_sync(1, ENG_NCONS);              // the CTA's own scratch (gp, s_x, s_part) changes hands
+        continue;
+      }
+      // the LM head: its argmax key is an atomic maximum over all CTAs -> one real grid barrier per step.  It also orders
+      // this step's plain stores (KV cache rows) before the next step's plain loads.
       n_bar++;
       eng_grid_barrier(P, n_bar * (unsigned int)G, c);
       if (P.prof && c == 0) { const long long t_now = clock64(); P.prof[bid * ENG_NPROF + 0] += (unsigned long long)(t_now - t_mark); t_mark = t_now; }
-      if (key_reset_due) {                         // every CTA has read the previous step's key by now
-        if (bid == 0 && c == 0) P.st->amax_key = LNB_ARGMAX_EMPTY;
-        key_reset_due = false;
-      }
       if (type == EP_GEMV && E->epi == EPI_LOGITS && P.tp == 1) {
-        const unsigned long long key = __ldcg(&P.st->amax_key);
+        const unsigned long long key = __ldcg(keys[step & 1]);
         tok = (key == LNB_ARGMAX_EMPTY) ? -1 : (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+      }
+      if (bid == 0 && c == 0) {                    // everyone is past the previous step's reads of the other key
+        atomicExch(keys[(step + 1) & 1], LNB_ARGMAX_EMPTY);
+        __threadfence();
       }
     }
     // ---- end of step: greedy token known to every CTA ------------------------------------------------------------
-    key_reset_due = true;
     if (bid == 0 && c == 0 && P.advance && P.tok_out) P.tok_out[P.st->step + step] = tok;
     pos += 1;
   }

@@ -75,6 +75,12 @@ struct GemvParams {
   int m_off;               // index of activation row 0 of this launch inside the forward call (row blocking)
   LnbP2P p2p;              // EPI_P2P: peer regions (st must be set: epoch / done counters live in the device state)
   uint32_t ar_epoch_override;  // EPI_P2P inside the persistent engine: the epoch is tracked per CTA, not in st (0: use st)
+  // persistent engine only: activations travel between phases as self-validating words {tag:16 | bf16:16} (engine.cuh)
+  unsigned long long* amax_key_ptr;  // EPI_LOGITS: the argmax key to maximise (NULL: &st->amax_key)
+  uint32_t* out_t;         // tagged output vector (NULL: plain bf16 output)
+  uint32_t tag_hi;         // this phase's tag << 16
+  const uint32_t* res_t;   // tagged residual vector (NULL: plain `res`)
+  uint32_t res_tag_hi;     // tag << 16 of the phase that produced the residual
 };
 
 template <int TN, int KS, int MB, int KT, int NST>
@@ -97,6 +103,17 @@ struct GemvCfg {
   }
 };
 
+// one word of a tagged activation vector, as soon as its producer has stored it (bounded: a word that never comes is a
+// bug or a dead SM -> trap, never a hang)
+LNB_DEVINL uint32_t wait_tagged_word(const uint32_t* p, uint32_t tag_hi) {
+  uint32_t w, spins = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
+    if ((w & 0xffff0000u) == tag_hi) return w;
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Epilogue of one output element: v = the untruncated fp32 dot product of activation row em with
 // weight row n.  Must be called by all 32 lanes of a warp (it shuffles); lane == tile row % 32.
@@ -118,8 +135,10 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
   } else if (EPI == EPI_RESID) {
     if (valid) {
       float a = trunc_bf(v);
-      float rsd = bf2f(p.res[(size_t)em * p.ldo + n]);
-      p.out_bf16[(size_t)em * p.ldo + n] = f2bf(__fadd_rn(rsd, a));
+      float rsd = p.res_t ? __uint_as_float(wait_tagged_word(p.res_t + n, p.res_tag_hi) << 16) : bf2f(p.res[(size_t)em * p.ldo + n]);
+      const uint16_t o = f2bf(__fadd_rn(rsd, a));
+      if (p.out_t) p.out_t[n] = p.tag_hi | o;
+      else p.out_bf16[(size_t)em * p.ldo + n] = o;
     }
   } else if (EPI == EPI_LOGITS) {
     float lv = trunc_bf(v);
@@ -132,7 +151,7 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
         unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
         key = other > key ? other : key;
       }
-      if (lane == 0 && key != LNB_ARGMAX_EMPTY) atomicMax(&p.st->amax_key, key);
+      if (lane == 0 && key != LNB_ARGMAX_EMPTY) atomicMax(p.amax_key_ptr ? p.amax_key_ptr : &p.st->amax_key, key);
     }
   } else if (EPI == EPI_QKV_ROPE) {
     // rows [0,q_dim) = q, [q_dim, q_dim+kv_dim) = k, rest = v.  RoPE pairs (2i,2i+1) are
@@ -158,9 +177,11 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
           const double a = (double)other, b = (double)mine;
           o = (float)(a * dd + b * cc);
         }
-        if (n < p.q_dim) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(o);
+        if (p.out_t) p.out_t[n] = p.tag_hi | f2bf(o);                   // engine: q, and this step's k row for the attention phase
+        if (n < p.q_dim) { if (!p.out_t) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(o); }
         else ck[(size_t)pos * p.kv_dim + nn] = f2bf(o);                  // SetSlice :402
       } else {
+        if (p.out_t) p.out_t[n] = p.tag_hi | f2bf(mine);
         cv[(size_t)pos * p.kv_dim + (n - p.q_dim - p.kv_dim)] = f2bf(mine);         // :403
       }
     }
@@ -173,7 +194,8 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
     if (valid && (er & 4) == 0) {
       const uint16_t sg = p.silu_tab[f2bf(mine)];                       // t(TABLE_SILU[bits]) activations.go:38
       const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
-      p.out_bf16[(size_t)em * p.ldo + (size_t)panel * 4 + (er & 3)] = f2bf(mm);
+      if (p.out_t) p.out_t[(size_t)panel * 4 + (er & 3)] = p.tag_hi | f2bf(mm);
+      else p.out_bf16[(size_t)em * p.ldo + (size_t)panel * 4 + (er & 3)] = f2bf(mm);
     }
   }
 }

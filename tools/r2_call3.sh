@@ -3,10 +3,8 @@ set -u
 mkdir -p gpurun_out
 OUT=gpurun_out/r2_call3.log
 {
-  nvidia-smi --query-gpu=name,clocks.sm,clocks.mem,power.limit,temperature.gpu --format=csv,noheader
-  echo "== chain kbench (reference on this box)"; LNB_ENGINE=0 timeout 200 python tools/kbench.py fast 2>&1 | tail -2
-  echo "== engine kbench PF=0 (nested-loop producer)"; LNB_ENGINE_PF_KB=0 timeout 200 python tools/kbench.py fast,strict 2>&1 | tail -4
-  echo "== engine kbench PF=256 (iterator producer + L2 prefetch)"; LNB_ENGINE_PF_KB=256 timeout 200 python tools/kbench.py fast,strict 2>&1 | tail -4
-  echo "== engine kbench PF=1 (iterator producer, ~no prefetch)"; LNB_ENGINE_PF_KB=1 timeout 200 python tools/kbench.py fast 2>&1 | tail -2
+  echo "== engine tests"; timeout 400 python -m pytest tests/test_gpu_engine.py tests/test_gpu_8b.py tests/test_gpu_model.py -q -x 2>&1 | tail -8
+  echo "== prefetch window sweep"; timeout 400 python tools/engine_sweep.py 0,256,1024,4096 2>&1 | tail -8
+  echo "== engine profile"; timeout 300 python tools/engine_prof.py fast,strict 2>&1 | tail -40
 } > "$OUT" 2>&1
 tail -60 "$OUT"
