@@ -116,6 +116,14 @@ __host__ __device__ inline void eng_split(int P, int b, int G, int* lo, int* hi)
   *lo = (int)(((long long)P * b) / G);
   *hi = (int)(((long long)P * (b + 1)) / G);
 }
+// k-tile of a row tile with np panels: the phase's kt (sized for full tiles), doubled while the stage has room -- a row
+// tile of 1 panel at kt = 256 would move 4 KB per stage and crawl at the ring's latency (4 stages x 4 KB per ~1.2 us).
+// FAST only: the STRICT chain tiles are compile-time unrolled for kt <= 512.
+__host__ __device__ inline int eng_tile_kt(int ks, int np, int K, int kt, int stage_bytes) {
+  if (ks == 1 || true) return kt;   // (scaling measured slower on B200: kept for the record, disabled)
+  while (kt * 2 <= K && kt * 2 <= 2048 && np * (kt * 2) * 16 <= stage_bytes && K % (kt * 2) == 0) kt *= 2;
+  return kt;
+}
 // shared-memory need of the attention phase for T_max rows
 __host__ __device__ inline size_t eng_sdpa_smem(int T_max, int hd, int n_rep) {
   return (size_t)T_max * ((hd + 8) + hd) * 2 + (size_t)n_rep * ((size_t)T_max * 12 + (size_t)hd * 4) + (size_t)n_rep * 5 * 8 + 64;
@@ -214,10 +222,20 @@ LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch,
   float sq[CH];
   float inc = 0.f;
   if (on) {
+    // 128-bit loads: a thread's CH consecutive floats, read one by one, would be a CH-way bank conflict (stride CH words)
+    if (CH % 4 == 0) {
 #pragma unroll
-    for (int k = 0; k < CH; k++) {
-      const float v = s_x[t * CH + k];
-      sq[k] = __fmul_rn(v, v);
+      for (int k = 0; k < CH; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(s_x + t * CH + k);
+        sq[k] = __fmul_rn(v.x, v.x); sq[k + 1] = __fmul_rn(v.y, v.y);
+        sq[k + 2] = __fmul_rn(v.z, v.z); sq[k + 3] = __fmul_rn(v.w, v.w);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CH; k++) {
+        const float v = s_x[t * CH + k];
+        sq[k] = __fmul_rn(v, v);
+      }
     }
     float cs = 0.f;
 #pragma unroll
@@ -319,11 +337,11 @@ LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch,
       uint32_t nb;
       if (e > cidx && seq_try_jump(sb, E, run, &nb)) { sb = nb; cidx = e; continue; }
       float s = __uint_as_float(sb);
+      float xs[CH];
 #pragma unroll
-      for (int k = 0; k < CH; k++) {
-        const float xv = s_x[cidx * CH + k];
-        s = __fadd_rn(s, __fmul_rn(xv, xv));
-      }
+      for (int k = 0; k < CH; k++) xs[k] = s_x[cidx * CH + k];       // (vectorised by the compiler: the row is 16-byte aligned)
+#pragma unroll
+      for (int k = 0; k < CH; k++) s = __fadd_rn(s, __fmul_rn(xs[k], xs[k]));
       sb = __float_as_uint(s);
       cidx++;
     }
@@ -383,9 +401,11 @@ LNB_DEVINL float eng_chain_tile(const uint8_t* __restrict__ tile, const float* _
 }
 
 // four consecutive words of a tagged vector, polled until all of them carry `tag_hi`
+// (relaxed at gpu scope, not volatile: volatile loads are kept in order by the hardware, one L2 round trip each -- a
+// thread's 4..14 polling loads of a prologue must be in flight together)
 LNB_DEVINL uint4 ld_volatile_u4(const uint32_t* p) {
   uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 LNB_DEVINL bool tags_ok(const uint4& v, uint32_t tag_hi) {
@@ -459,6 +479,8 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         for (int rt = p0; rt < p1; rt += PT) {
           const int np = min(PT, p1 - rt);
           const uint8_t* src_row = wbase + (size_t)(rt + tid) * (size_t)K * 16u;
+          const int kt = eng_tile_kt(KS, np, K, E->kt, STAGE);
+          const int n_tiles = (K + kt - 1) / kt;
           for (int t = 0; t < n_tiles; t++, seq++) {
             const int s = seq % NST;
             const uint32_t par = (seq / NST) & 1u;
@@ -499,6 +521,8 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         const uint8_t* wbase = reinterpret_cast<const uint8_t*>(E->W);
         for (int rt = p0; rt < p1; rt += PT) {
           const int np = min(PT, p1 - rt);
+          const int kt = eng_tile_kt(KS, np, K, E->kt, STAGE);
+          const int n_tiles = (K + kt - 1) / kt;
           for (int t = 0; t < n_tiles; t++) {
             const uint32_t bpp = (uint32_t)min(kt, K - t * kt) * 16u;
             const unsigned long long tile_bytes = (unsigned long long)bpp * (unsigned long long)np;
@@ -556,24 +580,6 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
         const uint32_t* xtg = (flags & EF_X_TOKEN) ? nullptr : E->x_t;
         const uint32_t x_tag_hi = (tag_now - (uint32_t)E->x_delta) << 16;
         if (p1 > p0) {
-          // ---- the phase as gemv_epilogue sees it ------------------------------------------------------------
-          if (c == 0) {
-            GemvParams g{};
-            g.W = E->W; g.N = E->N; g.K = K; g.M = 1;
-            g.x = xg; g.ldx = E->ldx; g.norm_w = E->norm_w; g.eps = P.eps;
-            g.out_bf16 = E->out_bf16; g.out_f32 = E->out_f32; g.ldo = E->ldo;
-            g.res = (flags & EF_RES_TOKEN) ? P.emb + (size_t)tok * P.dim : E->res;
-            g.q_dim = E->q_dim; g.kv_dim = E->kv_dim; g.head_dim = P.head_dim;
-            g.cache_k = E->cache_k; g.cache_v = E->cache_v; g.pos_arr = nullptr; g.cache_seq_stride = 0;
-            g.cis = P.cis; g.silu_tab = P.silu_tab;
-            g.n_offset = E->n_offset; g.st = P.st; g.amax_key_ptr = keys[step & 1]; g.argmax_row = 0; g.publish = 0; g.advance = 0; g.tok_out = nullptr;
-            g.pos_ptr = &ctl->pos; g.m_off = 0;
-            g.p2p = P.p2p;
-            g.ar_epoch_override = epoch;
-            g.out_t = E->out_t; g.tag_hi = tag_now << 16;
-            g.res_t = (flags & EF_RES_TOKEN) ? nullptr : E->res_t; g.res_tag_hi = (tag_now - (uint32_t)E->res_delta) << 16;
-            *gp = g;
-          }
           // ---- prologue: activations -> f32 in shared memory (gemv.cuh prologue, MB = 1) -----------------------
           // all global loads of a thread are issued before the first shared-memory store (the compiler cannot prove
           // that the generic pointers do not alias shared memory and would serialise them, one L2 round trip each)
@@ -595,6 +601,24 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
                   }
                   if (with_w) wv[u] = __ldg(reinterpret_cast<const uint4*>(E->norm_w + (size_t)ch * 8));
                 }
+              }
+          // ---- the phase as gemv_epilogue sees it ------------------------------------------------------------
+                  if (c == 0 && base == 0) {   // (while this thread's input loads are in flight)
+                GemvParams g{};
+                g.W = E->W; g.N = E->N; g.K = K; g.M = 1;
+                g.x = xg; g.ldx = E->ldx; g.norm_w = E->norm_w; g.eps = P.eps;
+                g.out_bf16 = E->out_bf16; g.out_f32 = E->out_f32; g.ldo = E->ldo;
+                g.res = (flags & EF_RES_TOKEN) ? P.emb + (size_t)tok * P.dim : E->res;
+                g.q_dim = E->q_dim; g.kv_dim = E->kv_dim; g.head_dim = P.head_dim;
+                g.cache_k = E->cache_k; g.cache_v = E->cache_v; g.pos_arr = nullptr; g.cache_seq_stride = 0;
+                g.cis = P.cis; g.silu_tab = P.silu_tab;
+                g.n_offset = E->n_offset; g.st = P.st; g.amax_key_ptr = keys[step & 1]; g.argmax_row = 0; g.publish = 0; g.advance = 0; g.tok_out = nullptr;
+                g.pos_ptr = &ctl->pos; g.m_off = 0;
+                g.p2p = P.p2p;
+                g.ar_epoch_override = epoch;
+                g.out_t = E->out_t; g.tag_hi = tag_now << 16;
+                g.res_t = (flags & EF_RES_TOKEN) ? nullptr : E->res_t; g.res_tag_hi = (tag_now - (uint32_t)E->res_delta) << 16;
+                *gp = g;
               }
 #pragma unroll
               for (int u = 0; u < 4; u++) {
@@ -620,6 +644,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             }
           }
           named_bar_sync(1, ENG_NCONS);
+          if (P.prof && c == 0) { const long long t_now = clock64(); P.prof[bid * ENG_NPROF + 6] += (unsigned long long)(t_now - t_mark); t_mark = t_now; }
           if (E->pro == PRO_RMSNORM) {
             if (P.strict) {
               int ch = 0, nt = 0;
@@ -664,6 +689,8 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
           if (KS > 1 || cw < Cfg::kChainWarps) {
             for (int rt = p0; rt < p1; rt += PT) {
               const int np = min(PT, p1 - rt);
+              const int kt = eng_tile_kt(KS, np, K, E->kt, STAGE);
+              const int n_tiles = (K + kt - 1) / kt;
               // FAST: this thread's rows are r and r + 32 of the 64-row tile; STRICT: row c of the 128-row tile
               const int pp0 = r >> 3, rr = r & 7;
               const int pp1 = pp0 + 4;
@@ -704,7 +731,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
                   // Rows beyond the tile's panels read whatever the stage holds (finite or not, it is never stored:
                   // `valid` is false for them) -- unconditional loads keep the loop free of predicates -- and the next
                   // chunk's operands are loaded before the current chunk's 16 FMAs issue.
-                  const uint8_t* tile1 = tile0 + 4 * ((size_t)kt * 16);
+                  const uint8_t* tile1 = tile0 + 4 * ((size_t)kt * 16);   // (within shared memory for every kt <= 512)
 #ifdef ENG_FAST_SIMPLE
 #pragma unroll 4
                   for (int ch = j; ch < nchunks; ch += KS) {

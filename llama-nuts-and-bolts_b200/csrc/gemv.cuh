@@ -108,7 +108,7 @@ struct GemvCfg {
 LNB_DEVINL uint32_t wait_tagged_word(const uint32_t* p, uint32_t tag_hi) {
   uint32_t w, spins = 0;
   for (;;) {
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(p));
     if ((w & 0xffff0000u) == tag_hi) return w;
     if (++spins > (1u << 28)) __trap();
   }
