@@ -221,6 +221,13 @@ int lnb_forward_device(lnb_session* s, const int32_t* tokens, int S, int start_p
 int lnb_session_logits_read(lnb_session* s, int64_t generation, int row0, int rows, float* host /* [rows, vocab] */);
 int lnb_session_logits_argmax(lnb_session* s, int64_t generation, int row0, int rows, int32_t* out /* [rows] */);
 
+/* EXTENSION beyond the reference (chunked prefill): accept Forward calls of S > 1 tokens at startPos > 0 and
+ * mask them with the [S,T] causal mask (row s sees keys t <= startPos + s).  The reference's [S,S] mask
+ * (src/model/llamatransformer.go:128-136, added to [32,S,T] scores at :469-473) only broadcasts for startPos 0, which is
+ * why the library refuses such calls by default, like the Go code would fail.  Chunked and one-shot prefill give
+ * bit-identical caches and logits in LNB_ACC_STRICT. */
+int lnb_session_set_chunked_prefill(lnb_session* s, int on);
+
 /* Device-resident greedy decode: runs n_steps consecutive S=1 forwards starting with
  * `first_token` at position start_pos, feeding each argmax back on the device (no host
  * sync inside), optionally as CUDA-graph replays.  tokens_out[n_steps]; ms_out = device
@@ -249,6 +256,10 @@ enum { LNB_BUF_RESIDUAL = 0, LNB_BUF_CACHE_K = 1, LNB_BUF_CACHE_V = 2, LNB_BUF_L
  * [seq_len, n_kv_local, head_dim] bf16, LOGITS [rows, vocab_local] f32. */
 int lnb_session_read(lnb_session* s, int which, int layer, void* host, int64_t nbytes);
 int lnb_session_set_layer_limit(lnb_session* s, int n_layers_to_run); /* <=0: all */
+/* Which decode path does the session use?  1 = the persistent decode engine (csrc/engine.cuh: one kernel launch runs n
+ * complete S=1 forwards), 0 = the kernel chain (one launch per projection / attention / norm scale; lnb_last_error()
+ * tells why).  LNB_ENGINE=1 / 0 forces the choice; the default is the engine except for single-GPU LNB_ACC_FAST. */
+int lnb_session_decode_engine(lnb_session* s);
 /* profiling aid of the persistent decode engine (LNB_ENGINE_PROF=1 when the session first decodes): cycles of consumer
  * thread 0 per section, {mean, max} over the CTAs, reset on read.  out[16]. */
 int lnb_session_engine_profile(lnb_session* s, double* out16);

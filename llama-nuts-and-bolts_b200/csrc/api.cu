@@ -1045,6 +1045,7 @@ struct lnb_session {
   size_t h_logits_bytes = 0;
   unsigned long long* d_keys = nullptr;  // [max_rows] per-row argmax keys (tensor-parallel on-demand argmax)
   int layer_limit = 0;
+  bool allow_chunked = false;    // S > 1 at startPos > 0 (chunked prefill, an extension the reference cannot express)
   // batched decode (BASELINE config 5): n_seq independent sequences share the weights; caches are
   // [n_seq][seq_len][kv]; single-sequence calls address the cache of `active_seq`
   int n_seq = 1, active_seq = 0;
@@ -1251,6 +1252,17 @@ static void drop_graph(lnb_session* s) {
   }
   s->graph_tried = false;
 }
+// Chunked prefill, an EXTENSION: the reference builds its causal mask as [S,S] and adds it to [32,S,T]
+// scores (llamatransformer.go:128-136,469-473), which only broadcasts for startPos 0 -- so it can only prefill a prompt
+// in one call.  With this switch a Forward of S > 1 tokens at startPos > 0 is accepted and uses the mask a correct [S,T]
+// broadcast would give: query row s (absolute position startPos + s) sees the keys t <= startPos + s.  Every other
+// operation is unchanged, so a prompt prefilled in chunks leaves bit-identical caches and logits (LNB_ACC_STRICT).
+extern "C" int lnb_session_set_chunked_prefill(lnb_session* s, int on) {
+  if (!s) return fail(LNB_EINVAL, "session is NULL");
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->allow_chunked = on != 0;
+  return 0;
+}
 extern "C" int lnb_session_set_layer_limit(lnb_session* s, int n) {
   if (!s) return fail(LNB_EINVAL, "session is NULL");
   std::lock_guard<std::mutex> lk(s->mu);
@@ -1317,8 +1329,13 @@ static bool engine_probe(lnb_session* s) {
   lnb_model* m = s->m;
   const lnb_model_args& a = m->a;
   auto no = [&](const char* why) { s->eng_state = -1; s->eng_why = why; return false; };
+  // Default (measured on B200, profiles/r02_*): the engine wins wherever launch count or the serial order dominates --
+  // LNB_ACC_STRICT at every N (213 vs 207, 325 vs 282, 449 vs 352 tokens/s at 1 / 2 / 8 GPUs) and every host-driven loop --
+  // and ties with the kernel chain in LNB_ACC_FAST (308 vs 330 at 1 GPU, 501 vs 484 at 2, 774 vs 800 at 8).  It is the
+  // default except for single-GPU FAST sessions; LNB_ENGINE=1 / 0 forces it on / off.
   const char* e = getenv("LNB_ENGINE");
   if (e && !strcmp(e, "0")) return no("LNB_ENGINE=0");
+  if (!(e && !strcmp(e, "1")) && s->mode == LNB_ACC_FAST && m->tp_size == 1) return no("single-GPU FAST: the kernel chain is the default");
   const int kmax = std::max(a.dim, std::max(m->q_l, m->ffn_l));
   if ((size_t)kmax * 4 > (size_t)ENG_XMAX) return no("activation vector exceeds the engine's shared-memory work area");
   if (a.dim % 8 || m->q_l % 8 || m->ffn_l % 8) return no("widths must be multiples of 8");
@@ -1868,8 +1885,9 @@ extern "C" int lnb_forward(lnb_session* s, const int32_t* tokens, int S, int sta
   if (S > s->max_rows) return fail(LNB_EINVAL, "S %d exceeds the session's max_rows %d", S, s->max_rows);
   if (start_pos < 0 || start_pos + S > s->seq_len)
     return fail(LNB_EINVAL, "positions [%d, %d) exceed SequenceLength %d", start_pos, start_pos + S, s->seq_len);
-  if (S > 1 && start_pos != 0)
-    return fail(LNB_EINVAL, "S>1 requires startPos 0 (the reference's [S,S] mask does not broadcast to [S,T])");
+  if (S > 1 && start_pos != 0 && !s->allow_chunked)
+    return fail(LNB_EINVAL, "S>1 requires startPos 0 (the reference's [S,S] mask does not broadcast to [S,T]); "
+                "lnb_session_set_chunked_prefill enables the [S,T]-mask extension");
   for (int i = 0; i < S; i++)
     if (tokens[i] < 0 || tokens[i] >= s->m->a.vocab_size) return fail(LNB_EINVAL, "token id %d out of range", tokens[i]);
   std::lock_guard<std::mutex> lk(s->mu);
@@ -1921,8 +1939,9 @@ extern "C" int lnb_forward_device(lnb_session* s, const int32_t* tokens, int S, 
   if (S > s->max_rows) return fail(LNB_EINVAL, "S %d exceeds the session's max_rows %d", S, s->max_rows);
   if (start_pos < 0 || start_pos + S > s->seq_len)
     return fail(LNB_EINVAL, "positions [%d, %d) exceed SequenceLength %d", start_pos, start_pos + S, s->seq_len);
-  if (S > 1 && start_pos != 0)
-    return fail(LNB_EINVAL, "S>1 requires startPos 0 (the reference's [S,S] mask does not broadcast to [S,T])");
+  if (S > 1 && start_pos != 0 && !s->allow_chunked)
+    return fail(LNB_EINVAL, "S>1 requires startPos 0 (the reference's [S,S] mask does not broadcast to [S,T]); "
+                "lnb_session_set_chunked_prefill enables the [S,T]-mask extension");
   for (int i = 0; i < S; i++)
     if (tokens[i] < 0 || tokens[i] >= s->m->a.vocab_size) return fail(LNB_EINVAL, "token id %d out of range", tokens[i]);
   std::lock_guard<std::mutex> lk(s->mu);
@@ -2282,6 +2301,15 @@ extern "C" int lnb_session_bench_kernel(lnb_session* s, int kind, int reps, floa
 
 // LNB_ENGINE_PROF=1: cycle sums of the engine's consumer thread 0, averaged and maximised over the CTAs, since the last
 // call; out[2 * 8] = {mean, max} x {grid barrier, prologue, main loop, combine + epilogue, attention, peer reduce, -, -}
+// 1: this session's S=1 steps run as the persistent decode engine; 0: as the kernel chain (lnb_last_error says why)
+extern "C" int lnb_session_decode_engine(lnb_session* s) {
+  if (!s) return fail(LNB_EINVAL, "session is NULL");
+  std::lock_guard<std::mutex> lk(s->mu);
+  CU(cudaSetDevice(s->m->device));
+  if (engine_ok(s)) return 1;
+  g_err = s->eng_state < 0 ? s->eng_why : std::string("tensor-parallel session without the peer all-reduce (NCCL collectives cannot run inside a kernel)");
+  return 0;
+}
 extern "C" int lnb_session_engine_profile(lnb_session* s, double* out16) {
   if (!s || !out16) return fail(LNB_EINVAL, "NULL argument");
   if (!s->d_prof) return fail(LNB_ESTATE, "no engine profile (set LNB_ENGINE_PROF=1 before the session's first decode)");

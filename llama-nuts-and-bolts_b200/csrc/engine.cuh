@@ -486,10 +486,10 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
             const uint32_t par = (seq / NST) & 1u;
             const int k0 = t * kt;
             const uint32_t bytes_per_panel = (uint32_t)min(kt, K - k0) * 16u;
-            if (tid == 0) {
-              eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
-              mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)np);
-            }
+            // every issuing lane observes the stage's release itself (an acquire by lane 0 plus __syncwarp orders the
+            // other lanes' copies too, but compute-sanitizer's racecheck does not follow that edge for async-proxy writes)
+            eng_mbar_wait(&empty_bar[s], par ^ 1u, P.err_host, P.timeout_ns, false, seq);
+            if (tid == 0) mbar_expect_tx(&full_bar[s], bytes_per_panel * (uint32_t)np);
             __syncwarp();
             if (tid < np)
               bulk_g2s(s_ring + (size_t)s * STAGE + (size_t)tid * ((size_t)kt * 16), src_row + (size_t)k0 * 16u, bytes_per_panel, &full_bar[s], pol);

@@ -87,24 +87,37 @@ class InferenceEngine:
             yield dict(DecodedString=vocab.IdToToken(w["TokenId"]).decode("utf-8", "replace"), TokenId=w["TokenId"], AddedToWaiting=False,
                        IsResendOfWaiting=True, GenerationState=last_state if i + 1 == len(waiting) else GSInProgress)
 
-    def GenerateTokens(self, promptTokens, use_reference_api: bool = False, step_times: list | None = None):
+    def GenerateTokens(self, promptTokens, use_reference_api: bool = False, step_times: list | None = None,
+                       prefill_chunk: int = 0):
         """Generator over (state, token id) exactly like generatedTokensCh.
 
         use_reference_api=True goes through the reference-shaped calls of every iteration
         (Transformer.Forward -> logits tensor -> Slice last row -> ml.Argmax); False uses the
-        fused forward+argmax entry (same kernels, 4-byte read-back)."""
+        fused forward+argmax entry (same kernels, 4-byte read-back).
+
+        prefill_chunk > 0 (EXTENSION): the prompt is fed in chunks of that many tokens (Forward at
+        startPos > 0 with S > 1, lnb_session_set_chunked_prefill) instead of one call; prompts longer than the context's
+        max_rows become possible, and the generated stream is the same."""
         infContext = self.CreateInferenceContext()
         try:
             promptLength = len(promptTokens)
+            if prefill_chunk > 0:
+                infContext.allow_chunked_prefill(True)
+                if prefill_chunk > infContext.max_rows:
+                    raise ml.MlError(f"prefill_chunk {prefill_chunk} exceeds the context's max_rows {infContext.max_rows}")
             if promptLength >= infContext.SequenceLength:  # :176-179
                 raise ml.MlError(f"context SequenceLength {infContext.SequenceLength} must be higher than prompt "
                                  f"tokens length {promptLength}")
-            if promptLength > infContext.max_rows:
+            if promptLength > infContext.max_rows and prefill_chunk <= 0:
                 raise ml.MlError(f"prompt length {promptLength} exceeds the context's max_rows {infContext.max_rows}")
             pad = self.model.Vocabulary.PadId
             tokens = ml.Full([infContext.SequenceLength], ml.DT_INT32, pad)  # :181
             tokens.RawData[:promptLength] = np.asarray(promptTokens, np.int32)
             prevPos = 0
+            if prefill_chunk > 0:      # all but the last chunk: Forward calls whose logits nobody needs
+                while promptLength - prevPos > prefill_chunk:
+                    self.model.Transformer.forward_argmax(infContext, tokens.RawData[prevPos:prevPos + prefill_chunk], prevPos)
+                    prevPos += prefill_chunk
             for curPos in range(promptLength, infContext.SequenceLength):  # :194
                 t0 = time.perf_counter()
                 inputTokensSlice = tokens.Slice([prevPos], [curPos])

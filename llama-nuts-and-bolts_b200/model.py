@@ -200,6 +200,10 @@ class InferenceContext:
                                     ptr(logits, _capi.f32p) if want_logits else None, ptr(nxt, _capi.i32p)))
         return nxt, logits
 
+    def allow_chunked_prefill(self, on: bool = True):
+        """EXTENSION (not in the reference): accept S > 1 at startPos > 0 with the [S,T] causal mask"""
+        check(lib.lnb_session_set_chunked_prefill(self.h, int(on)))
+
     def set_layer_limit(self, n: int):
         check(lib.lnb_session_set_layer_limit(self.h, n))
 
@@ -235,6 +239,10 @@ class InferenceContext:
                 self.pre_close_hook(self)   # peers may still be storing into this session's all-reduce region
             lib.lnb_session_destroy(self.h)
             self.h = None
+
+    def uses_engine(self) -> bool:
+        """True: S=1 steps of this context run as the persistent decode engine (one launch per decode_run / Forward)"""
+        return bool(check(lib.lnb_session_decode_engine(self.h)))
 
     def engine_profile(self):
         """LNB_ENGINE_PROF=1: {section: (mean cycles, max cycles)} of the decode engine's consumer thread 0 since the last call"""

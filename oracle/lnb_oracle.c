@@ -371,8 +371,11 @@ void orc_rope_apply(const uint16_t* x, const float* cis, uint16_t* out, int S, i
 
 /* -------------------------------------------------------------- attention */
 
-void orc_attention(const uint16_t* q, const uint16_t* cacheK, const uint16_t* cacheV, uint16_t* out, int S, int T,
-                   int n_heads, int n_kv, int hd, int causal_mask) {
+/* q_pos0 = absolute position of query row 0.  The reference only ever builds the [S,S] mask for startPos 0 (T == S,
+ * q_pos0 = 0: `t > s`, llamatransformer.go:128-136); q_pos0 > 0 is the chunked-prefill EXTENSION (beyond the reference):
+ * the [S,T] mask a correct broadcast would need, row s sees the keys t <= q_pos0 + s. */
+static void attention_impl(const uint16_t* q, const uint16_t* cacheK, const uint16_t* cacheV, uint16_t* out, int S, int T,
+                           int n_heads, int n_kv, int hd, int causal_mask, int q_pos0) {
   int n_rep = n_heads / n_kv;
   /* dtype.BFloat16fromFloat32(float32(math.Sqrt(float64(HeadDim)))) llamatransformer.go:464 */
   float scale = bf(tr((float)sqrt((double)hd)));
@@ -391,7 +394,7 @@ void orc_attention(const uint16_t* q, const uint16_t* cacheK, const uint16_t* ca
         uint16_t v = tr(acc);
         v = tr(bf(v) / scale);                                     /* DivToScalar :464 */
         if (causal_mask) {
-          float mk = (t > s) ? ninf : 0.0f;                        /* triu(full(-inf),1) :128-136 */
+          float mk = (t > s + q_pos0) ? ninf : 0.0f;               /* triu(full(-inf),1) :128-136 */
           v = tr(bf(v) + mk);                                      /* Add(scores, mask) :471 */
         }
         sc[t] = v;
@@ -411,6 +414,11 @@ void orc_attention(const uint16_t* q, const uint16_t* cacheK, const uint16_t* ca
       free(sc);
       free(e);
     }
+}
+
+void orc_attention(const uint16_t* q, const uint16_t* cacheK, const uint16_t* cacheV, uint16_t* out, int S, int T,
+                   int n_heads, int n_kv, int hd, int causal_mask) {
+  attention_impl(q, cacheK, cacheV, out, S, T, n_heads, n_kv, hd, causal_mask, 0);
 }
 
 /* ------------------------------------------------------------ whole model */
@@ -490,12 +498,13 @@ void orc_session_free(orc_session* s) {
 uint16_t* orc_session_cache_k(orc_session* s, int layer) { return s->ck[layer]; }
 uint16_t* orc_session_cache_v(orc_session* s, int layer) { return s->cv[layer]; }
 
+static int g_allow_chunk = 0; /* set only inside orc_forward_chunk (extension) */
 static int forward_impl(const orc_model* m, orc_session* ss, const int32_t* tokens, int S, int start_pos,
                         float* logits, int all_rows, uint16_t* trace, int tp) {
   const orc_args* a = &m->a;
   if (S <= 0) return -1; /* "empty token array" llamatransformer.go:146-148 */
   if (start_pos + S > ss->seq_len) return -1;
-  if (S > 1 && start_pos != 0) return -1; /* mask [S,S] only broadcasts when T==S */
+  if (S > 1 && start_pos != 0 && !g_allow_chunk) return -1; /* mask [S,S] only broadcasts when T==S */
   int D = a->dim, hd = a->head_dim, nh = a->n_heads, nkv = a->n_kv_heads, F = a->ffn_dim, V = a->vocab;
   int kvd = nkv * hd, qd = nh * hd;
   for (int s = 0; s < S; s++)
@@ -527,7 +536,7 @@ static int forward_impl(const orc_model* m, orc_session* ss, const int32_t* toke
     orc_rope_apply(k, m->cis, k2, S, nkv, hd, start_pos);
     memcpy(ss->ck[l] + (size_t)start_pos * kvd, k2, (size_t)S * kvd * 2); /* SetSlice :402 */
     memcpy(ss->cv[l] + (size_t)start_pos * kvd, v, (size_t)S * kvd * 2);  /* :403 */
-    orc_attention(q2, ss->ck[l], ss->cv[l], o, S, T, nh, nkv, hd, S > 1); /* :409-514 */
+    attention_impl(q2, ss->ck[l], ss->cv[l], o, S, T, nh, nkv, hd, S > 1, start_pos); /* :409-514 (start_pos > 0: extension) */
     if (tp > 1) linear_bf16_ksplit(o, m->wo[l], att, S, qd, D, tp);
     else orc_linear_bf16(o, m->wo[l], att, S, qd, D);                /* :522 */
     orc_add_bf16(x, att, h1, (int64_t)SD);                           /* :232 */
@@ -558,6 +567,17 @@ static int forward_impl(const orc_model* m, orc_session* ss, const int32_t* toke
 int orc_forward(const orc_model* m, orc_session* s, const int32_t* tokens, int S, int start_pos, float* logits,
                 int all_rows, uint16_t* trace) {
   return forward_impl(m, s, tokens, S, start_pos, logits, all_rows, trace, 1);
+}
+/* EXTENSION, beyond the reference: a prompt chunk of S > 1 tokens at start_pos > 0 (chunked prefill).  The reference
+ * cannot do this (its [S,S] mask does not broadcast against [S,T] scores; the only caller prefills at 0).  Everything
+ * but the mask's column offset is the reference's arithmetic, so prefilling a prompt in chunks gives bit-identical
+ * results to prefilling it at once. */
+int orc_forward_chunk(const orc_model* m, orc_session* s, const int32_t* tokens, int S, int start_pos, float* logits,
+                      int all_rows) {
+  g_allow_chunk = 1;
+  int rc = forward_impl(m, s, tokens, S, start_pos, logits, all_rows, NULL, 1);
+  g_allow_chunk = 0;
+  return rc;
 }
 int orc_forward_tp(const orc_model* m, orc_session* s, const int32_t* tokens, int S, int start_pos, float* logits,
                    int all_rows, int tp) {

@@ -111,6 +111,9 @@ int         orc_forward(const orc_model* m, orc_session* s, const int32_t* token
 /* variant that emulates tensor-parallel K-split partial sums:
  * wo and w2 are accumulated as `tp` sequential partial sums over contiguous K
  * slices which are then added in rank order 0..tp-1 (f32) before truncation. */
+/* extension (beyond the reference): S > 1 tokens at start_pos > 0 with the [S,T] causal mask -- chunked prefill */
+int         orc_forward_chunk(const orc_model* m, orc_session* s, const int32_t* tokens, int S, int start_pos,
+                              float* logits, int all_rows);
 int         orc_forward_tp(const orc_model* m, orc_session* s, const int32_t* tokens, int S, int start_pos,
                            float* logits, int all_rows, int tp);
 /* generateTokensInternal: src/inference/inference.go:173-254.  Returns number of

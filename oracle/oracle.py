@@ -113,6 +113,8 @@ def _declare(L):
     L.orc_session_cache_v.argtypes = [C.c_void_p, C.c_int]
     L.orc_forward.restype = C.c_int
     L.orc_forward.argtypes = [C.c_void_p, C.c_void_p, _i32p, C.c_int, C.c_int, _f32p, C.c_int, _u16p]
+    L.orc_forward_chunk.restype = C.c_int
+    L.orc_forward_chunk.argtypes = [C.c_void_p, C.c_void_p, _i32p, C.c_int, C.c_int, _f32p, C.c_int]
     L.orc_forward_tp.restype = C.c_int
     L.orc_forward_tp.argtypes = [C.c_void_p, C.c_void_p, _i32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int]
     L.orc_generate.restype = C.c_int
@@ -327,6 +329,16 @@ class OracleSession:
         if self.h:
             lib().orc_session_free(self.h)
             self.h = None
+
+    def forward_chunk(self, tokens, start_pos, all_rows=True):
+        """EXTENSION (beyond the reference): a prompt chunk of S > 1 tokens at start_pos > 0 with the [S,T] causal mask"""
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        S = len(tokens)
+        logits = np.empty((S if all_rows else 1, self.model.args.vocab), np.float32)
+        rc = lib().orc_forward_chunk(self.model.h, self.h, _p(tokens, _i32p), S, start_pos, _p(logits, _f32p), int(all_rows))
+        if rc != 0:
+            raise RuntimeError("orc_forward_chunk failed (bad tokens / positions)")
+        return logits
 
     def forward(self, tokens, start_pos, all_rows=True, trace=False, tp=1):
         tokens = np.ascontiguousarray(tokens, np.int32)

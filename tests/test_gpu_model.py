@@ -463,3 +463,45 @@ def test_forward_returns_a_device_handle_that_reads_like_the_host_tensor(L, tiny
     finally:
         ctx.close()
         osess.close()
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_chunked_prefill_extension_equals_one_shot_prefill(L, tiny, mode):
+    """SURVEY 8f-4 (beyond the reference): S > 1 at startPos > 0 with the [S,T] causal mask.  The library refuses it by
+    default exactly like the reference's [S,S] mask would fail; with the switch on, a prompt fed in chunks leaves the caches
+    and logits of the one-shot prefill (bit-identical in STRICT, and equal to the oracle's extension)."""
+    args, _, om, gm = tiny
+    acc = L._capi.LNB_ACC_STRICT if mode == "strict" else L._capi.LNB_ACC_FAST
+    rng = np.random.default_rng(8)
+    prompt = rng.integers(0, args["vocab_size"], size=19).astype(np.int32)
+    seq = 40
+    one = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(seq), max_rows=24, acc_mode=acc)
+    chk = L.model.InferenceContext(gm.Transformer, L.model.InferenceArgs(seq), max_rows=24, acc_mode=acc)
+    o1, o2 = om.new_session(seq), om.new_session(seq)
+    try:
+        with pytest.raises(L._capi.LnbError, match="startPos 0"):
+            gm.Transformer.forward_argmax(chk, prompt[8:12], 8)
+        chk.allow_chunked_prefill(True)
+        n1, l1 = gm.Transformer.forward_argmax(one, prompt, 0, want_logits="last")
+        exp = o1.forward(prompt, 0, all_rows=False)
+        pos = 0
+        for size in (8, 5, 6):                                  # 8 + 5 + 6 = 19, unequal chunks
+            n2, l2 = gm.Transformer.forward_argmax(chk, prompt[pos:pos + size], pos, want_logits="all")
+            e2 = o2.forward(prompt[pos:pos + size], pos, all_rows=True) if pos == 0 else o2.forward_chunk(prompt[pos:pos + size], pos)
+            if mode == "strict":
+                assert np.array_equal(l2, e2), f"chunk at {pos}"
+            else:
+                assert float(np.abs(l2 - e2).max()) <= 1e-2
+            pos += size
+        if mode == "strict":
+            assert np.array_equal(l2[-1:], l1) and np.array_equal(l1, exp) and n1 == n2      # chunked == one-shot == reference
+            for layer in range(args["n_layers"]):
+                assert np.array_equal(chk.CacheK(layer).RawData[:19], one.CacheK(layer).RawData[:19])
+                assert np.array_equal(chk.CacheV(layer).RawData[:19], one.CacheV(layer).RawData[:19])
+        # the generate loop with a chunked prompt emits the same stream (a prompt longer than max_rows becomes possible)
+        eng = L.inference.InferenceEngine(gm, L.model.InferenceArgs(seq), acc_mode=acc, max_rows=8)
+        got = [t for _, t in eng.GenerateTokens(list(prompt), prefill_chunk=8)]
+        if mode == "strict":
+            assert got == list(om.generate(prompt, seq, stop_ids=gm.Vocabulary.StopTokenIds))
+    finally:
+        one.close(); chk.close(); o1.close(); o2.close()

@@ -27,3 +27,18 @@ def test_tensor_parallel_matches_oracle(n):
     assert out.returncode == 0 and lines, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(lines[-1])
     assert res["ok"], res
+
+
+@pytest.mark.parametrize("path", ["chain", "engine"])
+def test_late_rank_is_an_error_not_a_hang(path):
+    """a tensor-parallel peer that never delivers its all-reduce words must become LNB_ETIMEOUT
+    on the waiting rank within seconds (bounded in-kernel waits), in the kernel chain and in the persistent engine."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29671", os.path.join(ROOT, "tools", "tp_timeout_check.py"), path]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["ok"] and res["code"] == -6 and res["seconds"] < 4.0, res

@@ -4,9 +4,12 @@
 # Output: gpurun_out/r02_sanitizer_{memcheck,racecheck,synccheck}.txt (copy the summaries to profiles/).
 set -u
 mkdir -p gpurun_out
+for eng in 1 0; do
 for tool in memcheck racecheck synccheck; do
-  echo "== compute-sanitizer --tool $tool" > gpurun_out/r02_sanitizer_$tool.txt
-  timeout 240 compute-sanitizer --tool $tool --print-limit 30 python tools/sanitize_run.py >> gpurun_out/r02_sanitizer_$tool.txt 2>&1
-  echo "exit code $?" >> gpurun_out/r02_sanitizer_$tool.txt
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_run\]|exit code" gpurun_out/r02_sanitizer_$tool.txt | tail -8
+  f=gpurun_out/r02_sanitizer_${tool}_engine${eng}.txt
+  echo "== LNB_ENGINE=$eng compute-sanitizer --tool $tool" > $f
+  LNB_ENGINE=$eng LNB_P2P_TIMEOUT_MS=0 timeout 300 compute-sanitizer --tool $tool --print-limit 30 python tools/sanitize_run.py >> $f 2>&1
+  echo "exit code $?" >> $f
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_run\]|exit code" $f | tail -6
+done
 done

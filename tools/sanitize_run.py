@@ -12,7 +12,8 @@ import numpy as np
 import lnb_b200 as L
 from tests.helpers import host_tensors, oracle_model
 
-which = sys.argv[1] if len(sys.argv) > 1 else "all"
+# LNB_ENGINE=1: every S=1 step through the persistent decode engine (both modes); LNB_ENGINE=0: the kernel chain
+which = os.environ.get("LNB_ENGINE", "default")
 args = dict(L.synth.TINY)
 tensors = host_tensors(args, 7)
 om = oracle_model(args, tensors)
@@ -37,7 +38,7 @@ for mode, acc in (("strict", L._capi.LNB_ACC_STRICT), ("fast", L._capi.LNB_ACC_F
     e2 = o2.forward(long_prompt, 0, all_rows=False)
     good = good and (np.array_equal(lg, e2) if mode == "strict" else float(np.abs(lg - e2).max()) <= 2e-2)
     nb, _ = ctx.forward_batch([5, 6], [8, 40])                                                  # batched decode step, 2 sequences
-    print(f"[sanitize_run] {mode}: parity {'ok' if good else 'MISMATCH'}; graph={g}; launches so far {ctx.launch_count()}", flush=True)
+    print(f"[sanitize_run] LNB_ENGINE={which} {mode}: parity {'ok' if good else 'MISMATCH'}; graph={g}; launches so far {ctx.launch_count()}", flush=True)
     ok = ok and good
     ctx.close(); osess.close(); o2.close()
 # op-level entry points (generic kernels)
