@@ -569,7 +569,9 @@ def run_prefill(a):
     clocks = sampler.summary()
     launches = ctx.launch_count() - l0
     per = wall / a.steps
-    flops = 2 * 6_979_321_856 * S - 2 * 128256 * 4096 * (S - 1) + 2 * 2 * 32 * 128 * S * S // 2 * 32 // 32 * 32
+    # algorithmic flops of what this call computes: every projection for all S rows, the LM head for the last row only,
+    # causal attention (QK^T and PV over the S(S+1)/2 visible (query, key) pairs of 32 heads x 32 layers, 128 MACs each)
+    flops = 2 * 6_979_321_856 * S + 2 * 128256 * 4096 + 32 * 32 * (S * (S + 1) // 2) * 128 * 2 * 2
     parity = None
     if a.parity and env.rank == 0:
         om, _, _, _ = cpu_oracle_setup()

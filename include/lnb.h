@@ -261,7 +261,7 @@ int lnb_session_set_layer_limit(lnb_session* s, int n_layers_to_run); /* <=0: al
  * tells why).  LNB_ENGINE=1 / 0 forces the choice; the default is the engine except for single-GPU LNB_ACC_FAST. */
 int lnb_session_decode_engine(lnb_session* s);
 /* profiling aid of the persistent decode engine (LNB_ENGINE_PROF=1 when the session first decodes): cycles of consumer
- * thread 0 per section, {mean, max} over the CTAs, reset on read.  out[16]. */
+ * thread 0 per section, {mean, max} over the CTAs, reset on read.  out[24]. */
 int lnb_session_engine_profile(lnb_session* s, double* out16);
 /* number of kernels launched by this session since creation (bench.py gpu_launches) */
 int64_t lnb_session_launch_count(lnb_session* s);
@@ -289,7 +289,8 @@ int lnb_op_rmsnorm_bf16(const uint16_t* x, const uint16_t* w, uint16_t* out, int
  * r[s] = f32(1 / sqrt(f64( (sequential fp32 sum_k x[s,k]^2) / D + eps ))), bit-exact.
  * algo: 0 = what the model path uses (env LNB_RMS_ALGO=chain|scan|seg overrides the built-in choice),
  * 1 = one-thread FADD chain, 2 = iterative binade scan, 3 = one-pass predict / fold / walk
- * (csrc/seqsum.cuh; 2 and 3 return LNB_EINVAL when D does not fit their shape).  Identical bits. */
+ * (csrc/seqsum.cuh; 2 and 3 return LNB_EINVAL when D does not fit their shape), 4 = the variant that runs inside the
+ * persistent decode engine (256 threads, runs folded per warp; csrc/engine.cuh).  Identical bits. */
 int lnb_op_rms_scale_f32(const uint16_t* x, float* r, int S, int D, float eps, int algo);
 /* applyRotaryEmbeddings for one tensor (llamatransformer.go:753-790): x[S,H,hd] */
 int lnb_op_rope_bf16(const uint16_t* x, const float* cis, uint16_t* out, int S, int H, int hd, int start_pos);

@@ -914,7 +914,7 @@ static int launch_simple(const Launcher& L, void (*kern)(Args...), dim3 grid, di
 // interchangeable kernels, identical bits: 1 = one-thread FADD chain (rms_scale_kernel), 2 = iterative binade
 // scan, 3 = one-pass predict / fold / walk (both seqsum.cuh; need a row length that fits seq_scan_shape).
 // algo 0 = the model path's choice: LNB_RMS_ALGO=chain|scan|seg, else kRmsDefaultAlgo.
-enum { RMS_AUTO = 0, RMS_CHAIN = 1, RMS_SCAN = 2, RMS_SEG = 3 };
+enum { RMS_AUTO = 0, RMS_CHAIN = 1, RMS_SCAN = 2, RMS_SEG = 3, RMS_ENGINE = 4 };   // 4 = the decode engine's in-CTA variant (engine.cuh)
 static const int kRmsDefaultAlgo = RMS_SEG;  // measured: 209 tok/s vs 195 (chain) vs 171 (iterative scan), STRICT 8B decode
 static int rms_default_algo() {
   static const int a = [] {
@@ -2310,7 +2310,7 @@ extern "C" int lnb_session_decode_engine(lnb_session* s) {
   g_err = s->eng_state < 0 ? s->eng_why : std::string("tensor-parallel session without the peer all-reduce (NCCL collectives cannot run inside a kernel)");
   return 0;
 }
-extern "C" int lnb_session_engine_profile(lnb_session* s, double* out16) {
+extern "C" int lnb_session_engine_profile(lnb_session* s, double* out16) {   // (out: 2 * ENG_NPROF doubles)
   if (!s || !out16) return fail(LNB_EINVAL, "NULL argument");
   if (!s->d_prof) return fail(LNB_ESTATE, "no engine profile (set LNB_ENGINE_PROF=1 before the session's first decode)");
   CU(cudaSetDevice(s->m->device));
@@ -2519,7 +2519,29 @@ extern "C" int lnb_op_rms_scale_f32(const uint16_t* x, float* r, int S, int D, f
   OpScope scope_;
   if (!x || !r) return fail(LNB_EINVAL, "NULL argument");
   if (S <= 0 || D <= 0 || (D & 1)) return fail(LNB_EINVAL, "bad shape");
-  if (algo < RMS_AUTO || algo > RMS_SEG) return fail(LNB_EINVAL, "bad algo %d", algo);
+  if (algo < RMS_AUTO || algo > RMS_ENGINE) return fail(LNB_EINVAL, "bad algo %d", algo);
+  if (algo == RMS_ENGINE) {
+    int ech = 0, ent = 0;
+    if (!eng_scan_shape(D, &ech, &ent) || (size_t)D * 4 + 4096 > 200 * 1024) return fail(LNB_EINVAL, "row length %d does not fit the engine's scan", D);
+    const size_t xb2 = (size_t)S * D * 2;
+    OPBUF(dx2, xb2); OPBUF(dr2, (size_t)S * 4);
+    H2D(dx2, x, xb2);
+    const size_t smem = (size_t)D * 4 + 4096;
+    switch (ech) {
+      case 16: CU(cudaFuncSetAttribute(eng_rms_scale_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+               eng_rms_scale_kernel<16><<<S, ENG_NCONS, smem>>>(dx2.as<uint16_t>(), D, dr2.as<float>(), D, eps); break;
+      case 8: CU(cudaFuncSetAttribute(eng_rms_scale_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              eng_rms_scale_kernel<8><<<S, ENG_NCONS, smem>>>(dx2.as<uint16_t>(), D, dr2.as<float>(), D, eps); break;
+      case 4: CU(cudaFuncSetAttribute(eng_rms_scale_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              eng_rms_scale_kernel<4><<<S, ENG_NCONS, smem>>>(dx2.as<uint16_t>(), D, dr2.as<float>(), D, eps); break;
+      default: CU(cudaFuncSetAttribute(eng_rms_scale_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+               eng_rms_scale_kernel<2><<<S, ENG_NCONS, smem>>>(dx2.as<uint16_t>(), D, dr2.as<float>(), D, eps); break;
+    }
+    int rc2 = op_finish();
+    if (rc2) return rc2;
+    D2H(r, dr2, (size_t)S * 4);
+    return 0;
+  }
   int ch, nt;
   const bool fits = seq_scan_shape(D, &ch, &nt);
   if ((algo == RMS_SCAN || algo == RMS_SEG) && !fits) return fail(LNB_EINVAL, "row length %d does not fit the scan kernels", D);

@@ -100,7 +100,7 @@ constexpr int ENG_WORK = 84 * 1024;
 constexpr int ENG_XMAX = 56 * 1024;                       // f32 activation vector: K <= 14336
 constexpr int ENG_PART_OFF = ENG_XMAX;                    // [8][64] f32 stream partials (FAST), 2 KB
 constexpr int ENG_SCAN_OFF = ENG_XMAX + 2048;             // seg-scan scratch (STRICT RMSNorm), 4 KB
-constexpr int ENG_NPROF = 8;                              // per-CTA cycle counters (LNB_ENGINE_PROF): see EngineParams.prof
+constexpr int ENG_NPROF = 12;                              // per-CTA cycle counters (LNB_ENGINE_PROF): see EngineParams.prof
 constexpr int ENG_SMEM = 1024 + ENG_RING + ENG_WORK;
 template <int KS> struct EngCfg {
   static constexpr int kNST = 4;
@@ -207,16 +207,13 @@ LNB_DEVINL uint2 eng_wait_word(const EngineParams& P, const uint2* src, uint32_t
 // consumers of an engine CTA.  s_x = the row as f32 in shared memory (D = NT * CH elements); threads t >= NT only
 // take part in the barriers.  Returns the reference's sequential fp32 sum (valid on every thread via *s_out).
 template <int CH>
-LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch, float* s_out) {
+LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch, float* s_out, unsigned long long* prof = nullptr) {
+  long long tp0 = (prof && t == 0) ? clock64() : 0;   // profile slots 7 (squares, prediction, maps, warp scan), 9 (walk)
   uint32_t* s_run_i0 = reinterpret_cast<uint32_t*>(scratch);            // [256]
   uint32_t* s_run_i1 = s_run_i0 + 256;                                   // [256]
   uint16_t* s_run_end = reinterpret_cast<uint16_t*>(s_run_i1 + 256);     // [256]
   uint8_t* s_code = reinterpret_cast<uint8_t*>(s_run_end + 256);         // [256]
   float* s_wsum = reinterpret_cast<float*>(s_code + 256);                // [8]
-  uint32_t* s_wflag = reinterpret_cast<uint32_t*>(s_wsum + 8);           // [8] x 4
-  uint32_t* s_whead = s_wflag + 8;
-  uint32_t* s_wi0 = s_whead + 8;
-  uint32_t* s_wi1 = s_wi0 + 8;
   const int lane = t & 31, wid = t >> 5, nw = NT >> 5;
   const bool on = t < NT;
   float sq[CH];
@@ -250,12 +247,8 @@ LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch,
     s_run_end[t] = 0;
   }
   named_bar_sync(1, ENG_NCONS);
-  int code = 0, pc = 0, nc = 0;
-  SeqSeg v;
-  v.m.i0 = v.m.i1 = 0u;
-  v.flag = 1u;
-  v.head = (uint32_t)t;
   if (on) {
+    // approximate prefix sums (any rounding will do: they only PREDICT the binade of every chunk)
     float wpre = 0.f;
     {
       float wv = (lane < nw) ? s_wsum[lane] : 0.f;
@@ -271,20 +264,19 @@ LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch,
     if (lane == 0) before = 0.f;
     before = __fadd_rn(before, wpre);
     const float after = __fadd_rn(inc, wpre);
-    code = (t == 0) ? 0 : seq_predict(before, after);
+    const int code = (t == 0) ? 0 : seq_predict(before, after);
     s_code[t] = (uint8_t)code;
+    SeqSeg v;
+    v.m.i0 = v.m.i1 = 0u;
     if (code) {
 #pragma unroll
       for (int k = 0; k < CH; k++) v.m = seq_compose(v.m, seq_term(__float_as_uint(sq[k]), code));
     }
-    pc = __shfl_up_sync(0xffffffffu, code, 1);
-    nc = __shfl_down_sync(0xffffffffu, code, 1);
-  }
-  named_bar_sync(1, ENG_NCONS);
-  if (on) {
-    if (lane == 0) pc = t ? (int)s_code[t - 1] : 0;
-    if (lane == 31) nc = (t + 1 < NT) ? (int)s_code[t + 1] : 0;
-    v.flag = (code == 0 || pc != code) ? 1u : 0u;
+    // runs of equally predicted chunks, folded into one parity map per run -- WITHIN the warp only: a run that crosses a
+    // warp boundary is published as two runs (the walk takes one more jump; the cross-warp scan and two barriers are gone)
+    const int pc = __shfl_up_sync(0xffffffffu, code, 1), nc = __shfl_down_sync(0xffffffffu, code, 1);
+    v.flag = (code == 0 || pc != code || lane == 0) ? 1u : 0u;   // uncertain chunks are runs of their own (never jumped)
+    v.head = (uint32_t)t;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       SeqSeg o;
@@ -294,38 +286,14 @@ LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch,
       o.m.i1 = __shfl_up_sync(0xffffffffu, v.m.i1, d);
       if (lane >= d) v = seq_seg_op(o, v);
     }
-    if (lane == 31) { s_wflag[wid] = v.flag; s_whead[wid] = v.head; s_wi0[wid] = v.m.i0; s_wi1[wid] = v.m.i1; }
-  }
-  named_bar_sync(1, ENG_NCONS);
-  if (on) {
-    SeqSeg a;
-    a.flag = (lane < nw) ? s_wflag[lane] : 1u;
-    a.head = (lane < nw) ? s_whead[lane] : 0u;
-    a.m.i0 = (lane < nw) ? s_wi0[lane] : 0u;
-    a.m.i1 = (lane < nw) ? s_wi1[lane] : 0u;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      SeqSeg o;
-      o.flag = __shfl_up_sync(0xffffffffu, a.flag, d);
-      o.head = __shfl_up_sync(0xffffffffu, a.head, d);
-      o.m.i0 = __shfl_up_sync(0xffffffffu, a.m.i0, d);
-      o.m.i1 = __shfl_up_sync(0xffffffffu, a.m.i1, d);
-      if (lane >= d) a = seq_seg_op(o, a);
-    }
-    SeqSeg p;
-    const int src = (wid + 31) & 31;
-    p.flag = __shfl_sync(0xffffffffu, a.flag, src);
-    p.head = __shfl_sync(0xffffffffu, a.head, src);
-    p.m.i0 = __shfl_sync(0xffffffffu, a.m.i0, src);
-    p.m.i1 = __shfl_sync(0xffffffffu, a.m.i1, src);
-    if (wid > 0) v = seq_seg_op(p, v);
-    if (code && nc != code) {                        // last chunk of a run: publish the run at its head
+    if (code && (nc != code || lane == 31)) {        // last chunk of a run: publish the run at its head
       s_run_end[v.head] = (uint16_t)(t + 1);
       s_run_i0[v.head] = v.m.i0;
       s_run_i1[v.head] = v.m.i1;
     }
   }
   named_bar_sync(1, ENG_NCONS);
+  if (prof && t == 0) { const long long n_ = clock64(); prof[7] += (unsigned long long)(n_ - tp0); tp0 = n_; }
   if (t == 0) {                                      // the walk: jump over runs, real FADDs everywhere else
     uint32_t sb = 0u;
     int cidx = 0;
@@ -346,6 +314,7 @@ LNB_DEVINL void eng_seq_sumsq(const float* s_x, int t, int NT, uint8_t* scratch,
       cidx++;
     }
     *s_out = __uint_as_float(sb);
+    if (prof) { const long long n_ = clock64(); prof[9] += (unsigned long long)(n_ - tp0); prof[10] += 1ull; }
   }
   named_bar_sync(1, ENG_NCONS);
 }
@@ -431,6 +400,24 @@ LNB_DEVINL void l2_prefetch_bulk(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
+// The engine's scan as a kernel of its own (op-level C-ABI, algo 4): one row per CTA, 256 threads -- lets the adversarial-row
+// tests of the standalone scan kernels (zeros, subnormals, binade crossings, inf) run against this variant too.
+template <int CH>
+__global__ void __launch_bounds__(ENG_NCONS) eng_rms_scale_kernel(const uint16_t* __restrict__ x, int ldx, float* __restrict__ r, int D, float eps) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* s_x = reinterpret_cast<float*>(sm);
+  uint8_t* scr = sm + (size_t)D * 4;
+  __shared__ float s_sum;
+  const int t = threadIdx.x;
+  for (int k = t; k < D; k += ENG_NCONS) s_x[k] = bf2f(x[(size_t)blockIdx.x * ldx + k]);
+  named_bar_sync(1, ENG_NCONS);
+  eng_seq_sumsq<CH>(s_x, t, D / CH, scr, &s_sum);
+  if (t == 0) {
+    const float me = __fadd_rn(__fdiv_rn(s_sum, (float)D), eps);
+    r[blockIdx.x] = (float)(1.0 / sqrt((double)me));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 template <int KS>
 __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const EngineParams P) {
@@ -453,7 +440,7 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
   if (tid == 0) {
     for (int s = 0; s < NST; s++) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], Cfg::kChainWarps);
+      mbar_init(&empty_bar[s], Cfg::kChainWarps * 32);
     }
     mbar_fence_init();
     ctl->ld_bytes = 0ull;
@@ -651,11 +638,12 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
               eng_scan_shape(K, &ch, &nt);
               uint8_t* scr = s_work + ENG_SCAN_OFF;
               float* s_sum = s_scalar + 4;
+              unsigned long long* pr = P.prof ? P.prof + (size_t)bid * ENG_NPROF : nullptr;
               switch (ch) {
-                case 16: eng_seq_sumsq<16>(s_x, c, nt, scr, s_sum); break;
-                case 8: eng_seq_sumsq<8>(s_x, c, nt, scr, s_sum); break;
-                case 4: eng_seq_sumsq<4>(s_x, c, nt, scr, s_sum); break;
-                default: eng_seq_sumsq<2>(s_x, c, nt, scr, s_sum); break;
+                case 16: eng_seq_sumsq<16>(s_x, c, nt, scr, s_sum, pr); break;
+                case 8: eng_seq_sumsq<8>(s_x, c, nt, scr, s_sum, pr); break;
+                case 4: eng_seq_sumsq<4>(s_x, c, nt, scr, s_sum, pr); break;
+                default: eng_seq_sumsq<2>(s_x, c, nt, scr, s_sum, pr); break;
               }
               if (c == 0) {
                 const float me = __fadd_rn(__fdiv_rn(*s_sum, (float)K), P.eps);
@@ -704,7 +692,9 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
                 eng_mbar_wait(&full_bar[s], par, P.err_host, P.timeout_ns, !warp_on, seq);
                 const int k0 = t * kt;
                 const int nchunks = min(kt, K - k0) / 8;
-                const uint8_t* tile0 = s_ring + (size_t)s * STAGE + (size_t)pp0 * ((size_t)kt * 16) + rr * 16;
+                // (rows without a panel in this tile read the stage's panel 0 -- data this thread has synchronised with -- and
+                //  are never stored: `valid` is false for them)
+                const uint8_t* tile0 = s_ring + (size_t)s * STAGE + (on0 ? (size_t)pp0 * ((size_t)kt * 16) : (size_t)0) + rr * 16;
                 const float* xt = s_x + k0;
                 if (KS == 1) {
                   if (on0) {
@@ -727,32 +717,39 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
                     }
                   }
                 } else {
-                  // FAST: stream j owns the chunks ch = j, j + 8, ...; two rows (two independent chains) per thread.
-                  // Rows beyond the tile's panels read whatever the stage holds (finite or not, it is never stored:
-                  // `valid` is false for them) -- unconditional loads keep the loop free of predicates -- and the next
-                  // chunk's operands are loaded before the current chunk's 16 FMAs issue.
-                  const uint8_t* tile1 = tile0 + 4 * ((size_t)kt * 16);   // (within shared memory for every kt <= 512)
-#ifdef ENG_FAST_SIMPLE
-#pragma unroll 4
-                  for (int ch = j; ch < nchunks; ch += KS) {
-                    const float4 xa = *reinterpret_cast<const float4*>(xt + ch * 8);
-                    const float4 xb = *reinterpret_cast<const float4*>(xt + ch * 8 + 4);
-                    uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
-                    if (on0) w0 = *reinterpret_cast<const uint4*>(tile0 + ch * 128);
-                    if (on1) w1 = *reinterpret_cast<const uint4*>(tile1 + ch * 128);
-                    float a = acc0, b = acc1;
-                    a = __fmaf_rn(xa.x, bf_lo(w0.x), a); b = __fmaf_rn(xa.x, bf_lo(w1.x), b);
-                    a = __fmaf_rn(xa.y, bf_hi(w0.x), a); b = __fmaf_rn(xa.y, bf_hi(w1.x), b);
-                    a = __fmaf_rn(xa.z, bf_lo(w0.y), a); b = __fmaf_rn(xa.z, bf_lo(w1.y), b);
-                    a = __fmaf_rn(xa.w, bf_hi(w0.y), a); b = __fmaf_rn(xa.w, bf_hi(w1.y), b);
-                    a = __fmaf_rn(xb.x, bf_lo(w0.z), a); b = __fmaf_rn(xb.x, bf_lo(w1.z), b);
-                    a = __fmaf_rn(xb.y, bf_hi(w0.z), a); b = __fmaf_rn(xb.y, bf_hi(w1.z), b);
-                    a = __fmaf_rn(xb.z, bf_lo(w0.w), a); b = __fmaf_rn(xb.z, bf_lo(w1.w), b);
-                    a = __fmaf_rn(xb.w, bf_hi(w0.w), a); b = __fmaf_rn(xb.w, bf_hi(w1.w), b);
-                    acc0 = a; acc1 = b;
-                  }
-#else
-                  {
+                  // FAST: stream j owns the chunks ch = j, j + 8, ...
+                  // Row tiles with <= 4 panels (wo, w2, the tail tile of the others) have no second row at all: one chain per
+                  // thread.  Otherwise two independent chains; a row without a panel reads the stage's panel 0 (data this thread
+                  // has synchronised with -- never memory a bulk copy may be writing) and is not stored (`valid` is false).
+                  // The next chunk's operands are loaded before the current chunk's FMAs issue.
+                  if (np <= 4) {
+                    int ch = j;
+                    float4 xa, xb;
+                    uint4 w0;
+                    if (ch < nchunks) {
+                      xa = *reinterpret_cast<const float4*>(xt + ch * 8);
+                      xb = *reinterpret_cast<const float4*>(xt + ch * 8 + 4);
+                      w0 = *reinterpret_cast<const uint4*>(tile0 + ch * 128);
+                    }
+#pragma unroll 2
+                    for (; ch < nchunks; ch += KS) {
+                      const float4 ca = xa, cb = xb;
+                      const uint4 c0 = w0;
+                      const int nx = ch + KS;
+                      if (nx < nchunks) {
+                        xa = *reinterpret_cast<const float4*>(xt + nx * 8);
+                        xb = *reinterpret_cast<const float4*>(xt + nx * 8 + 4);
+                        w0 = *reinterpret_cast<const uint4*>(tile0 + nx * 128);
+                      }
+                      float a = acc0;
+                      a = __fmaf_rn(ca.x, bf_lo(c0.x), a); a = __fmaf_rn(ca.y, bf_hi(c0.x), a);
+                      a = __fmaf_rn(ca.z, bf_lo(c0.y), a); a = __fmaf_rn(ca.w, bf_hi(c0.y), a);
+                      a = __fmaf_rn(cb.x, bf_lo(c0.z), a); a = __fmaf_rn(cb.y, bf_hi(c0.z), a);
+                      a = __fmaf_rn(cb.z, bf_lo(c0.w), a); a = __fmaf_rn(cb.w, bf_hi(c0.w), a);
+                      acc0 = a;
+                    }
+                  } else {
+                    const uint8_t* tile1 = s_ring + (size_t)s * STAGE + (on1 ? (size_t)pp1 * ((size_t)kt * 16) : (size_t)0) + rr * 16;
                     int ch = j;
                     float4 xa, xb;
                     uint4 w0, w1;
@@ -785,10 +782,11 @@ __global__ void __launch_bounds__(ENG_THREADS, 1) decode_engine_kernel(const Eng
                       acc0 = a; acc1 = b;
                     }
                   }
-#endif
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                // every lane releases the stage it read.  (One elected lane after a warp barrier is formally enough -- release
+                // is cumulative over what the barrier ordered before it -- but compute-sanitizer's racecheck does not follow
+                // that edge and reports the next bulk copy into the stage as a WAR hazard against the other lanes' reads.)
+                mbar_arrive(&empty_bar[s]);
               }
               if (P.prof && c == 0) { const long long t_now = clock64(); P.prof[bid * ENG_NPROF + 2] += (unsigned long long)(t_now - t_mark); t_mark = t_now; }
               // ---- combine the KS streams in stream order, then the fused epilogue -------------------------------

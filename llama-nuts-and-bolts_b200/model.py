@@ -246,9 +246,10 @@ class InferenceContext:
 
     def engine_profile(self):
         """LNB_ENGINE_PROF=1: {section: (mean cycles, max cycles)} of the decode engine's consumer thread 0 since the last call"""
-        out = (C.c_double * 16)()
+        out = (C.c_double * 24)()
         check(lib.lnb_session_engine_profile(self.h, out))
-        names = ["grid_barrier", "prologue", "main_loop", "epilogue", "attention", "peer_reduce", "input_wait"]
+        names = ["grid_barrier", "prologue", "main_loop", "epilogue", "attention", "peer_reduce", "input_wait", "scan_maps", "scan_scans",
+                 "scan_walk", "scan_count"]
         return {n: (out[2 * i], out[2 * i + 1]) for i, n in enumerate(names)}
 
     def disable_peer_allreduce(self):

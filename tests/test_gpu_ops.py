@@ -127,7 +127,9 @@ def test_rms_scale_scan_and_chain_bit_exact(L, D):
     x[-1] = 0                                   # all-zero row: 1/sqrt(eps)
     exp = O.rms_scale(x, 1e-5)
     c = L._capi
-    for algo in (3, 2, 1, 0):
+    for algo in (4, 3, 2, 1, 0):                # 4 = the decode engine's in-CTA variant (warp-local runs, csrc/engine.cuh)
+        if algo == 4 and D > 4096:
+            continue                            # 256 threads x 16 squares
         r = np.empty(S, np.float32)
         c.check(c.lib.lnb_op_rms_scale_f32(c.ptr(x, c.u16p), c.ptr(r, c.f32p), S, D, 1e-5, algo))
         assert np.array_equal(r.view(np.uint32), exp.view(np.uint32)), (algo, np.nonzero(r != exp))

@@ -18,7 +18,7 @@ names = {0: "wqkv", 1: "wo", 2: "w13", 3: "w2", 4: "lm_head"}
 def show(tag, prof, n):
     parts = []
     for k, (mean, mx) in prof.items():
-        if mx > 0:
+        if mx > 0 and k != "scan_count":
             parts.append(f"{k} {mean / n / MHZ:6.2f}/{mx / n / MHZ:6.2f}")
     print(f"  {tag:>10s} us per unit (mean/max over CTAs): " + " | ".join(parts), flush=True)
 
