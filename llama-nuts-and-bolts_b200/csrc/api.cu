@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "seqsum.cuh"
 #include "engine.cuh"
+#include "engine_batch.cuh"
 #include "pth.hpp"
 #include "tokenizer.hpp"
 
@@ -1061,10 +1062,18 @@ struct lnb_session {
   // tagged activation vectors of the engine ({tag:16 | bf16:16} words): residual stream x, post-attention stream h1,
   // q|k|v of the step, attention output o, FFN hidden m
   uint32_t *x_t = nullptr, *h1_t = nullptr, *qkv_t = nullptr, *o_t = nullptr, *m_t = nullptr;
+  // batch engine (engine_batch.cuh): chunk-major bf16 activations [K/8][8][8] of up to 8 sequences, its phase list, argmax keys
+  uint16_t *bx = nullptr, *bh1 = nullptr, *bq = nullptr, *bo = nullptr, *bm = nullptr;
+  BatchPhase* d_bphases = nullptr;
+  int n_bphases = 0;
+  unsigned long long* d_bkeys = nullptr;
+  int bkey_layers = -1;
+  const float* bkey_logits = nullptr;
   uint32_t eng_tag = 1;          // next free tag (tags of one launch: [eng_tag, eng_tag + n_steps * n_phases))
   bool last_was_engine = false;  // the residual stream of the last forward lives in x_t
   unsigned long long* d_prof = nullptr;   // LNB_ENGINE_PROF=1: per-CTA cycle counters of the engine's consumer thread 0
   int eng_state = 0;             // 0 = not probed, 1 = usable, -1 = this session uses the kernel chain
+  bool eng_single_default = true; // single-sequence S=1 steps use the engine (false: single-GPU FAST, where the kernel chain is faster)
   std::string eng_why;           // why not
   int eng_key_seq = -1, eng_key_layers = -1, eng_key_kind = -2;
   const float* eng_key_logits = nullptr;
@@ -1168,6 +1177,7 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   cudaFree(s->p2p_region);
   cudaFree(s->d_phases); cudaFree(s->d_bar); cudaFree(s->d_prof);
   cudaFree(s->x_t); cudaFree(s->h1_t); cudaFree(s->qkv_t); cudaFree(s->o_t); cudaFree(s->m_t);
+  cudaFree(s->bx); cudaFree(s->bh1); cudaFree(s->bq); cudaFree(s->bo); cudaFree(s->bm); cudaFree(s->d_bphases); cudaFree(s->d_bkeys);
   cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out); cudaFree(s->d_pos_arr); cudaFree(s->d_next_arr);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
@@ -1335,7 +1345,8 @@ static bool engine_probe(lnb_session* s) {
   // default except for single-GPU FAST sessions; LNB_ENGINE=1 / 0 forces it on / off.
   const char* e = getenv("LNB_ENGINE");
   if (e && !strcmp(e, "0")) return no("LNB_ENGINE=0");
-  if (!(e && !strcmp(e, "1")) && s->mode == LNB_ACC_FAST && m->tp_size == 1) return no("single-GPU FAST: the kernel chain is the default");
+  // single-sequence steps of single-GPU FAST sessions stay on the kernel chain by default (the batch engine does not care)
+  s->eng_single_default = (e && !strcmp(e, "1")) || !(s->mode == LNB_ACC_FAST && m->tp_size == 1);
   const int kmax = std::max(a.dim, std::max(m->q_l, m->ffn_l));
   if ((size_t)kmax * 4 > (size_t)ENG_XMAX) return no("activation vector exceeds the engine's shared-memory work area");
   if (a.dim % 8 || m->q_l % 8 || m->ffn_l % 8) return no("widths must be multiples of 8");
@@ -1378,7 +1389,8 @@ static bool engine_probe(lnb_session* s) {
   return true;
 }
 // the engine needs the peer all-reduce under tensor parallelism (NCCL calls cannot be issued from inside a kernel)
-static bool engine_ok(lnb_session* s) { return engine_probe(s) && (s->m->tp_size == 1 || s->p2p_ready); }
+static bool engine_capable(lnb_session* s) { return engine_probe(s) && (s->m->tp_size == 1 || s->p2p_ready); }
+static bool engine_ok(lnb_session* s) { return engine_capable(s) && s->eng_single_default; }
 
 static int eng_kt(int mode, int N, int K, int G) {
   const int per = (N / 8 + G - 1) / G;                      // most panels one CTA owns
@@ -1572,6 +1584,132 @@ static int engine_fault(lnb_session* s, cudaError_t e) {
   if ((c >> 28) == 0xDu) return fail(LNB_ECUDA, "decode engine: weight stage %u never completed (%s)", c & 0xffffffu, cudaGetErrorString(e));
   if ((c >> 28) == 0xEu) return fail(LNB_ECUDA, "decode engine: the activations tagged %u never arrived (%s)", c & 0xffffu, cudaGetErrorString(e));
   return fail(LNB_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
+}
+
+// ---- batch engine (engine_batch.cuh): one launch advances all sequences of a batched session by one token -------------------
+static bool batch_engine_ok(lnb_session* s) {
+  if (s->n_seq < 2 || !engine_capable(s)) return false;
+  const lnb_model_args& a = s->m->a;
+  if ((size_t)a.dim * 4 > 16 * 1024) return false;                      // norm weights as f32 in 16 KB of shared memory
+  const char* e = getenv("LNB_BATCH_ENGINE");
+  if (e && !strcmp(e, "0")) return false;
+  return true;
+}
+static int batch_engine_build(lnb_session* s, const float* logits_out) {
+  lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  const int n_layers = (s->layer_limit > 0 && s->layer_limit < a.n_layers) ? s->layer_limit : a.n_layers;
+  if (s->d_bphases && s->bkey_layers == n_layers && s->bkey_logits == logits_out) return 0;
+  if (!s->bx) {
+    cudaError_t e = cudaMalloc((void**)&s->bx, (size_t)a.dim * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->bh1, (size_t)a.dim * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->bq, (size_t)m->q_l * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->bo, (size_t)m->q_l * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->bm, (size_t)m->ffn_l * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_bkeys, 64);
+    if (e != cudaSuccess) return fail(LNB_ENOMEM, "batch engine buffers: %s", cudaGetErrorString(e));
+    CU(cudaMemset(s->bx, 0, (size_t)a.dim * 16)); CU(cudaMemset(s->bh1, 0, (size_t)a.dim * 16));
+    CU(cudaMemset(s->bq, 0, (size_t)m->q_l * 16)); CU(cudaMemset(s->bo, 0, (size_t)m->q_l * 16));
+    CU(cudaMemset(s->bm, 0, (size_t)m->ffn_l * 16));
+    if (s->mode == LNB_ACC_STRICT) CU(cudaFuncSetAttribute(batch_engine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENG_SMEM));
+    else CU(cudaFuncSetAttribute(batch_engine_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENG_SMEM));
+  }
+  const int G = m->sm_count, mode = s->mode;
+  const bool tp = m->tp_size > 1;
+  std::vector<BatchPhase> ph;
+  auto gemv = [&](int pro, int epi, const uint16_t* W, int N, int K, const uint16_t* x, const uint16_t* norm_w, uint16_t* out, int ldo,
+                  const uint16_t* res) {
+    BatchPhase e{};
+    e.type = BP_GEMV; e.pro = pro; e.epi = epi; e.W = W; e.N = N; e.K = K; e.kt = eng_kt(mode, N, K, G); e.x = x;
+    e.norm_w = norm_w; e.out = out; e.ldo = ldo; e.res = res;
+    return e;
+  };
+  auto scale = [&](const uint16_t* x, bool from_token) {
+    BatchPhase e{};
+    e.type = BP_SCALE; e.K = a.dim; e.x = x; e.out = s->bx; e.flags = from_token ? EF_X_TOKEN : 0;
+    return e;
+  };
+  auto reduce = [&](const uint16_t* res, uint16_t* out) {
+    BatchPhase e{};
+    e.type = BP_REDUCE; e.res = res; e.out = out;
+    return e;
+  };
+  for (int l = 0; l < n_layers; l++) {
+    LayerW& W = m->layers[l];
+    ph.push_back(scale(s->bx, l == 0));
+    {
+      BatchPhase e = gemv(PRO_RMSNORM, EPI_QKV_ROPE, W.wqkv, m->q_l + 2 * m->kv_l, a.dim, s->bx, W.attn_norm, s->bq, m->q_l, nullptr);
+      e.q_dim = m->q_l; e.kv_dim = m->kv_l; e.cache_k = s->ck[l]; e.cache_v = s->cv[l];
+      ph.push_back(e);
+    }
+    {
+      BatchPhase e{};
+      e.type = BP_SDPA; e.x = s->bq; e.out = s->bo; e.q_dim = m->q_l; e.kv_dim = m->kv_l; e.cache_k = s->ck[l]; e.cache_v = s->cv[l];
+      ph.push_back(e);
+    }
+    ph.push_back(gemv(PRO_PLAIN, tp ? EPI_P2P : EPI_RESID, W.wo, a.dim, m->q_l, s->bo, nullptr, s->bh1, a.dim, s->bx));
+    if (tp) ph.push_back(reduce(s->bx, s->bh1));
+    ph.push_back(scale(s->bh1, false));
+    ph.push_back(gemv(PRO_RMSNORM, EPI_SWIGLU, W.w13, 2 * m->ffn_l, a.dim, s->bh1, W.ffn_norm, s->bm, m->ffn_l, nullptr));
+    ph.push_back(gemv(PRO_PLAIN, tp ? EPI_P2P : EPI_RESID, W.w2, a.dim, m->ffn_l, s->bm, nullptr, s->bx, a.dim, s->bh1));
+    if (tp) ph.push_back(reduce(s->bh1, s->bx));
+  }
+  ph.push_back(scale(s->bx, n_layers == 0));
+  {
+    BatchPhase e = gemv(PRO_RMSNORM, EPI_LOGITS, m->output, m->vocab_l, a.dim, s->bx, m->norm, nullptr, m->vocab_l, nullptr);
+    e.out_f32 = const_cast<float*>(logits_out); e.n_offset = m->tp_rank * m->vocab_l;
+    ph.push_back(e);
+  }
+  {
+    BatchPhase e{};
+    e.type = BP_TOKENS;
+    ph.push_back(e);
+  }
+  cudaFree(s->d_bphases);
+  s->d_bphases = nullptr;
+  CU(cudaMalloc((void**)&s->d_bphases, ph.size() * sizeof(BatchPhase)));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaMemcpy(s->d_bphases, ph.data(), ph.size() * sizeof(BatchPhase), cudaMemcpyHostToDevice));
+  s->n_bphases = (int)ph.size();
+  s->bkey_layers = n_layers; s->bkey_logits = logits_out;
+  return 0;
+}
+// tokens / positions of the n sequences are already in s->d_tokens / s->d_pos_arr
+static int batch_engine_launch(lnb_session* s, int n) {
+  lnb_model* m = s->m;
+  const lnb_model_args& a = m->a;
+  BatchParams P{};
+  P.phases = s->d_bphases; P.n_phases = s->n_bphases; P.n = n; P.st = s->st;
+  P.emb = m->tok_embd; P.dim = a.dim; P.head_dim = a.head_dim; P.n_rep = a.n_heads / a.n_kv_heads; P.seq_len = s->seq_len;
+  P.cis = m->cis; P.silu_tab = m->silu_tab; P.eps = a.norm_eps; P.attn_scale = attn_scale_bf16(a.head_dim);
+  P.strict = s->mode == LNB_ACC_STRICT ? 1 : 0;
+  P.tokens = s->d_tokens; P.pos_arr = s->d_pos_arr; P.cache_seq_stride = (long long)s->seq_len * m->kv_l;
+  P.rscale = s->rs; P.keys = s->d_bkeys; P.next_arr = s->d_next_arr; P.bar_ctr = s->d_bar;
+  P.p2p = s->p2p; P.tp = m->tp_size;
+  P.timeout_ns = s->p2p.timeout_ns ? s->p2p.timeout_ns : 1500000000ull;
+  {
+    const char* e = getenv("LNB_P2P_TIMEOUT_MS");
+    if (e) P.timeout_ns = atol(e) > 0 ? (unsigned long long)atol(e) * 1000000ull : 0ull;
+  }
+  P.err_host = s->h_err;
+  *s->h_err = 0;
+  CU(cudaMemsetAsync(s->d_bar, 0, 4, s->stream));
+  CU(cudaMemsetAsync(s->d_bkeys, 0, 64, s->stream));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(m->sm_count);
+  cfg.blockDim = dim3(ENG_THREADS);
+  cfg.dynamicSmemBytes = ENG_SMEM;
+  cfg.stream = s->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (s->mode == LNB_ACC_STRICT) CU(cudaLaunchKernelEx(&cfg, batch_engine_kernel<1>, P));
+  else CU(cudaLaunchKernelEx(&cfg, batch_engine_kernel<8>, P));
+  s->launches++;
+  s->last_was_engine = false;
+  return 0;
 }
 
 static int sync_stream(lnb_session* s) {
@@ -2097,10 +2235,20 @@ extern "C" int lnb_forward_batch(lnb_session* s, const int32_t* tokens, const in
   memcpy(ppin, positions, (size_t)n * 4);
   CU(cudaMemcpyAsync(s->d_tokens, s->h_pin, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->d_pos_arr, ppin, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
-  set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, 0, n, -1, 0);
-  s->launches++;
-  rc = enqueue_forward(s, n, false, n > 1 ? n : 2, false, true, true);
-  if (rc) return rc;
+  if (batch_engine_ok(s)) {
+    // ONE launch of the batch engine: every weight matrix streamed once for all n sequences
+    if ((rc = batch_engine_build(s, logits ? s->logits : nullptr))) return rc;
+    if ((rc = batch_engine_launch(s, n))) return rc;
+    if (logits && m->tp_size > 1)
+      for (int r = 0; r < n; r++)
+        NC(g_nccl.AllGather(s->logits + (size_t)r * m->vocab_l, s->logits_full + (size_t)r * m->a.vocab_size, m->vocab_l, ncclFloat32_,
+                            m->comm, s->stream));
+  } else {
+    set_state_kernel<<<1, 1, 0, s->stream>>>(s->st, 0, n, -1, 0);
+    s->launches++;
+    rc = enqueue_forward(s, n, false, n > 1 ? n : 2, false, true, true);
+    if (rc) return rc;
+  }
   if (logits) {
     const float* src = (m->tp_size > 1) ? s->logits_full : s->logits;
     CU(cudaMemcpyAsync(logits, src, (size_t)n * m->a.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -2108,8 +2256,7 @@ extern "C" int lnb_forward_batch(lnb_session* s, const int32_t* tokens, const in
   int32_t* npin = s->h_pin + s->max_rows + 16;
   if (argmax_out) CU(cudaMemcpyAsync(npin, s->d_next_arr, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
   if ((rc = p2p_err_enqueue(s))) return rc;
-  CU(cudaStreamSynchronize(s->stream));
-  CU(cudaGetLastError());
+  if ((rc = sync_stream(s))) return rc;
   if ((rc = p2p_err_check(s))) return rc;
   if (argmax_out) memcpy(argmax_out, npin, (size_t)n * 4);
   return 0;
@@ -2307,7 +2454,7 @@ extern "C" int lnb_session_decode_engine(lnb_session* s) {
   std::lock_guard<std::mutex> lk(s->mu);
   CU(cudaSetDevice(s->m->device));
   if (engine_ok(s)) return 1;
-  g_err = s->eng_state < 0 ? s->eng_why : std::string("tensor-parallel session without the peer all-reduce (NCCL collectives cannot run inside a kernel)");
+  g_err = s->eng_state < 0 ? s->eng_why : !s->eng_single_default ? std::string("single-GPU FAST: the kernel chain is the default") : std::string("tensor-parallel session without the peer all-reduce (NCCL collectives cannot run inside a kernel)");
   return 0;
 }
 extern "C" int lnb_session_engine_profile(lnb_session* s, double* out16) {   // (out: 2 * ENG_NPROF doubles)

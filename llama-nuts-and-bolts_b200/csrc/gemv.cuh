@@ -77,6 +77,8 @@ struct GemvParams {
   uint32_t ar_epoch_override;  // EPI_P2P inside the persistent engine: the epoch is tracked per CTA, not in st (0: use st)
   // persistent engine only: activations travel between phases as self-validating words {tag:16 | bf16:16} (engine.cuh)
   unsigned long long* amax_key_ptr;  // EPI_LOGITS: the argmax key to maximise (NULL: &st->amax_key)
+  unsigned long long* amax_keys_row; // batch engine: one key per activation row (every row is the last row of its own sequence)
+  int cm;                  // batch engine: bf16 activations are CHUNK-MAJOR [K/8][8 rows][8]: element (row m, col n) at cm_idx(m, n)
   uint32_t* out_t;         // tagged output vector (NULL: plain bf16 output)
   uint32_t tag_hi;         // this phase's tag << 16
   const uint32_t* res_t;   // tagged residual vector (NULL: plain `res`)
@@ -102,6 +104,10 @@ struct GemvCfg {
     return b;
   }
 };
+
+// chunk-major activation layout of the batch engine: 8 sequences' values of one 8-element k-chunk are 128 contiguous bytes, so
+// the k-range of a k-tile is ONE contiguous block for all rows (engine_batch.cuh)
+LNB_DEVINL size_t cm_idx(int m, int n) { return ((((size_t)(n >> 3)) * 8 + (size_t)m) << 3) + (size_t)(n & 7); }
 
 // one word of a tagged activation vector, as soon as its producer has stored it (bounded: a word that never comes is a
 // bug or a dead SM -> trap, never a hang)
@@ -135,17 +141,25 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
   } else if (EPI == EPI_RESID) {
     if (valid) {
       float a = trunc_bf(v);
-      float rsd = p.res_t ? __uint_as_float(wait_tagged_word(p.res_t + n, p.res_tag_hi) << 16) : bf2f(p.res[(size_t)em * p.ldo + n]);
+      const size_t oi = p.cm ? cm_idx(p.m_off + em, n) : (size_t)em * p.ldo + n;
+      float rsd = p.res_t ? __uint_as_float(wait_tagged_word(p.res_t + n, p.res_tag_hi) << 16) : bf2f(p.res[oi]);
       const uint16_t o = f2bf(__fadd_rn(rsd, a));
       if (p.out_t) p.out_t[n] = p.tag_hi | o;
-      else p.out_bf16[(size_t)em * p.ldo + n] = o;
+      else p.out_bf16[oi] = o;
     }
   } else if (EPI == EPI_LOGITS) {
     float lv = trunc_bf(v);
     if (valid && p.out_f32) p.out_f32[(size_t)em * p.ldo + n] = lv;
     unsigned long long key = LNB_ARGMAX_EMPTY;
-    if (valid && em == p.argmax_row && lv > -3.402823466e+38f) key = argmax_key(lv, (uint32_t)(n + p.n_offset));
-    if (p.st) {
+    if (valid && (em == p.argmax_row || p.amax_keys_row) && lv > -3.402823466e+38f) key = argmax_key(lv, (uint32_t)(n + p.n_offset));
+    if (p.amax_keys_row) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+      }
+      if (lane == 0 && key != LNB_ARGMAX_EMPTY) atomicMax(&p.amax_keys_row[p.m_off + em], key);
+    } else if (p.st) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
@@ -178,7 +192,7 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
           o = (float)(a * dd + b * cc);
         }
         if (p.out_t) p.out_t[n] = p.tag_hi | f2bf(o);                   // engine: q, and this step's k row for the attention phase
-        if (n < p.q_dim) { if (!p.out_t) p.out_bf16[(size_t)em * p.ldo + n] = f2bf(o); }
+        if (n < p.q_dim) { if (!p.out_t) p.out_bf16[p.cm ? cm_idx(p.m_off + em, n) : (size_t)em * p.ldo + n] = f2bf(o); }
         else ck[(size_t)pos * p.kv_dim + nn] = f2bf(o);                  // SetSlice :402
       } else {
         if (p.out_t) p.out_t[n] = p.tag_hi | f2bf(mine);
@@ -194,8 +208,9 @@ LNB_DEVINL void gemv_epilogue(const GemvParams& p, float v, int n, int em, bool 
     if (valid && (er & 4) == 0) {
       const uint16_t sg = p.silu_tab[f2bf(mine)];                       // t(TABLE_SILU[bits]) activations.go:38
       const float mm = __fmul_rn(bf2f(sg), up);                         // MultiplyElementwise :614
-      if (p.out_t) p.out_t[(size_t)panel * 4 + (er & 3)] = p.tag_hi | f2bf(mm);
-      else p.out_bf16[(size_t)em * p.ldo + (size_t)panel * 4 + (er & 3)] = f2bf(mm);
+      const int col = panel * 4 + (er & 3);
+      if (p.out_t) p.out_t[col] = p.tag_hi | f2bf(mm);
+      else p.out_bf16[p.cm ? cm_idx(p.m_off + em, col) : (size_t)em * p.ldo + col] = f2bf(mm);
     }
   }
 }
