@@ -1063,7 +1063,8 @@ struct lnb_session {
   // q|k|v of the step, attention output o, FFN hidden m
   uint32_t *x_t = nullptr, *h1_t = nullptr, *qkv_t = nullptr, *o_t = nullptr, *m_t = nullptr;
   // batch engine (engine_batch.cuh): chunk-major bf16 activations [K/8][8][8] of up to 8 sequences, its phase list, argmax keys
-  uint16_t *bx = nullptr, *bh1 = nullptr, *bq = nullptr, *bo = nullptr, *bm = nullptr;
+  uint16_t *bx = nullptr, *bh1 = nullptr, *bq = nullptr, *bo = nullptr, *bm = nullptr, *bxn = nullptr;
+  int batch_tc = 0;     // FAST batch engine: projections on the tensor cores (batch_engine_kernel<0>)
   BatchPhase* d_bphases = nullptr;
   int n_bphases = 0;
   unsigned long long* d_bkeys = nullptr;
@@ -1177,7 +1178,7 @@ extern "C" int lnb_session_destroy(lnb_session* s) {
   cudaFree(s->p2p_region);
   cudaFree(s->d_phases); cudaFree(s->d_bar); cudaFree(s->d_prof);
   cudaFree(s->x_t); cudaFree(s->h1_t); cudaFree(s->qkv_t); cudaFree(s->o_t); cudaFree(s->m_t);
-  cudaFree(s->bx); cudaFree(s->bh1); cudaFree(s->bq); cudaFree(s->bo); cudaFree(s->bm); cudaFree(s->d_bphases); cudaFree(s->d_bkeys);
+  cudaFree(s->bx); cudaFree(s->bh1); cudaFree(s->bq); cudaFree(s->bo); cudaFree(s->bm); cudaFree(s->bxn); cudaFree(s->d_bphases); cudaFree(s->d_bkeys);
   cudaFree(s->logits); cudaFree(s->logits_full); cudaFree(s->d_tokens); cudaFree(s->st); cudaFree(s->d_tok_out); cudaFree(s->d_pos_arr); cudaFree(s->d_next_arr);
   for (auto p : s->ck) cudaFree(p);
   for (auto p : s->cv) cudaFree(p);
@@ -1607,26 +1608,44 @@ static int batch_engine_build(lnb_session* s, const float* logits_out) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->bo, (size_t)m->q_l * 16);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->bm, (size_t)m->ffn_l * 16);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_bkeys, 64);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->bxn, (size_t)a.dim * 16);
     if (e != cudaSuccess) return fail(LNB_ENOMEM, "batch engine buffers: %s", cudaGetErrorString(e));
     CU(cudaMemset(s->bx, 0, (size_t)a.dim * 16)); CU(cudaMemset(s->bh1, 0, (size_t)a.dim * 16));
     CU(cudaMemset(s->bq, 0, (size_t)m->q_l * 16)); CU(cudaMemset(s->bo, 0, (size_t)m->q_l * 16));
-    CU(cudaMemset(s->bm, 0, (size_t)m->ffn_l * 16));
+    CU(cudaMemset(s->bm, 0, (size_t)m->ffn_l * 16)); CU(cudaMemset(s->bxn, 0, (size_t)a.dim * 16));
+    // FAST: the tensor-core form (every K a multiple of 16; LNB_BATCH_TC=0 keeps the FMA-pipe kernel)
+    {
+      const char* e2 = getenv("LNB_BATCH_TC");
+      s->batch_tc = s->mode != LNB_ACC_STRICT && !(e2 && !strcmp(e2, "0")) && a.dim % 16 == 0 && m->q_l % 16 == 0 && m->ffn_l % 16 == 0;
+    }
     if (s->mode == LNB_ACC_STRICT) CU(cudaFuncSetAttribute(batch_engine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENG_SMEM));
+    else if (s->batch_tc) CU(cudaFuncSetAttribute(batch_engine_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     else CU(cudaFuncSetAttribute(batch_engine_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENG_SMEM));
   }
   const int G = m->sm_count, mode = s->mode;
   const bool tp = m->tp_size > 1;
+  const bool tc = s->batch_tc != 0;
   std::vector<BatchPhase> ph;
   auto gemv = [&](int pro, int epi, const uint16_t* W, int N, int K, const uint16_t* x, const uint16_t* norm_w, uint16_t* out, int ldo,
                   const uint16_t* res) {
     BatchPhase e{};
     e.type = BP_GEMV; e.pro = pro; e.epi = epi; e.W = W; e.N = N; e.K = K; e.kt = eng_kt(mode, N, K, G); e.x = x;
     e.norm_w = norm_w; e.out = out; e.ldo = ldo; e.res = res;
+    if (tc) {
+      // tensor-core form: 128-row tiles; the k-tile grows as the CTA's share of the rows shrinks (about 32 KB per stage,
+      // copies of 2 .. 8 KB); RMSNorm happened in the SCALE phase (x = the normalised row)
+      const int per = std::max(1, std::min(16, (N / 8 + G - 1) / G));
+      int kt = BT_KT_MAX;
+      while (kt > 128 && per * kt * 16 > EngCfg<1>::kStage) kt >>= 1;
+      e.kt = std::min(kt, K);
+      if (pro == PRO_RMSNORM) { e.pro = PRO_PLAIN; e.x = s->bxn; e.norm_w = nullptr; }
+    }
     return e;
   };
-  auto scale = [&](const uint16_t* x, bool from_token) {
+  auto scale = [&](const uint16_t* x, bool from_token, const uint16_t* norm_w) {
     BatchPhase e{};
     e.type = BP_SCALE; e.K = a.dim; e.x = x; e.out = s->bx; e.flags = from_token ? EF_X_TOKEN : 0;
+    if (tc) { e.norm_w = norm_w; e.xn = s->bxn; }
     return e;
   };
   auto reduce = [&](const uint16_t* res, uint16_t* out) {
@@ -1636,7 +1655,7 @@ static int batch_engine_build(lnb_session* s, const float* logits_out) {
   };
   for (int l = 0; l < n_layers; l++) {
     LayerW& W = m->layers[l];
-    ph.push_back(scale(s->bx, l == 0));
+    ph.push_back(scale(s->bx, l == 0, W.attn_norm));
     {
       BatchPhase e = gemv(PRO_RMSNORM, EPI_QKV_ROPE, W.wqkv, m->q_l + 2 * m->kv_l, a.dim, s->bx, W.attn_norm, s->bq, m->q_l, nullptr);
       e.q_dim = m->q_l; e.kv_dim = m->kv_l; e.cache_k = s->ck[l]; e.cache_v = s->cv[l];
@@ -1649,12 +1668,12 @@ static int batch_engine_build(lnb_session* s, const float* logits_out) {
     }
     ph.push_back(gemv(PRO_PLAIN, tp ? EPI_P2P : EPI_RESID, W.wo, a.dim, m->q_l, s->bo, nullptr, s->bh1, a.dim, s->bx));
     if (tp) ph.push_back(reduce(s->bx, s->bh1));
-    ph.push_back(scale(s->bh1, false));
+    ph.push_back(scale(s->bh1, false, W.ffn_norm));
     ph.push_back(gemv(PRO_RMSNORM, EPI_SWIGLU, W.w13, 2 * m->ffn_l, a.dim, s->bh1, W.ffn_norm, s->bm, m->ffn_l, nullptr));
     ph.push_back(gemv(PRO_PLAIN, tp ? EPI_P2P : EPI_RESID, W.w2, a.dim, m->ffn_l, s->bm, nullptr, s->bx, a.dim, s->bh1));
     if (tp) ph.push_back(reduce(s->bh1, s->bx));
   }
-  ph.push_back(scale(s->bx, n_layers == 0));
+  ph.push_back(scale(s->bx, n_layers == 0, m->norm));
   {
     BatchPhase e = gemv(PRO_RMSNORM, EPI_LOGITS, m->output, m->vocab_l, a.dim, s->bx, m->norm, nullptr, m->vocab_l, nullptr);
     e.out_f32 = const_cast<float*>(logits_out); e.n_offset = m->tp_rank * m->vocab_l;
@@ -1692,13 +1711,14 @@ static int batch_engine_launch(lnb_session* s, int n) {
     if (e) P.timeout_ns = atol(e) > 0 ? (unsigned long long)atol(e) * 1000000ull : 0ull;
   }
   P.err_host = s->h_err;
+  P.prof = s->d_prof;
   *s->h_err = 0;
   CU(cudaMemsetAsync(s->d_bar, 0, 4, s->stream));
   CU(cudaMemsetAsync(s->d_bkeys, 0, 64, s->stream));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(m->sm_count);
   cfg.blockDim = dim3(ENG_THREADS);
-  cfg.dynamicSmemBytes = ENG_SMEM;
+  cfg.dynamicSmemBytes = s->batch_tc ? BT_SMEM : ENG_SMEM;
   cfg.stream = s->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeCooperative;
@@ -1706,6 +1726,7 @@ static int batch_engine_launch(lnb_session* s, int n) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (s->mode == LNB_ACC_STRICT) CU(cudaLaunchKernelEx(&cfg, batch_engine_kernel<1>, P));
+  else if (s->batch_tc) CU(cudaLaunchKernelEx(&cfg, batch_engine_kernel<0>, P));
   else CU(cudaLaunchKernelEx(&cfg, batch_engine_kernel<8>, P));
   s->launches++;
   s->last_was_engine = false;

@@ -86,6 +86,13 @@ LNB_DEVINL void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, 
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of the (converged) warp, chosen by the hardware: ptxas then knows a single lane issues the tcgen05 instructions
+// under this predicate and moves their operands to uniform registers once, without a loop over possibly distinct values
+LNB_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0u;
+}
 #ifndef LNB_TC_A_IN_TMEM
 #define LNB_TC_A_IN_TMEM 0
 #endif
@@ -153,30 +160,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
-      for (int t = 0; t < n_kt; t++) {
-        const int s = t % TC_NS;
-        mbar_wait(&full_bar[s], ((uint32_t)(t / TC_NS)) & 1u);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + (size_t)s * TC_A_STAGE);
-        const uint32_t b_base = smem_u32(sB + (size_t)s * TC_B_STAGE);
+    // the whole warp runs the loop, one elected lane issues: the operands are then warp-uniform for ptxas and sit in uniform
+    // registers (from a `lane == 0` branch every MMA was preceded by a loop of R2UR transfers, ~120 cycles -- twice the
+    // 64 cycles a 128 x 128 x 16 MMA occupies the tensor pipe)
+    const bool lead = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+    for (int t = 0; t < n_kt; t++) {
+      const int s = t % TC_NS;
+      mbar_wait(&full_bar[s], ((uint32_t)(t / TC_NS)) & 1u);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA + (size_t)s * TC_A_STAGE);
+      const uint32_t b_base = smem_u32(sB + (size_t)s * TC_B_STAGE);
+      uint64_t a_desc = umma_desc(a_base, 128, TC_KT * 16);  // SBO = 16 chunks * 128 B; next k16 step = +256 B = +16 in the address field
+      uint64_t b_desc = umma_desc(b_base, 128, TC_KT * 16);
 #pragma unroll
-        for (int k16 = 0; k16 < TC_KT / 16; k16++) {
-          const uint64_t a_desc = umma_desc(a_base + k16 * 256, 128, TC_KT * 16);  // SBO = 16 chunks * 128 B
-          const uint64_t b_desc = umma_desc(b_base + k16 * 256, 128, TC_KT * 16);
+      for (int k16 = 0; k16 < TC_KT / 16; k16++) {
 #if LNB_TC_A_IN_TMEM
-          const uint32_t a_tmem = tmem_base + 128 + (uint32_t)(k16 & 1) * 8;   // 8 columns = 16 bf16 per lane, double-buffered
+        const uint32_t a_tmem = tmem_base + 128 + (uint32_t)(k16 & 1) * 8;   // 8 columns = 16 bf16 per lane, double-buffered
+        if (lead) {
           tmem_cp_128x256b(a_tmem, a_desc);
           umma_bf16_ts(tmem_base, a_tmem, b_desc, idesc, (t > 0 || k16 > 0) ? 1u : 0u);
-#else
-          umma_bf16(tmem_base, a_desc, b_desc, idesc, (t > 0 || k16 > 0) ? 1u : 0u);   // 128 x 128 x 16 per instruction
-#endif
         }
-        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+#else
+        if (lead) umma_bf16(tmem_base, a_desc, b_desc, idesc, (t > 0 || k16 > 0) ? 1u : 0u);   // 128 x 128 x 16 per instruction
+#endif
+        a_desc += 16; b_desc += 16;
       }
-      umma_commit(acc_bar);
+      if (lead) umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
     }
+    if (lead) umma_commit(acc_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global ================================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access

@@ -244,12 +244,16 @@ class InferenceContext:
         """True: S=1 steps of this context run as the persistent decode engine (one launch per decode_run / Forward)"""
         return bool(check(lib.lnb_session_decode_engine(self.h)))
 
-    def engine_profile(self):
-        """LNB_ENGINE_PROF=1: {section: (mean cycles, max cycles)} of the decode engine's consumer thread 0 since the last call"""
+    def engine_profile(self, batch=False):
+        """LNB_ENGINE_PROF=1: {section: (mean cycles, max cycles)} of the decode engine's consumer thread 0 since the last call
+        (batch=True: the sections of the batch engine, engine_batch.cuh BatchParams.prof)"""
         out = (C.c_double * 24)()
         check(lib.lnb_session_engine_profile(self.h, out))
         names = ["grid_barrier", "prologue", "main_loop", "epilogue", "attention", "peer_reduce", "input_wait", "scan_maps", "scan_scans",
                  "scan_walk", "scan_count"]
+        if batch:
+            names = ["grid_barrier", "setup", "x_tile|mma:acc_wait", "stage_wait", "fma|mma:w_wait", "epilogue", "scale", "attention", "other",
+                     "tiles", "mma:x_wait", "mma:issue"]
         return {n: (out[2 * i], out[2 * i + 1]) for i, n in enumerate(names)}
 
     def disable_peer_allreduce(self):
