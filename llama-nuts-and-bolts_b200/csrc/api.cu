@@ -17,6 +17,7 @@
 
 #include "../../include/lnb.h"
 #include "gemm_tc.cuh"
+#include "sdpa_tc.cuh"
 #include "gemv.cuh"
 #include "kernels.cuh"
 #include "seqsum.cuh"
@@ -1104,6 +1105,7 @@ static int session_create_impl(lnb_model* m, int seq_len, int max_rows, int acc_
   CU(cudaSetDevice(m->device));
   CU(cudaFuncSetAttribute(sdpa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute(sdpa_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+  CU(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
   lnb_session* s = new lnb_session();
   s->m = m;
   s->seq_len = seq_len;
@@ -1393,6 +1395,11 @@ static bool engine_probe(lnb_session* s) {
 static bool engine_capable(lnb_session* s) { return engine_probe(s) && (s->m->tp_size == 1 || s->p2p_ready); }
 static bool engine_ok(lnb_session* s) { return engine_capable(s) && s->eng_single_default; }
 
+// LNB_ACC_FAST prompt attention on the tensor cores (sdpa_tc.cuh); LNB_SDPA_TC=0 keeps the FMA-pipe tile kernel
+static bool sdpa_tc_enabled() {
+  const char* e = getenv("LNB_SDPA_TC");
+  return !(e && !strcmp(e, "0"));
+}
 static int eng_kt(int mode, int N, int K, int G) {
   const int per = (N / 8 + G - 1) / G;                      // most panels one CTA owns
   const int PT = mode == LNB_ACC_STRICT ? EngCfg<1>::kPT : EngCfg<8>::kPT;
@@ -1948,7 +1955,12 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows, bool gathe
     if ((rc = launch_simple(L, rope_kv_kernel, dim3(ew_grid), dim3(256), 0, (const uint16_t*)s->qkv_raw, qkv_n, s->q, m->q_l, m->kv_l,
                             a.head_dim, s->ck[l] + tc_cache_off, s->cv[l] + tc_cache_off, (const float*)m->cis, pos_ptr, S)))
       return rc;
-    if (a.head_dim == SP_HD) {
+    if (a.head_dim == SP_HD && sdpa_tc_enabled()) {
+      if ((rc = launch_simple(L, sdpa_tc_kernel, dim3(m->q_l / a.head_dim, (S + 127) / 128), dim3(256), (size_t)ST_SMEM,
+                              (const uint16_t*)s->q, m->q_l, (const uint16_t*)(s->ck[l] + tc_cache_off),
+                              (const uint16_t*)(s->cv[l] + tc_cache_off), m->kv_l, a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale)))
+        return rc;
+    } else if (a.head_dim == SP_HD) {
       if ((rc = launch_simple(L, sdpa_prefill_kernel, dim3(m->q_l / a.head_dim, (S + SP_QB - 1) / SP_QB), dim3(256), (size_t)SP_SMEM,
                               (const uint16_t*)s->q, m->q_l, (const uint16_t*)(s->ck[l] + tc_cache_off),
                               (const uint16_t*)(s->cv[l] + tc_cache_off), m->kv_l, a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale)))
@@ -2762,10 +2774,17 @@ extern "C" int lnb_op_attention_bf16(const uint16_t* q, const uint16_t* cache_k,
     const int Mpad = (S + 127) / 128 * 128;
     OPBUF(d8, (size_t)Mpad * n_heads * hd * 2); OPBUF(dpos, 16);
     CU(cudaMemset(dpos.p, 0, 16));
-    CU(cudaFuncSetAttribute(sdpa_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-    sdpa_prefill_kernel<<<dim3(n_heads, (S + SP_QB - 1) / SP_QB), 256, SP_SMEM>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(),
-                                                                                  dv.as<uint16_t>(), n_kv * hd, n_heads / n_kv,
-                                                                                  d8.as<uint16_t>(), n_heads * hd, dpos.as<int32_t>(), S, f);
+    if (sdpa_tc_enabled() && S >= 32) {
+      CU(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+      sdpa_tc_kernel<<<dim3(n_heads, (S + 127) / 128), 256, ST_SMEM>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(), dv.as<uint16_t>(),
+                                                                       n_kv * hd, n_heads / n_kv, d8.as<uint16_t>(), n_heads * hd,
+                                                                       dpos.as<int32_t>(), S, f);
+    } else {
+      CU(cudaFuncSetAttribute(sdpa_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+      sdpa_prefill_kernel<<<dim3(n_heads, (S + SP_QB - 1) / SP_QB), 256, SP_SMEM>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(),
+                                                                                    dv.as<uint16_t>(), n_kv * hd, n_heads / n_kv,
+                                                                                    d8.as<uint16_t>(), n_heads * hd, dpos.as<int32_t>(), S, f);
+    }
     unpack_x8_kernel<<<grid_for((int64_t)S * n_heads * hd / 8), 256>>>(d8.as<uint16_t>(), S, n_heads * hd, dout.as<uint16_t>(), n_heads * hd);
     int rc2 = op_finish();
     if (rc2) return rc2;

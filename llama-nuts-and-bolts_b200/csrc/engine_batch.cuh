@@ -99,7 +99,6 @@ constexpr int BT_X_OFF = 16 * 1024;          // 8 x 2 KB in the work area
 constexpr int BT_D_OFF = 48 * 1024;          // accumulator hand-over [2][8][129] f32
 constexpr int BT_SMEM = ENG_SMEM + 512;      // + the mbarriers of this form
 static_assert(BT_SMEM <= 227 * 1024, "shared memory per CTA");
-LNB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 LNB_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"

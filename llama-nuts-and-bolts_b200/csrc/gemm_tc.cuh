@@ -86,6 +86,9 @@ LNB_DEVINL void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, 
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// generic-proxy writes (st.shared / st.global by threads) before async-proxy reads (tcgen05.mma operands, bulk copies)
+LNB_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+LNB_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // one lane of the (converged) warp, chosen by the hardware: ptxas then knows a single lane issues the tcgen05 instructions
 // under this predicate and moves their operands to uniform registers once, without a loop over possibly distinct values
 LNB_DEVINL bool elect_one() {

@@ -1,0 +1,222 @@
+// sdpa_tc.cuh -- the attention core of a prompt call on the 5th-generation tensor cores (LNB_ACC_FAST prefill, head_dim 128).
+// Replaces, for S >= 32 rows, the scaled-dot-product block of LlamaAttention.Forward (src/model/llamatransformer.go:402-514):
+//   sc_st = t( t(sum_d q_sd * k_td) / t(sqrt(hd)) )                MatMul :459, DivToScalar :464
+//   masked entries (t > pos0 + s) contribute nothing               :471
+//   e_st = exp_f64(sc_st);  Z_s = sum_t e_st (f64);  p_st = t(f32(e_st / Z_s))     Softmax :484-495
+//   o_sd = t( sum_t p_st * v_td )                                  MatMul :504
+// Truncation points, the f64 exponentials and the f64 division are the reference's; the two inner sums (over d for the
+// scores, over t for the output) run in the tensor core's order and Z is added per thread and then across the two threads
+// of a row -- a documented reorder, which is why this kernel belongs to LNB_ACC_FAST (STRICT keeps sdpa_kernel).
+//
+// One CTA = (query head H, 128 query rows).  Per 128-key tile:
+//   S[128 x 128] = Q . K^T      8 x tcgen05.mma (128 x 128 x 16), A = Q tile, B = K tile, both K-major core-matrix tiles in
+//                               shared memory ([16 row groups][16 chunks][8 rows][8 elems], the X8 tile of gemm_tc.cuh)
+//   pass 1: every thread reads half a row of S from TMEM and adds exp_f64 of its entries (row sums Z)
+//   pass 2: S again (recomputing 8 MMAs is cheaper than keeping 2048 columns), p = t(f32(e / Z)) written as the bf16 A tile
+//           P[128 x 128 keys];  O[128 x 128] += P . V   with B = V^T staged by the threads (V rows are key-major in the
+//           cache; the transposing copy is 64 two-byte stores per thread and tile)
+// The exponentials bound the kernel (2 x 64 per thread and tile on the FP64 pipe); the MMAs are ~3 % of it.
+// 256 threads: warp w reads TMEM lane quarter w % 4 (row = 32 * (w % 4) + lane), column half w / 4.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace lnb {
+
+constexpr int ST_TILE = 128 * 128 * 2;                 // one 128 x 128 bf16 operand tile
+constexpr int ST_SMEM = 1024 + 4 * ST_TILE + 128 * 8 * 3;   // Q, K, V^T, P tiles + Z halves + Z
+
+// element (r, c) of a K-major 128 x 128 operand tile: core matrix (r / 8, c / 8) = 128 contiguous bytes
+LNB_DEVINL uint32_t st_off(int r, int c) { return (uint32_t)((((r >> 3) * 16 + (c >> 3)) * 8 + (r & 7)) * 16 + (c & 7) * 2); }
+
+__global__ void __launch_bounds__(256, 1) sdpa_tc_kernel(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ cache_k,
+                                                         const uint16_t* __restrict__ cache_v, int kv_dim, int n_rep,
+                                                         uint16_t* __restrict__ out_x8, int ldo, const int32_t* __restrict__ pos_ptr,
+                                                         int S, float scale_bf16_as_f32) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+  uint8_t* sQ = smem + 1024;
+  uint8_t* sK = sQ + ST_TILE;
+  uint8_t* sV = sK + ST_TILE;      // V^T: row = d, column = key
+  uint8_t* sP = sV + ST_TILE;
+  double* sZh = reinterpret_cast<double*>(sP + ST_TILE);   // [2][128] per column half
+  double* sZ = sZh + 256;                                  // [128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = blockIdx.x, h = H / n_rep;
+  const int qt = (int)gridDim.y - 1 - (int)blockIdx.y;     // the long (late) query tiles start first
+  const int s0 = qt * 128;
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  pdl_wait();
+  const int pos0 = *pos_ptr;
+  const int t_end = min(pos0 + S, pos0 + s0 + 128);        // keys this row block can see
+  const int n_tiles = (t_end + 127) / 128;
+  const bool lead = (warp == 0) && elect_one();
+  uint32_t mma_phase = 0;
+
+  // Q tile: 2048 pieces of 16 bytes (row r, chunk c8)
+  for (int i = tid; i < 2048; i += 256) {
+    const int r = i >> 4, c8 = i & 15;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (s0 + r < S) v = *reinterpret_cast<const uint4*>(q + (size_t)(s0 + r) * ldq + (size_t)H * 128 + c8 * 8);
+    *reinterpret_cast<uint4*>(sQ + st_off(r, c8 * 8)) = v;
+  }
+  auto load_k = [&](int tile) {
+    const int t0 = tile * 128;
+    for (int i = tid; i < 2048; i += 256) {
+      const int r = i >> 4, c8 = i & 15;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (t0 + r < t_end) v = *reinterpret_cast<const uint4*>(cache_k + (size_t)(t0 + r) * kv_dim + (size_t)h * 128 + c8 * 8);
+      *reinterpret_cast<uint4*>(sK + st_off(r, c8 * 8)) = v;
+    }
+  };
+  auto load_vt = [&](int tile) {
+    const int t0 = tile * 128;
+    for (int i = tid; i < 2048; i += 256) {
+      const int tl = i & 127, c8 = i >> 7;                 // consecutive lanes = consecutive keys
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (t0 + tl < t_end) v = *reinterpret_cast<const uint4*>(cache_v + (size_t)(t0 + tl) * kv_dim + (size_t)h * 128 + c8 * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 8; e++)
+        *reinterpret_cast<uint16_t*>(sV + st_off(c8 * 8 + e, tl)) = (uint16_t)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+    }
+  };
+  // D[128 x 128] (+)= A . B^T over the 128-wide k extent of two operand tiles
+  auto mma_tile = [&](uint32_t d_tmem, const uint8_t* a, const uint8_t* b, bool accumulate) {
+    if (lead) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+      uint64_t a_desc = umma_desc(smem_u32(a), 128, 2048);   // next chunk 128 B, next 8 rows 2048 B, next k16 step 256 B
+      uint64_t b_desc = umma_desc(smem_u32(b), 128, 2048);
+#pragma unroll
+      for (int k16 = 0; k16 < 8; k16++) {
+        umma_bf16(d_tmem, a_desc, b_desc, idesc, (accumulate || k16 > 0) ? 1u : 0u);
+        a_desc += 16; b_desc += 16;
+      }
+      umma_commit(mma_bar);
+    }
+    __syncwarp();
+  };
+  auto mma_wait = [&]() {
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+  };
+
+  const int row = (warp & 3) * 32 + lane;                  // TMEM lane = query row of the tile
+  const int half = warp >> 2;                              // columns [64 * half, 64 * half + 64)
+  const int qpos = pos0 + s0 + row;                        // keys t <= qpos are visible to this row
+  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+
+  // ---------------- pass 1: row sums of exp ------------------------------------------------------------------------
+  double z = 0.0;
+  for (int tile = 0; tile < n_tiles; tile++) {
+    load_k(tile);
+    fence_proxy_async_smem();
+    __syncthreads();
+    mma_tile(tS, sQ, sK, false);
+    mma_wait();
+    const int t0 = tile * 128 + half * 64;
+#pragma unroll 1
+    for (int cb = 0; cb < 64; cb += 16) {
+      uint32_t acc[16];
+      tmem_ld16(tS + lane_sel + (uint32_t)(half * 64 + cb), acc);
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const int t = t0 + cb + e;
+        if (t <= qpos && t < t_end) {
+          float sc = trunc_bf(__uint_as_float(acc[e]));
+          sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
+          z = __dadd_rn(z, exp((double)sc));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                       // S and the K tile are free again
+  }
+  sZh[half * 128 + row] = z;
+  __syncthreads();
+  if (tid < 128) sZ[tid] = __dadd_rn(sZh[tid], sZh[128 + tid]);
+  __syncthreads();
+  const double Z = sZ[row];
+
+  // ---------------- pass 2: p = t(f32(e / Z)), O += P . V -----------------------------------------------------------
+  for (int tile = 0; tile < n_tiles; tile++) {
+    load_k(tile);
+    load_vt(tile);
+    fence_proxy_async_smem();
+    __syncthreads();
+    mma_tile(tS, sQ, sK, false);
+    mma_wait();
+    const int t0 = tile * 128 + half * 64;
+#pragma unroll 1
+    for (int cb = 0; cb < 64; cb += 16) {
+      uint32_t acc[16];
+      tmem_ld16(tS + lane_sel + (uint32_t)(half * 64 + cb), acc);
+      uint32_t pk[8];
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        float p0 = 0.f, p1 = 0.f;
+        const int t = t0 + cb + e;
+        if (t <= qpos && t < t_end) {
+          float sc = trunc_bf(__uint_as_float(acc[e]));
+          sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
+          p0 = (float)__ddiv_rn(exp((double)sc), Z);
+        }
+        if (t + 1 <= qpos && t + 1 < t_end) {
+          float sc = trunc_bf(__uint_as_float(acc[e + 1]));
+          sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
+          p1 = (float)__ddiv_rn(exp((double)sc), Z);
+        }
+        pk[e >> 1] = (__float_as_uint(p0) >> 16) | (__float_as_uint(p1) & 0xffff0000u);
+      }
+      uint8_t* dst = sP + st_off(row, half * 64 + cb);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);          // columns cb .. cb+7 of this row
+      *reinterpret_cast<uint4*>(dst + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);    // the next chunk
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    mma_tile(tO, sP, sV, tile > 0);
+    mma_wait();                                            // P, V^T, K and S are free again
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---------------- O -> t(.) -> the X8 operand of the Wo GEMM ------------------------------------------------------
+  const int srow = s0 + row;
+#pragma unroll 1
+  for (int cb = 0; cb < 64; cb += 16) {
+    uint32_t acc[16];
+    tmem_ld16(tO + lane_sel + (uint32_t)(half * 64 + cb), acc);
+    if (srow < S) {
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        uint4 w;
+        w.x = (acc[g * 8 + 0] >> 16) | (acc[g * 8 + 1] & 0xffff0000u);
+        w.y = (acc[g * 8 + 2] >> 16) | (acc[g * 8 + 3] & 0xffff0000u);
+        w.z = (acc[g * 8 + 4] >> 16) | (acc[g * 8 + 5] & 0xffff0000u);
+        w.w = (acc[g * 8 + 6] >> 16) | (acc[g * 8 + 7] & 0xffff0000u);
+        *reinterpret_cast<uint4*>(out_x8 + x8_index(srow, H * 128 + half * 64 + cb + g * 8, ldo)) = w;   // 8 columns = one chunk
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace lnb

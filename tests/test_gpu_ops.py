@@ -185,10 +185,17 @@ def test_attention_strict_bit_exact(L, S, T, causal):
                                         S, T, nh, nkv, hd, causal, c.LNB_ACC_STRICT))
     exp = O.attention(q, ck, cv, T, causal)
     assert np.array_equal(out, exp), f"{(out != exp).sum()} of {out.size} differ"
-    # FAST only reorders the f64 softmax denominator
     c.check(c.lib.lnb_op_attention_bf16(c.ptr(q, c.u16p), c.ptr(ck, c.u16p), c.ptr(cv, c.u16p), c.ptr(out, c.u16p),
                                         S, T, nh, nkv, hd, causal, c.LNB_ACC_FAST))
-    assert bf16_ulp_diff(out, exp).max() <= 1 and (out != exp).mean() < 1e-3
+    if S >= 32 and causal:
+        # prompt-sized FAST attention runs sdpa_tc_kernel: q.k and p.v accumulate in the tensor core's order, so a score or an
+        # output can land on the other side of a bf16 truncation boundary (measured on B200: 0.05 % of the outputs differ,
+        # max-abs 0.0024 = a third of a bf16 ulp at 1.0; tools/sdpa_tc_check.py)
+        d = np.abs(O.bf16_to_f32(out).astype(np.float64) - O.bf16_to_f32(exp).astype(np.float64))
+        assert d.max() <= 2.0 ** -7 and (out != exp).mean() < 5e-3
+    else:
+        # FAST only reorders the f64 softmax denominator
+        assert bf16_ulp_diff(out, exp).max() <= 1 and (out != exp).mean() < 1e-3
 
 
 def test_attention_mask_shape_error(L):

@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+{
+echo "== sdpa_tc vs oracle"; timeout 600 python tools/sdpa_tc_check.py 70 200 513 2>&1 | tail -5
+echo "== model prefill tests"; timeout 600 python -m pytest tests/test_gpu_model.py tests/test_gpu_ops.py -q -x 2>&1 | tail -5
+echo "== prefill2048 bench"; timeout 900 python bench.py --config prefill2048 --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r2_bench_prefill2048_c.json
+} > gpurun_out/r2_sdpa.log 2>&1
+cat gpurun_out/r2_sdpa.log
