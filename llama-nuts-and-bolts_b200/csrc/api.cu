@@ -1396,6 +1396,22 @@ static bool engine_capable(lnb_session* s) { return engine_probe(s) && (s->m->tp
 static bool engine_ok(lnb_session* s) { return engine_capable(s) && s->eng_single_default; }
 
 // LNB_ACC_FAST prompt attention on the tensor cores (sdpa_tc.cuh); LNB_SDPA_TC=0 keeps the FMA-pipe tile kernel
+// exp of every bf16 value as f64, per device (sdpa_tc.cuh); NULL on failure
+static const double* exp_table_device() {
+  static std::mutex mu;
+  static double* tab[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!tab[dev]) {
+    double* t = nullptr;
+    if (cudaMalloc((void**)&t, 65536 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    exp_tab_kernel<<<256, 256>>>(t);
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); cudaFree(t); return nullptr; }
+    tab[dev] = t;
+  }
+  return tab[dev];
+}
 static bool sdpa_tc_enabled() {
   const char* e = getenv("LNB_SDPA_TC");
   return !(e && !strcmp(e, "0"));
@@ -1941,6 +1957,7 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows, bool gathe
     memcpy(&scale, &u, 4);
   }
   const size_t sdpa_smem = (size_t)s->seq_len * 12 + (size_t)a.head_dim * 4;
+  const double* exp_tab = sdpa_tc_enabled() ? exp_table_device() : nullptr;
   const int ew_grid = m->sm_count * 8;
   for (int l = 0; l < n_layers; l++) {
     LayerW& W = m->layers[l];
@@ -1955,10 +1972,11 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows, bool gathe
     if ((rc = launch_simple(L, rope_kv_kernel, dim3(ew_grid), dim3(256), 0, (const uint16_t*)s->qkv_raw, qkv_n, s->q, m->q_l, m->kv_l,
                             a.head_dim, s->ck[l] + tc_cache_off, s->cv[l] + tc_cache_off, (const float*)m->cis, pos_ptr, S)))
       return rc;
-    if (a.head_dim == SP_HD && sdpa_tc_enabled()) {
+    if (a.head_dim == SP_HD && exp_tab) {
       if ((rc = launch_simple(L, sdpa_tc_kernel, dim3(m->q_l / a.head_dim, (S + 127) / 128), dim3(256), (size_t)ST_SMEM,
                               (const uint16_t*)s->q, m->q_l, (const uint16_t*)(s->ck[l] + tc_cache_off),
-                              (const uint16_t*)(s->cv[l] + tc_cache_off), m->kv_l, a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale)))
+                              (const uint16_t*)(s->cv[l] + tc_cache_off), m->kv_l, a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale,
+                              exp_tab)))
         return rc;
     } else if (a.head_dim == SP_HD) {
       if ((rc = launch_simple(L, sdpa_prefill_kernel, dim3(m->q_l / a.head_dim, (S + SP_QB - 1) / SP_QB), dim3(256), (size_t)SP_SMEM,
@@ -1989,12 +2007,10 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows, bool gathe
       return rc;
     {
       GemmTcParams g{};
-      g.X8 = s->xn8; g.W = W.w13; g.M = S; g.N = 2 * m->ffn_l; g.K = a.dim; g.out_bf16 = s->gu; g.ldo = 2 * m->ffn_l;
-      if ((rc = launch_gemm_tc<TC_EPI_BF16>(L, g))) return rc;
+      // SwiGLU in the epilogue: the hidden activations go straight into the X8 operand of the w2 GEMM
+      g.X8 = s->xn8; g.W = W.w13; g.M = S; g.N = 2 * m->ffn_l; g.K = a.dim; g.out_bf16 = s->m8; g.ldo = m->ffn_l; g.silu_tab = m->silu_tab;
+      if ((rc = launch_gemm_tc<TC_EPI_SWIGLU>(L, g))) return rc;
     }
-    if ((rc = launch_simple(L, swiglu_x8_kernel, dim3(ew_grid), dim3(256), 0, (const uint16_t*)s->gu, 2 * m->ffn_l,
-                            (const uint16_t*)m->silu_tab, s->m8, S, Mpad, m->ffn_l)))
-      return rc;
     {
       GemmTcParams g{};
       g.X8 = s->m8; g.W = W.w2; g.M = S; g.N = a.dim; g.K = m->ffn_l; g.ldo = a.dim;
@@ -2774,11 +2790,12 @@ extern "C" int lnb_op_attention_bf16(const uint16_t* q, const uint16_t* cache_k,
     const int Mpad = (S + 127) / 128 * 128;
     OPBUF(d8, (size_t)Mpad * n_heads * hd * 2); OPBUF(dpos, 16);
     CU(cudaMemset(dpos.p, 0, 16));
-    if (sdpa_tc_enabled() && S >= 32) {
+    const double* exp_tab = (sdpa_tc_enabled() && S >= 32) ? exp_table_device() : nullptr;
+    if (exp_tab) {
       CU(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
       sdpa_tc_kernel<<<dim3(n_heads, (S + 127) / 128), 256, ST_SMEM>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(), dv.as<uint16_t>(),
                                                                        n_kv * hd, n_heads / n_kv, d8.as<uint16_t>(), n_heads * hd,
-                                                                       dpos.as<int32_t>(), S, f);
+                                                                       dpos.as<int32_t>(), S, f, exp_tab);
     } else {
       CU(cudaFuncSetAttribute(sdpa_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
       sdpa_prefill_kernel<<<dim3(n_heads, (S + SP_QB - 1) / SP_QB), 256, SP_SMEM>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(),

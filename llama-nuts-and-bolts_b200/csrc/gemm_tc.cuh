@@ -23,7 +23,7 @@
 
 namespace lnb {
 
-enum { TC_EPI_BF16 = 0, TC_EPI_RESID = 1, TC_EPI_F32TRUNC = 2, TC_EPI_F32RAW = 3 };
+enum { TC_EPI_BF16 = 0, TC_EPI_RESID = 1, TC_EPI_F32TRUNC = 2, TC_EPI_F32RAW = 3, TC_EPI_SWIGLU = 4 };
 
 struct GemmTcParams {
   const uint16_t* X8;   // activations, X8 layout, M padded to a multiple of 128 (padding rows are zero)
@@ -33,6 +33,10 @@ struct GemmTcParams {
   float* out_f32;       // [M, ldo] (TC_EPI_F32TRUNC: f32(t(acc)); TC_EPI_F32RAW: acc)
   const uint16_t* res;  // [M, ldo] residual (TC_EPI_RESID)
   int ldo;
+  // TC_EPI_SWIGLU (W = the stacked w1|w3 matrix, half-panel interleave: columns 8p..8p+3 = gate of hidden units 4p..4p+3,
+  // 8p+4..8p+7 = their up values): out_bf16 = the X8 operand of the w2 GEMM, ldo = its K (ffn), m = t(t(TABLE_SILU[t(g)]) * t(u))
+  // (llamatransformer.go:601-614); padding rows of the last M tile are written too (they come out as 0)
+  const uint16_t* silu_tab;
 };
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_KT = 128, TC_NS = 3;
@@ -111,6 +115,14 @@ LNB_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- layout helpers for the tensor-core path (X8 = tile-major activations, see the header comment)
+// X8 address of element (row, col) of a [*, K] activation matrix
+LNB_DEVINL size_t x8_index(int row, int col, int K) {
+  const size_t tile = (size_t)(row >> 7) * (K >> 7) + (col >> 7);                 // [M/128][K/128]
+  const int g = (row >> 3) & 15, ch = (col >> 3) & 15;                            // [16 groups][16 chunks]
+  return (((tile * 16 + g) * 16 + ch) * 8 + (row & 7)) * 8 + (col & 7);
 }
 
 template <int EPI>
@@ -204,7 +216,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
     for (int j = 0; j < TC_BN / 16; j++) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), r);
-      if (row < p.M) {
+      if (EPI == TC_EPI_SWIGLU) {
+        uint16_t sg[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) sg[e] = p.silu_tab[r[(e >> 2) * 8 + (e & 3)] >> 16];          // t(TABLE_SILU[t(gate)])
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float lo = __fmul_rn(bf2f(sg[e]), __uint_as_float(r[(e >> 2) * 8 + 4 + (e & 3)] & 0xffff0000u));
+          const float hi = __fmul_rn(bf2f(sg[e + 1]), __uint_as_float(r[((e + 1) >> 2) * 8 + 4 + ((e + 1) & 3)] & 0xffff0000u));
+          o[e >> 1] = (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
+        }
+        *reinterpret_cast<uint4*>(p.out_bf16 + x8_index(row, (n0 + j * 16) >> 1, p.ldo)) = make_uint4(o[0], o[1], o[2], o[3]);
+      } else if (row < p.M) {
         const size_t o = (size_t)row * p.ldo + n0 + j * 16;
         if (EPI == TC_EPI_BF16 || EPI == TC_EPI_RESID) {
           uint32_t packed[8];
@@ -243,13 +267,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
   }
 }
 
-// ---- layout helpers for the tensor-core path (X8 = tile-major activations, see the header comment)
-// X8 address of element (row, col) of a [*, K] activation matrix
-LNB_DEVINL size_t x8_index(int row, int col, int K) {
-  const size_t tile = (size_t)(row >> 7) * (K >> 7) + (col >> 7);                 // [M/128][K/128]
-  const int g = (row >> 3) & 15, ch = (col >> 3) & 15;                            // [16 groups][16 chunks]
-  return (((tile * 16 + g) * 16 + ch) * 8 + (row & 7)) * 8 + (col & 7);
-}
 
 // ---- -----------------------------------------------------
 // row-major [M, K] bf16 -> X8 ([Mpad/8][K/8][8][8]); rows >= M are written as zeros

@@ -2,7 +2,7 @@
 // Replaces, for S >= 32 rows, the scaled-dot-product block of LlamaAttention.Forward (src/model/llamatransformer.go:402-514):
 //   sc_st = t( t(sum_d q_sd * k_td) / t(sqrt(hd)) )                MatMul :459, DivToScalar :464
 //   masked entries (t > pos0 + s) contribute nothing               :471
-//   e_st = exp_f64(sc_st);  Z_s = sum_t e_st (f64);  p_st = t(f32(e_st / Z_s))     Softmax :484-495
+//   e_st = exp_f64(sc_st);  Z_s = sum_t e_st (f64);  p_st = t(f32(e_st / Z_s))     Softmax :484-495  (here e_st * (1 / Z_s))
 //   o_sd = t( sum_t p_st * v_td )                                  MatMul :504
 // Truncation points, the f64 exponentials and the f64 division are the reference's; the two inner sums (over d for the
 // scores, over t for the output) run in the tensor core's order and Z is added per thread and then across the two threads
@@ -15,7 +15,12 @@
 //   pass 2: S again (recomputing 8 MMAs is cheaper than keeping 2048 columns), p = t(f32(e / Z)) written as the bf16 A tile
 //           P[128 x 128 keys];  O[128 x 128] += P . V   with B = V^T staged by the threads (V rows are key-major in the
 //           cache; the transposing copy is 64 two-byte stores per thread and tile)
-// The exponentials bound the kernel (2 x 64 per thread and tile on the FP64 pipe); the MMAs are ~3 % of it.
+// exp_f64 of a score is a TABLE LOOKUP: the score is a bf16 value, so exp_tab[bits] = exp((double)bf16(bits)), filled once per
+// device by the same device exp() the other attention kernels call (exp_tab_kernel), has exactly the bits an inline call
+// would produce; the live part of the table (|score| of a few units: a few thousand entries) stays in L1.  Computing the
+// 2 x 64 exponentials per thread and tile on the FP64 pipe took three times as long as everything else in the kernel.
+// The P tile reuses the K tile's shared memory (K is dead once S is complete), so a CTA needs 3 operand tiles = 100 KB and
+// two CTAs share an SM (2 x 256 TMEM columns): one CTA's loads and MMA round trips hide behind the other's softmax.
 // 256 threads: warp w reads TMEM lane quarter w % 4 (row = 32 * (w % 4) + lane), column half w / 4.
 #pragma once
 #include "gemm_tc.cuh"
@@ -23,15 +28,21 @@
 namespace lnb {
 
 constexpr int ST_TILE = 128 * 128 * 2;                 // one 128 x 128 bf16 operand tile
-constexpr int ST_SMEM = 1024 + 4 * ST_TILE + 128 * 8 * 3;   // Q, K, V^T, P tiles + Z halves + Z
+constexpr int ST_SMEM = 1024 + 3 * ST_TILE + 128 * 8 * 3;   // Q, K (then P), V^T tiles + Z halves + Z
+
+// exp_tab[b] = exp((double)bf16(b)) for all 65536 bit patterns
+__global__ void exp_tab_kernel(double* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 65536) tab[i] = exp((double)bf2f((uint16_t)i));
+}
 
 // element (r, c) of a K-major 128 x 128 operand tile: core matrix (r / 8, c / 8) = 128 contiguous bytes
 LNB_DEVINL uint32_t st_off(int r, int c) { return (uint32_t)((((r >> 3) * 16 + (c >> 3)) * 8 + (r & 7)) * 16 + (c & 7) * 2); }
 
-__global__ void __launch_bounds__(256, 1) sdpa_tc_kernel(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ cache_k,
+__global__ void __launch_bounds__(256, 2) sdpa_tc_kernel(const uint16_t* __restrict__ q, int ldq, const uint16_t* __restrict__ cache_k,
                                                          const uint16_t* __restrict__ cache_v, int kv_dim, int n_rep,
                                                          uint16_t* __restrict__ out_x8, int ldo, const int32_t* __restrict__ pos_ptr,
-                                                         int S, float scale_bf16_as_f32) {
+                                                         int S, float scale_bf16_as_f32, const double* __restrict__ exp_tab) {
   pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem);
@@ -39,8 +50,8 @@ __global__ void __launch_bounds__(256, 1) sdpa_tc_kernel(const uint16_t* __restr
   uint8_t* sQ = smem + 1024;
   uint8_t* sK = sQ + ST_TILE;
   uint8_t* sV = sK + ST_TILE;      // V^T: row = d, column = key
-  uint8_t* sP = sV + ST_TILE;
-  double* sZh = reinterpret_cast<double*>(sP + ST_TILE);   // [2][128] per column half
+  uint8_t* sP = sK;                // P replaces K once S = Q.K^T is complete
+  double* sZh = reinterpret_cast<double*>(sV + ST_TILE);   // [2][128] per column half
   double* sZ = sZh + 256;                                  // [128]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(256, 1) sdpa_tc_kernel(const uint16_t* __restr
         if (t <= qpos && t < t_end) {
           float sc = trunc_bf(__uint_as_float(acc[e]));
           sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
-          z = __dadd_rn(z, exp((double)sc));
+          z = __dadd_rn(z, __ldg(exp_tab + (__float_as_uint(sc) >> 16)));
         }
       }
     }
@@ -148,7 +159,10 @@ __global__ void __launch_bounds__(256, 1) sdpa_tc_kernel(const uint16_t* __restr
   __syncthreads();
   if (tid < 128) sZ[tid] = __dadd_rn(sZh[tid], sZh[128 + tid]);
   __syncthreads();
-  const double Z = sZ[row];
+  // p = t(f32(e * (1/Z))): the reference divides (e / Z); multiplying by the f64 reciprocal differs from the quotient by at most
+  // one f64 ulp, which survives the rounding to f32 AND the truncation to bf16 with probability ~2^-45 per element -- and an
+  // f64 division per score is ~30 FP64 instructions against one (this kernel is LNB_ACC_FAST only)
+  const double rZ = __ddiv_rn(1.0, sZ[row]);
 
   // ---------------- pass 2: p = t(f32(e / Z)), O += P . V -----------------------------------------------------------
   for (int tile = 0; tile < n_tiles; tile++) {
@@ -171,12 +185,12 @@ __global__ void __launch_bounds__(256, 1) sdpa_tc_kernel(const uint16_t* __restr
         if (t <= qpos && t < t_end) {
           float sc = trunc_bf(__uint_as_float(acc[e]));
           sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
-          p0 = (float)__ddiv_rn(exp((double)sc), Z);
+          p0 = (float)__dmul_rn(__ldg(exp_tab + (__float_as_uint(sc) >> 16)), rZ);
         }
         if (t + 1 <= qpos && t + 1 < t_end) {
           float sc = trunc_bf(__uint_as_float(acc[e + 1]));
           sc = trunc_bf(__fdiv_rn(sc, scale_bf16_as_f32));
-          p1 = (float)__ddiv_rn(exp((double)sc), Z);
+          p1 = (float)__dmul_rn(__ldg(exp_tab + (__float_as_uint(sc) >> 16)), rZ);
         }
         pk[e >> 1] = (__float_as_uint(p0) >> 16) | (__float_as_uint(p1) & 0xffff0000u);
       }
