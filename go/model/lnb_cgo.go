@@ -77,6 +77,53 @@ func newDeviceSession(dm *deviceModel, inferenceArgs common.InferenceArgs, maxRo
 	return ds, lnbErr(C.lnb_session_create(dm.h, C.int(inferenceArgs.SequenceLength), C.int(maxRows), C.int(accMode), &ds.h))
 }
 
+// deviceLogits is what Forward returns when the logits stay in HBM (lnb_forward_device): ml.Tensor carries it instead of
+// S x vocab floats; Slice keeps it and ml.Argmax on such a tensor calls argmaxRows (4 bytes per row over PCIe), anything
+// that touches RawData calls read.  Valid until the session's next forward.
+type deviceLogits struct {
+	ds         *deviceSession
+	generation C.int64_t
+	rows       int
+}
+
+func (ds *deviceSession) forwardDevice(inputTokens *ml.Tensor, startPos int, allRows bool) (*deviceLogits, error) {
+	s := inputTokens.Size[0]
+	if s == 0 {
+		return nil, fmt.Errorf("empty token array")
+	}
+	d := &deviceLogits{ds: ds, rows: 1}
+	if allRows {
+		d.rows = s
+	}
+	rc := C.lnb_forward_device(ds.h, (*C.int32_t)(unsafe.Pointer(&inputTokens.RawData[0])), C.int(s), C.int(startPos), C.int(d.rows),
+		nil, &d.generation)
+	return d, lnbErr(rc)
+}
+
+func (d *deviceLogits) argmaxRows(row0, rows int) ([]int32, error) {
+	out := make([]int32, rows)
+	rc := C.lnb_session_logits_argmax(d.ds.h, d.generation, C.int(row0), C.int(rows), (*C.int32_t)(unsafe.Pointer(&out[0])))
+	return out, lnbErr(rc)
+}
+
+func (d *deviceLogits) read(row0, rows, vocab int) (*ml.Tensor, error) {
+	t := ml.NewEmptyTensor([]int{rows, vocab}, ml.DT_F32)
+	rc := C.lnb_session_logits_read(d.ds.h, d.generation, C.int(row0), C.int(rows), (*C.float)(unsafe.Pointer(&t.RawData[0])))
+	return t, lnbErr(rc)
+}
+
+// chunked prefill (extension): S > 1 at startPos > 0 with the [S,T] causal mask
+func (ds *deviceSession) allowChunkedPrefill(on bool) error {
+	v := C.int(0)
+	if on {
+		v = 1
+	}
+	return lnbErr(C.lnb_session_set_chunked_prefill(ds.h, v))
+}
+
+// after an LNB_ETIMEOUT of the peer all-reduce: back to ncclAllReduce (every rank must do the same)
+func (ds *deviceSession) disablePeerAllReduce() error { return lnbErr(C.lnb_session_p2p_disable(ds.h)) }
+
 // body of (*LlamaTransformer).Forward: tokens [S] int32 -> logits [S, vocab] f32
 func (ds *deviceSession) forward(inputTokens *ml.Tensor, startPos int, vocab int) (*ml.Tensor, error) {
 	s := inputTokens.Size[0]

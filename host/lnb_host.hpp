@@ -313,6 +313,32 @@ class InferenceContext {  // inferencecontext.go:8-46 (KV cache in HBM)
     check(lnb_forward(h_, inputTokens.data<int32_t>(), S, startPos, logits.data<float>(), 1, nullptr));
     return logits;
   }
+  // The same Forward with the logits left in HBM (lnb_forward_device): the returned handle stands for the [rowsKept, vocab]
+  // tensor; ArgmaxRows = Slice + ml.Argmax on the device (4 bytes per row back), ReadLogits = touching the tensor's data.
+  // A handle is valid until the context's next forward.
+  struct DeviceLogits { int64_t generation = 0; int rows = 0; };
+  DeviceLogits ForwardDevice(const std::vector<int32_t>& tokens, int startPos, bool allRows = false, int32_t* argmaxLast = nullptr) {
+    DeviceLogits d;
+    d.rows = allRows ? (int)tokens.size() : 1;
+    check(lnb_forward_device(h_, tokens.data(), (int)tokens.size(), startPos, d.rows, argmaxLast, &d.generation));
+    return d;
+  }
+  std::vector<int32_t> ArgmaxRows(const DeviceLogits& d, int row0, int rows) {
+    std::vector<int32_t> out((size_t)rows, -1);
+    check(lnb_session_logits_argmax(h_, d.generation, row0, rows, out.data()));
+    return out;
+  }
+  ml::Tensor ReadLogits(const DeviceLogits& d, int row0, int rows) {
+    ml::Tensor t({rows, vocab_}, ml::DataType::F32);
+    check(lnb_session_logits_read(h_, d.generation, row0, rows, t.data<float>()));
+    return t;
+  }
+  // chunked prefill (EXTENSION): allow S > 1 calls at startPos > 0 with the [S,T] causal mask
+  void AllowChunkedPrefill(bool on) { check(lnb_session_set_chunked_prefill(h_, on ? 1 : 0)); }
+  // 1 = the persistent decode engine serves this context's S=1 calls, 0 = the kernel chain
+  bool UsesDecodeEngine() { return lnb_session_decode_engine(h_) == 1; }
+  // after LNB_ETIMEOUT on the peer all-reduce: back to ncclAllReduce (every rank must do the same)
+  void DisablePeerAllReduce() { check(lnb_session_p2p_disable(h_)); }
   lnb_session* handle() { return h_; }
 
  private:
