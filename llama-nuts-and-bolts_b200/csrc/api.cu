@@ -1106,6 +1106,7 @@ static int session_create_impl(lnb_model* m, int seq_len, int max_rows, int acc_
   CU(cudaFuncSetAttribute(sdpa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute(sdpa_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
   CU(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+  CU(cudaFuncSetAttribute(sdpa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
   lnb_session* s = new lnb_session();
   s->m = m;
   s->seq_len = seq_len;
@@ -1415,6 +1416,11 @@ static const double* exp_table_device() {
 static bool sdpa_tc_enabled() {
   const char* e = getenv("LNB_SDPA_TC");
   return !(e && !strcmp(e, "0"));
+}
+// default: the software-pipelined form (sdpa_tc2_kernel); LNB_SDPA_TC=1: the serial form (sdpa_tc_kernel)
+static bool sdpa_tc_pipelined() {
+  const char* e = getenv("LNB_SDPA_TC");
+  return !(e && !strcmp(e, "1"));
 }
 static int eng_kt(int mode, int N, int K, int G) {
   const int per = (N / 8 + G - 1) / G;                      // most panels one CTA owns
@@ -1972,7 +1978,13 @@ static int enqueue_forward_tc(lnb_session* s, int S, int logits_rows, bool gathe
     if ((rc = launch_simple(L, rope_kv_kernel, dim3(ew_grid), dim3(256), 0, (const uint16_t*)s->qkv_raw, qkv_n, s->q, m->q_l, m->kv_l,
                             a.head_dim, s->ck[l] + tc_cache_off, s->cv[l] + tc_cache_off, (const float*)m->cis, pos_ptr, S)))
       return rc;
-    if (a.head_dim == SP_HD && exp_tab) {
+    if (a.head_dim == SP_HD && exp_tab && sdpa_tc_pipelined()) {
+      if ((rc = launch_simple(L, sdpa_tc2_kernel, dim3(m->q_l / a.head_dim, (S + 127) / 128), dim3(256), (size_t)SX_SMEM,
+                              (const uint16_t*)s->q, m->q_l, (const uint16_t*)(s->ck[l] + tc_cache_off),
+                              (const uint16_t*)(s->cv[l] + tc_cache_off), m->kv_l, a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale,
+                              exp_tab)))
+        return rc;
+    } else if (a.head_dim == SP_HD && exp_tab) {
       if ((rc = launch_simple(L, sdpa_tc_kernel, dim3(m->q_l / a.head_dim, (S + 127) / 128), dim3(256), (size_t)ST_SMEM,
                               (const uint16_t*)s->q, m->q_l, (const uint16_t*)(s->ck[l] + tc_cache_off),
                               (const uint16_t*)(s->cv[l] + tc_cache_off), m->kv_l, a.n_heads / a.n_kv_heads, s->o8, m->q_l, pos_ptr, S, scale,
@@ -2791,7 +2803,12 @@ extern "C" int lnb_op_attention_bf16(const uint16_t* q, const uint16_t* cache_k,
     OPBUF(d8, (size_t)Mpad * n_heads * hd * 2); OPBUF(dpos, 16);
     CU(cudaMemset(dpos.p, 0, 16));
     const double* exp_tab = (sdpa_tc_enabled() && S >= 32) ? exp_table_device() : nullptr;
-    if (exp_tab) {
+    if (exp_tab && sdpa_tc_pipelined()) {
+      CU(cudaFuncSetAttribute(sdpa_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
+      sdpa_tc2_kernel<<<dim3(n_heads, (S + 127) / 128), 256, SX_SMEM>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(), dv.as<uint16_t>(),
+                                                                        n_kv * hd, n_heads / n_kv, d8.as<uint16_t>(), n_heads * hd,
+                                                                        dpos.as<int32_t>(), S, f, exp_tab);
+    } else if (exp_tab) {
       CU(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
       sdpa_tc_kernel<<<dim3(n_heads, (S + 127) / 128), 256, ST_SMEM>>>(dq.as<uint16_t>(), n_heads * hd, dk.as<uint16_t>(), dv.as<uint16_t>(),
                                                                        n_kv * hd, n_heads / n_kv, d8.as<uint16_t>(), n_heads * hd,

@@ -50,7 +50,7 @@ out = np.empty((70, 8 * 128), np.uint16)
 c = L._capi
 c.check(c.lib.lnb_op_attention_bf16(c.ptr(q, c.u16p), c.ptr(ck, c.u16p), c.ptr(cv, c.u16p), c.ptr(out, c.u16p), 70, 70, 8, 2, 128, 1, c.LNB_ACC_FAST))
 d = np.abs(O.bf16_to_f32(out).astype(np.float64) - O.bf16_to_f32(O.attention(q, ck, cv, 70, 1)).astype(np.float64))
-print(f"[sanitize_run] sdpa_tc_kernel S=70: max-abs vs oracle {d.max():.2e}", flush=True)
+print(f"[sanitize_run] prompt attention on the tensor cores (default kernel) S=70: max-abs vs oracle {d.max():.2e}", flush=True)
 ok = ok and d.max() <= 2.0 ** -7
 # op-level entry points (generic kernels)
 x = np.arange(6, dtype=np.float32).reshape(2, 3)
