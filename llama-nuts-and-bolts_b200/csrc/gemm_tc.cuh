@@ -16,7 +16,7 @@
 //        [16 row-groups][16 k-chunks][8 rows][8 elems] = 32 KB contiguous -> ONE bulk copy per stage;
 //        LBO = 128 B (next k-chunk), SBO = 2048 B (next 8 rows).
 // One CTA computes a 128 x 128 tile: 8 accumulators of 128 lanes x 16 columns in TMEM (128 columns).
-// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator,
+// Warp roles: 0, 2, 3 = bulk-copy producers (one thread each), 1 = MMA issuer (one elected lane), 2 also allocates TMEM,
 // 4..7 = epilogue (tcgen05.ld -> truncate -> global).
 #pragma once
 #include "common.cuh"
@@ -153,9 +153,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // Three producer threads (warps 0, 2, 3): a stage is 1 + 16 bulk copies, and ONE thread needs ~50 cycles per copy -- 850
+    // cycles per stage against the 512 cycles its eight MMAs occupy the tensor pipe (ncu: tensor pipe 34 % active, L2 -> SM
+    // traffic at a third of what the SM can take: the pipe was waiting for the copy ISSUE, not for bandwidth).  Warp 0 announces
+    // the stage's bytes and copies the activation tile and 4 weight panels, warps 2 and 3 copy 6 panels each; a copy that
+    // completes before the announcement only makes the barrier's pending-byte count transiently negative.
     if (lane == 0) {
       pdl_wait();  // the activations come from the previous kernel (weights alone could go earlier)
+      const int part = (warp == 0) ? 0 : warp - 1;
+      const int j0 = (part == 0) ? 0 : (part == 1 ? 4 : 10), j1 = (part == 0) ? 4 : (part == 1 ? 10 : 16);
       const uint64_t pol_w = l2_policy_evict_first();
       const uint64_t pol_x = l2_policy_evict_last();   // every N-tile re-reads the same activations
       const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.X8);
@@ -163,13 +170,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcPara
       for (int t = 0; t < n_kt; t++) {
         const int s = t % TC_NS;
         mbar_wait(&empty_bar[s], (((uint32_t)(t / TC_NS)) & 1u) ^ 1u);
-        mbar_expect_tx(&full_bar[s], TC_A_STAGE + TC_B_STAGE);
         const size_t k0 = (size_t)t * TC_KT;
-        // A: one contiguous 128 x 128 tile of the tile-major X8 layout
-        bulk_g2s(sA + (size_t)s * TC_A_STAGE, xb + ((size_t)(m0 / TC_BM) * (p.K / TC_KT) + t) * TC_A_STAGE, TC_A_STAGE,
-                 &full_bar[s], pol_x);
+        if (part == 0) {
+          mbar_expect_tx(&full_bar[s], TC_A_STAGE + TC_B_STAGE);
+          // A: one contiguous 128 x 128 tile of the tile-major X8 layout
+          bulk_g2s(sA + (size_t)s * TC_A_STAGE, xb + ((size_t)(m0 / TC_BM) * (p.K / TC_KT) + t) * TC_A_STAGE, TC_A_STAGE,
+                   &full_bar[s], pol_x);
+        }
         // B: 16 panels of 8 rows, each (8 rows x KT) = KT*16 contiguous bytes
-        for (int j = 0; j < TC_BN / 8; j++)
+        for (int j = j0; j < j1; j++)
           bulk_g2s(sB + (size_t)s * TC_B_STAGE + (size_t)j * (TC_KT * 16),
                    wb + ((size_t)(n0 / 8 + j) * p.K + k0) * 16, TC_KT * 16, &full_bar[s], pol_w);
       }
